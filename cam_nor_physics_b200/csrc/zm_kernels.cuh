@@ -1,0 +1,361 @@
+// zm_kernels.cuh -- sm_100a CUDA kernels for the CAM-Nor Zhang-McFarlane deep-convection path.
+//
+// Design (B200-first, not a translation of the chunk-loop Fortran):
+//   * one thread per column for the trigger (buoyan_dilute + parcel_dilute): the two parcel
+//     loops of the reference (zm_conv.F90:4997-5148 and 5175-5273) are fused into ONE
+//     bottom-up sweep with all per-level state carried in registers, the only per-level
+//     storage being one buoyancy value in shared memory ([level][thread], conflict free);
+//   * trigger/gather (zm_conv.F90:905-917, 1095-1111) is an order-preserving warp-ballot
+//     compaction per chunk, so ideep/lengath are bit-identical to the serial loop, plus a
+//     device-side worklist so that later kernels run only on convective columns and the host
+//     never synchronises inside a step;
+//   * pass 2 of the dilute CAPE runs only on pass-1 triggered columns (the others are provably
+//     unchanged: their dmpdz row is untouched, zm_conv.F90:544,1053,1074);
+//   * cldprp + closure + q1q2_pjr + scatter + precipitation are one fused per-column kernel;
+//   * zm_conv_evap / momtran are thread-per-column level scans; convtran is a 2-D
+//     (gathered column x constituent) grid.
+// All arithmetic is FP64 with -fmad=false and the portable zm_math.h transcendentals, so
+// results are bit-identical to the CPU oracle built with the same math header.
+#pragma once
+#include "zm_device.cuh"
+
+#define ZM_MAXCIN 5
+
+// ---- argument blocks ----------------------------------------------------------------------
+struct ConvrIn {
+  int nchunks;
+  const int* ncol;                       // [nchunks]
+  const double *t, *qh, *pap, *paph, *dpp, *zm, *zi, *geos, *pblh, *tpert, *landfrac;
+  double delt;
+};
+struct ConvrOut {
+  double *prec, *jctop, *jcbot, *qtnd, *heat, *mcon, *cme, *cape, *eurt, *dlf, *pflx, *zdu, *rprd;
+  double *mu, *md, *du, *eu, *ed, *dp, *dsubcld;
+  int *jt, *maxg, *ideep, *lengath;
+  double *ql, *rliq, *dif, *dnlf, *dnif, *rice;
+};
+// per-column scratch (all sized ncolpad = nchunks*pcols; 2-D ones [pver][ncolpad])
+struct ConvrWork {
+  double *cape, *cin, *tl, *dmpdz;       // [ncolpad]
+  int *lcl, *lel, *mx;                   // [ncolpad]
+  double *tp, *qstp;                     // [pver][ncolpad]
+  int *wl1, *wl2;                        // worklists: pass-1 columns; final (col, slot) pairs
+  int *count;                            // [0]=n pass-1, [1]=n final, [2]=brent failures
+  double *errinfo;                       // first failure: rcall, col, p, Tfg, qt, s
+};
+
+__device__ __forceinline__ size_t cidx(int c, int k0, int i, int nlev) {
+  return ((size_t)c * nlev + k0) * P.pcols + i;      // k0 is 0-based
+}
+
+__device__ __forceinline__ void report_fail(const ConvrWork& w, int rcall, int col, double p,
+                                            double tfg, double qt, double s) {
+  int n = atomicAdd(&w.count[2], 1);
+  if (n == 0) {
+    w.errinfo[0] = rcall; w.errinfo[1] = col; w.errinfo[2] = p; w.errinfo[3] = tfg;
+    w.errinfo[4] = qt; w.errinfo[5] = s;
+  }
+}
+
+// ---- output initialisation (zm_conv.F90:559-563, 625-650, 771-784, 906) ---------------------
+__global__ void k_convr_init(ConvrIn in, ConvrOut o, ConvrWork w) {
+  const int pcols = P.pcols, pver = P.pver, pverp = P.pverp;
+  const size_t ncolpad = (size_t)in.nchunks * pcols;
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t nth = (size_t)gridDim.x * blockDim.x;
+  for (size_t e = tid; e < ncolpad * pver; e += nth) {
+    o.qtnd[e] = 0.0; o.heat[e] = 0.0; o.cme[e] = 0.0; o.eurt[e] = 0.0; o.dlf[e] = 0.0;
+    o.zdu[e] = 0.0; o.rprd[e] = 0.0; o.mu[e] = 0.0; o.md[e] = 0.0; o.du[e] = 0.0; o.eu[e] = 0.0;
+    o.ed[e] = 0.0; o.dp[e] = 0.0; o.ql[e] = 0.0; o.dif[e] = 0.0; o.dnlf[e] = 0.0; o.dnif[e] = 0.0;
+  }
+  for (size_t e = tid; e < ncolpad * pverp; e += nth) { o.mcon[e] = 0.0; o.pflx[e] = 0.0; }
+  for (size_t e = tid; e < ncolpad; e += nth) {
+    o.prec[e] = 0.0; o.rliq[e] = 0.0; o.rice[e] = 0.0; o.cape[e] = 0.0; o.dsubcld[e] = 0.0;
+    o.jctop[e] = (double)pver; o.jcbot[e] = 1.0;
+    o.jt[e] = 0; o.maxg[e] = 0; o.ideep[e] = 0;
+    w.dmpdz[e] = -P.tentrm;
+  }
+  for (size_t e = tid; e < (size_t)in.nchunks; e += nth) o.lengath[e] = 0;
+  if (tid < 3) w.count[tid] = 0;
+}
+
+// ---- buoyan_dilute + parcel_dilute, one thread per column ----------------------------------
+// zm_conv.F90:4425-4819 and 4824-5277.  PASS 1: every column.  PASS 2: worklist wl1 only.
+template <int PASS>
+__global__ void __launch_bounds__(128)
+k_buoyan_dilute(ConvrIn in, ConvrWork w) {
+  extern __shared__ double sm_buoy[];               // [pver+2][blockDim.x]
+  const int pcols = P.pcols, pver = P.pver, msg = P.msg;
+  const int ncolpad = in.nchunks * pcols;
+  const int nthr = blockDim.x;
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int col;
+  if (PASS == 1) { if (gid >= ncolpad) return; col = gid; }
+  else           { if (gid >= w.count[0]) return; col = w.wl1[gid]; }
+  const int c = col / pcols, i = col - c * pcols;
+  if (i >= in.ncol[c]) return;
+#define BUOY(k) sm_buoy[(k) * nthr + threadIdx.x]
+#define IN2(a, k) in.a[cidx(c, (k) - 1, i, pver)]
+#define IN2P(a, k) in.a[cidx(c, (k) - 1, i, pver + 1)]
+
+  const double eps1 = P.eps1, grav = P.grav, cp = P.cpres, rl = P.rl;
+  const double zs = in.geos[(size_t)c * pcols + i] * P.rgrav;
+  const double pblh = in.pblh[(size_t)c * pcols + i];
+  const double tpert = in.tpert[(size_t)c * pcols + i];
+  const double dmpdz = w.dmpdz[col];
+
+  // pblt (zm_conv.F90:839-843)
+  int pblt = pver;
+  for (int k = pver - 1; k >= msg + 1; --k) {
+    double zk = IN2(zm, k) + zs;
+    double zfk = IN2P(zi, k) + zs, zfk1 = IN2P(zi, k + 1) + zs;
+    if (fabs(zk - zs - pblh) < (zfk - zfk1) * 0.5) pblt = k;
+  }
+  const int lon = min(pver, pblt + 2);
+  int mx = lon;
+  double tl, ql, pl, zl = 0.0;
+  if (P.lparcel_pbl) {
+    // zm_conv.F90:4638-4673, 4698-4708
+    double pbl_dz = (IN2(zm, pblt) + zs) - zs;
+    double parcel_dz = fmax2(IN2P(zi, pver), P.parcel_hscale * pbl_dz);
+    double parcel_ztop = parcel_dz + zs;
+    double parcel_hdp = 0.0, parcel_qdp = 0.0, parcel_dp = 0.0;
+    int ipar = 0;
+    for (int k = pver; k >= msg + 1; --k) {
+      if (IN2P(zi, k + 1) <= parcel_dz) {
+        ipar = k;
+        double dp_zfrac;
+        if (k == pver) dp_zfrac = 1.0;
+        else dp_zfrac = fmin2(1.0, (parcel_dz - IN2P(zi, k + 1)) / (IN2P(zi, k) - IN2P(zi, k + 1)));
+        double qk = IN2(qh, k), tk = IN2(t, k), zk = IN2(zm, k) + zs;
+        double hmn_lev = (cp + qk * P.cpliq) * tk / (1.0 + qk) + (1.0 + qk / eps1) / (1.0 + qk) * grav * zk +
+                         (rl - (P.cpliq - P.cpwv) * (tk - P.tfreez)) * qk;
+        double dp_lev = IN2P(paph, k + 1) * 0.01 - IN2P(paph, k) * 0.01;
+        parcel_hdp = parcel_hdp + (hmn_lev * dp_lev) * dp_zfrac;
+        parcel_qdp = parcel_qdp + (qk * dp_lev) * dp_zfrac;
+        parcel_dp = parcel_dp + dp_lev * dp_zfrac;
+      }
+    }
+    double hpar = parcel_hdp / parcel_dp, qpar = parcel_qdp / parcel_dp;
+    mx = ipar;
+    tl = (hpar - rl * qpar - grav * parcel_ztop) / cp;
+    ql = qpar;
+    pl = IN2(pap, mx) * 0.01;
+  } else {
+    // zm_conv.F90:4677-4689
+    double hmax = 0.0;
+    for (int k = lon; k >= max(pblt, msg + 1); --k) {
+      double qk = IN2(qh, k), tk = IN2(t, k), zk = IN2(zm, k) + zs;
+      double hmn = (cp + qk * P.cpliq) * tk / (1.0 + qk) + (1.0 + qk / eps1) / (1.0 + qk) * grav * zk +
+                   (rl - (P.cpliq - P.cpwv) * (tk - P.tfreez)) * qk;
+      if (hmn > hmax) { hmax = hmn; mx = k; }
+    }
+    tl = IN2(t, mx);
+    ql = IN2(qh, mx);
+    pl = IN2(pap, mx) * 0.01;
+  }
+  int lcl = mx;
+
+  // ---- fused parcel sweep ------------------------------------------------------------------
+  double* tp_o = w.tp + col;        // stride ncolpad per level
+  double* qstp_o = w.qstp + col;
+  // levels outside [msg+1, mx] keep environment values (zm_conv.F90:4597-4598, 4760-4761)
+  for (int k = 1; k <= pver; ++k)
+    if (k <= msg || k > mx) {
+      tp_o[(size_t)(k - 1) * ncolpad] = IN2(t, k);
+      qstp_o[(size_t)(k - 1) * ncolpad] = IN2(qh, k);
+    }
+
+  double t_p, q_p, p_p, z_p;                 // environment at level k+1
+  double tmix1_p, qtmix_p, qsmix1_p, smix_p; // loop-1 parcel at level k+1
+  double qsmix2_p, xsh2o_p = 0.0, ds_xsh2o_p = 0.0, ds_freeze_p = 0.0;  // loop-2 parcel at k+1
+  double sp = 0.0, qtp = 0.0, mp = 0.0, sp0, qtp0, mp0 = 1.0;
+  bool ok = true;
+  {
+    const int k = mx;                        // launch level (zm_conv.F90:5002-5038, 5180-5200)
+    t_p = IN2(t, k); q_p = IN2(qh, k); p_p = IN2(pap, k) * 0.01; z_p = IN2(zm, k) + zs;
+    double dum;
+    if (P.lparcel_pbl) { qtp0 = ql; sp0 = enthalpy_q(tl, pl, qtp0, zl, dum); }
+    else               { qtp0 = q_p; sp0 = enthalpy_q(t_p, p_p, qtp0, z_p, dum); }
+    smix_p = sp0; qtmix_p = qtp0;
+    tmix1_p = t_p;
+    qsmix1_p = qsat_hPa_q(tmix1_p, p_p);
+    qsmix2_p = qsmix1_p;
+    double tpk = tmix1_p, qstpk = q_p;
+    double tpv = (tpk + tpert) * (1.0 + qstpk / eps1) / (1.0 + qstpk);
+    double tv = t_p * (1.0 + q_p / eps1) / (1.0 + q_p);
+    BUOY(k) = tpv - tv + P.tiedke_add;
+    tp_o[(size_t)(k - 1) * ncolpad] = tpk;
+    qstp_o[(size_t)(k - 1) * ncolpad] = qstpk;
+  }
+  const double lwmax = 1.e-3, tscool = 0.0;
+  for (int k = mx - 1; k >= msg + 1; --k) {
+    const double t_k = IN2(t, k), q_k = IN2(qh, k), p_k = IN2(pap, k) * 0.01, z_k = IN2(zm, k) + zs;
+    // ---- loop 1 body (zm_conv.F90:5042-5144) ----
+    double dp = (p_k - p_p);
+    double qtenv = 0.5 * (q_k + q_p);
+    double tenv = 0.5 * (t_k + t_p);
+    double penv = 0.5 * (p_k + p_p);
+    double zenv = 0.5 * (z_k + z_p);
+    double dum;
+    double senv = enthalpy_q(tenv, penv, qtenv, zenv, dum);
+    double dpdz = -(penv * grav) / (P.rgas * tenv);
+    double dzdp = 1.0 / dpdz;
+    double dmpdp = dmpdz * dzdp;
+    sp = sp - dmpdp * dp * senv;
+    qtp = qtp - dmpdp * dp * qtenv;
+    mp = mp - dmpdp * dp;
+    double smix_k = (sp0 + sp) / (mp0 + mp);
+    double qtmix_k = (qtp0 + qtp) / (mp0 + mp);
+    double tmix_k, qsmix_k;
+    if (!invert<1>(smix_k, p_k, z_k, qtmix_k, tmix1_p, tmix_k, qsmix_k)) {
+      ok = false; report_fail(w, 2, col, p_k, tmix1_p, qtmix_k, smix_k);
+    }
+    if (qsmix_k <= qtmix_k && qsmix1_p > qtmix_p) {
+      lcl = k;
+      double qxsk = qtmix_k - qsmix_k;
+      double qxskp1 = qtmix_p - qsmix1_p;
+      double dqxsdp = (qxsk - qxskp1) / dp;
+      pl = p_p - qxskp1 / dqxsdp;
+      zl = z_p - qxskp1 / dqxsdp * dzdp;
+      double dsdp = (smix_k - smix_p) / dp;
+      double dqtdp = (qtmix_k - qtmix_p) / dp;
+      double slcl = smix_p + dsdp * (pl - p_p);
+      double qtlcl = qtmix_p + dqtdp * (pl - p_p);
+      double qslcl;
+      if (!invert<1>(slcl, pl, zl, qtlcl, tmix_k, tl, qslcl)) {
+        ok = false; report_fail(w, 3, col, pl, tmix_k, qtlcl, slcl);
+      }
+    }
+    // ---- loop 2 body (zm_conv.F90:5202-5269) ----
+    double tmix2 = tmix_k, qsmix2 = qsmix_k;
+    double smix2 = entropy_q(tmix2, p_k, qtmix_k, dum);
+    double xsh2o_k = 0.0, ds_xsh2o_k = 0.0, ds_freeze_k = 0.0, new_s = 0.0, new_q = 0.0;
+#pragma unroll 1
+    for (int ii = 0; ii < 2; ++ii) {
+      xsh2o_k = fmax2(0.0, qtmix_k - qsmix2 - lwmax);
+      ds_xsh2o_k = ds_xsh2o_p - P.cpliq * zmm::log_(tmix2 / P.tfreez) * fmax2(0.0, (xsh2o_k - xsh2o_p));
+      if (tmix2 <= P.tfreez + tscool && ds_freeze_p == 0.0)
+        ds_freeze_k = (P.latice / tmix2) * fmax2(0.0, qtmix_k - qsmix2 - xsh2o_k);
+      if (tmix2 <= P.tfreez + tscool && ds_freeze_p != 0.0)
+        ds_freeze_k = ds_freeze_p + (P.latice / tmix2) * fmax2(0.0, (qsmix2_p - qsmix2));
+      new_s = smix2 + ds_xsh2o_k + ds_freeze_k;
+      new_q = qtmix_k - xsh2o_k;
+      double tfg = tmix2;
+      if (!invert<0>(new_s, p_k, 0.0, new_q, tfg, tmix2, qsmix2)) {
+        ok = false; report_fail(w, 4, col, p_k, tfg, new_q, new_s);
+      }
+    }
+    double tpk = tmix2;
+    double qstpk = (new_q > qsmix2) ? qsmix2 : new_q;
+    double tpv = (tpk + tpert) * (1.0 + qstpk / eps1) / (1.0 + new_q);
+    double tv = t_k * (1.0 + q_k / eps1) / (1.0 + q_k);
+    BUOY(k) = tpv - tv + P.tiedke_add;
+    tp_o[(size_t)(k - 1) * ncolpad] = tpk;
+    qstp_o[(size_t)(k - 1) * ncolpad] = qstpk;
+    // shift level k -> k+1
+    t_p = t_k; q_p = q_k; p_p = p_k; z_p = z_k;
+    tmix1_p = tmix_k; qtmix_p = qtmix_k; qsmix1_p = qsmix_k; smix_p = smix_k;
+    qsmix2_p = qsmix2; xsh2o_p = xsh2o_k; ds_xsh2o_p = ds_xsh2o_k; ds_freeze_p = ds_freeze_k;
+  }
+  (void)ok;
+
+  // ---- CAPE / CIN (zm_conv.F90:4742-4816) ----------------------------------------------------
+  const bool plge600 = pl >= P.plclmin;
+  double cape = 0.0, cin = 0.0;
+  int lel = pver;
+  if (!plge600) {
+    for (int k = msg + 1; k <= mx; ++k) {
+      tp_o[(size_t)(k - 1) * ncolpad] = IN2(t, k);
+      qstp_o[(size_t)(k - 1) * ncolpad] = IN2(qh, k);
+    }
+  } else {
+    int lelten[ZM_MAXCIN];
+    double capeten[ZM_MAXCIN], cinten[ZM_MAXCIN];
+#pragma unroll
+    for (int n = 0; n < ZM_MAXCIN; ++n) { lelten[n] = pver; capeten[n] = 0.0; cinten[n] = 0.0; }
+    int knt = 0;
+    for (int k = msg + 2; k <= pver; ++k) {
+      if (k < lcl) {
+        if (BUOY(k + 1) > 0.0 && BUOY(k) <= 0.0) {
+          knt = min(P.num_cin, knt + 1);
+#pragma unroll
+          for (int n = 0; n < ZM_MAXCIN; ++n) if (n == knt - 1) lelten[n] = k;
+        }
+      }
+    }
+    for (int k = msg + 1; k <= mx; ++k) {
+      double lg = zmm::log_((IN2P(paph, k + 1) * 0.01) / (IN2P(paph, k) * 0.01));
+      double b = BUOY(k);
+#pragma unroll
+      for (int n = 0; n < ZM_MAXCIN; ++n) {
+        if (n < P.num_cin && k > lelten[n]) {
+          capeten[n] = capeten[n] + P.rgas * b * lg;
+          cinten[n] = cinten[n] - P.rgas * fmin2(b, 0.0) * lg;
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < ZM_MAXCIN; ++n) {
+      if (n < P.num_cin && capeten[n] > cape) { cape = capeten[n]; cin = cinten[n]; lel = lelten[n]; }
+    }
+    cape = fmax2(cape, 0.0);
+  }
+  w.cape[col] = cape; w.cin[col] = cin; w.tl[col] = tl;
+  w.lcl[col] = lcl; w.lel[col] = lel; w.mx[col] = mx;
+#undef BUOY
+#undef IN2
+#undef IN2P
+}
+
+// ---- trigger + order-preserving compaction, one warp per chunk -------------------------------
+// zm_conv.F90:905-915 (FINAL=0: pass-1 worklist) and 1095-1111 (FINAL=1: ideep/lengath outputs).
+template <int FINAL>
+__global__ void k_trigger(ConvrIn in, ConvrOut o, ConvrWork w) {
+  const int pcols = P.pcols;
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= in.nchunks) return;
+  const int ncol = in.ncol[c];
+  int base = 0;
+  int wlbase = 0;
+  // first sweep: count; second sweep: write (keeps the worklist range of a chunk contiguous)
+  int total = 0;
+  for (int i0 = 0; i0 < ncol; i0 += 32) {
+    int i = i0 + lane;
+    bool trig = false;
+    if (i < ncol) {
+      int col = c * pcols + i;
+      double cape = w.cape[col];
+      trig = (cape > P.capelmt) && (w.cin[col] < cape * P.cin_threshd);
+    }
+    total += __popc(__ballot_sync(0xffffffffu, trig));
+  }
+  if (lane == 0) wlbase = total ? atomicAdd(&w.count[FINAL], total) : 0;
+  wlbase = __shfl_sync(0xffffffffu, wlbase, 0);
+  for (int i0 = 0; i0 < ncol; i0 += 32) {
+    int i = i0 + lane;
+    bool trig = false;
+    int col = c * pcols + i;
+    if (i < ncol) {
+      double cape = w.cape[col];
+      trig = (cape > P.capelmt) && (w.cin[col] < cape * P.cin_threshd);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, trig);
+    int pos = base + __popc(m & ((1u << lane) - 1u));
+    if (trig) {
+      if (FINAL) {
+        o.ideep[(size_t)c * pcols + pos] = i + 1;
+        w.wl2[2 * (wlbase + pos)] = col;
+        w.wl2[2 * (wlbase + pos) + 1] = c * pcols + pos;
+      } else {
+        w.wl1[wlbase + pos] = col;
+      }
+    }
+    base += __popc(m);
+  }
+  if (FINAL) {
+    if (lane == 0) o.lengath[c] = total;
+    for (int i = lane; i < ncol; i += 32) o.cape[(size_t)c * pcols + i] = w.cape[c * pcols + i];
+  }
+}

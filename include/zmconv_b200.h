@@ -1,0 +1,149 @@
+/* zmconv_b200.h -- C ABI of libzmconv_b200.so: the B200-native (sm_100a CUDA, FP64) drop-in for
+ * the five public procedures of module zm_conv in NorESMhub/CAM-Nor-physics
+ * (physics/zm_conv.F90:33-37): zm_convi, zm_convr, zm_conv_evap, convtran, momtran.
+ *
+ * Layout contract (identical to the reference's chunk storage): every field is the Fortran
+ * array (pcols, nlev[, ncnst]) of each chunk, chunks back to back:
+ *     element (i,k[,m]) of chunk c  ->  base[ ((c*ncnst + (m-1))*nlev + (k-1))*pcols + (i-1) ]
+ * nchunks = 1 reproduces the reference's per-chunk call exactly.  All integer index outputs
+ * (ideep, jt, maxg, and the real-valued jctop/jcbot) are 1-based like the reference.
+ *
+ * Gathered outputs (mu, md, du, eu, ed, dp, dsubcld, jt, maxg) are indexed by gathered position
+ * 1..lengath(c) inside each chunk, exactly like the reference (zm_conv.F90:926-940); rows
+ * lengath(c)+1..pcols are zero-filled (the reference leaves them undefined).
+ *
+ * Every *_batch entry point takes HOST pointers and does its own H2D/D2H; the *_batch_dev
+ * twins take DEVICE pointers and only enqueue work on `stream` (a cudaStream_t cast to void*,
+ * NULL = the library's own stream) -- callers that keep physics_state resident use those.
+ * Return value: 0 on success; >0 = number of Brent non-convergence events (the reference's
+ * endrun at zm_conv.F90:5401-5410, 5557-5566; details via zm_last_error); <0 = API/CUDA error.
+ * The library is re-entrant across host threads after zm_init (per-thread workspaces).
+ */
+#ifndef ZMCONV_B200_H
+#define ZMCONV_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* All scalars zm_convi copies into module state (zm_conv.F90:115-227) + ppgrid + physconst. */
+typedef struct zm_params {
+  int pcols, pver;              /* ppgrid (zm_conv.F90:17) */
+  int limcnv, num_cin;          /* zm_convi args (zm_conv.F90:115-120) */
+  int zm_org, microp;           /* must be 0: branches out of scope (zm_microphysics absent) */
+  int no_deep_pbl, lparcel_pbl;
+  int cam3;                     /* cam_physpkg_is('cam3'), zm_conv.F90:871 -> undilute buoyan */
+  int masterproc;               /* zm_conv.F90:213: tentrm=-dmpdz only assigned on masterproc */
+  double c0_lnd, c0_ocn, ke, ke_lnd, momcu, momcd;
+  double tiedke_add, capelmt, dmpdz, tau;
+  /* physconst (zm_conv.F90:19-20) */
+  double cpair, epsilo, gravit, latice, latvap, tmelt, rair, cpwv, cpliq, rh2o, cpvir, zvir;
+} zm_params_t;
+
+/* CAM6 namelist defaults + shr_const_mod physconst for a grid. */
+void zm_params_default(zm_params_t* p, int pcols, int pver, int limcnv);
+
+/* replaces zm_convi (zm_conv.F90:115; call site zm_conv_intr.F90:376-379). */
+int zm_init(const zm_params_t* p);
+int zm_finalize(void);
+/* copies the last error text (Brent failure diagnostics / CUDA error) into buf. */
+int zm_last_error(char* buf, int buflen);
+
+/* replaces zm_convr (zm_conv.F90:231-244; call site zm_conv_intr.F90:662-673).
+ * Argument order follows the Fortran dummy list; lchnk/org/orgt/org2d/conv/aero dropped. */
+int zm_convr_batch(int nchunks, const int* ncol,
+                   const double* t, const double* qh, double* prec, double* jctop, double* jcbot,
+                   const double* pblh, const double* zm, const double* geos, const double* zi,
+                   double* qtnd, double* heat, const double* pap, const double* paph,
+                   const double* dpp, double delt, double* mcon, double* cme, double* cape,
+                   double* eurt, const double* tpert, double* dlf, double* pflx, double* zdu,
+                   double* rprd, double* mu, double* md, double* du, double* eu, double* ed,
+                   double* dp, double* dsubcld, int* jt, int* maxg, int* ideep, int* lengath,
+                   double* ql, double* rliq, const double* landfrac,
+                   double* dif, double* dnlf, double* dnif, double* rice);
+int zm_convr_batch_dev(int nchunks, const int* ncol,
+                   const double* t, const double* qh, double* prec, double* jctop, double* jcbot,
+                   const double* pblh, const double* zm, const double* geos, const double* zi,
+                   double* qtnd, double* heat, const double* pap, const double* paph,
+                   const double* dpp, double delt, double* mcon, double* cme, double* cape,
+                   double* eurt, const double* tpert, double* dlf, double* pflx, double* zdu,
+                   double* rprd, double* mu, double* md, double* du, double* eu, double* ed,
+                   double* dp, double* dsubcld, int* jt, int* maxg, int* ideep, int* lengath,
+                   double* ql, double* rliq, const double* landfrac,
+                   double* dif, double* dnlf, double* dnif, double* rice, void* stream);
+
+/* replaces zm_conv_evap (zm_conv.F90:1712-1717; call site zm_conv_intr.F90:764-769);
+ * prdsnow absent (old_snow). prec is inout. */
+int zm_conv_evap_batch(int nchunks, const int* ncol,
+                       const double* t, const double* pmid, const double* pdel, const double* q,
+                       const double* landfrac,
+                       double* tend_s, double* tend_s_snwprd, double* tend_s_snwevmlt, double* tend_q,
+                       const double* prdprec, const double* cldfrc, double deltat,
+                       double* prec, double* snow, double* ntprprd, double* ntsnprd,
+                       double* flxprec, double* flxsnow);
+int zm_conv_evap_batch_dev(int nchunks, const int* ncol,
+                       const double* t, const double* pmid, const double* pdel, const double* q,
+                       const double* landfrac,
+                       double* tend_s, double* tend_s_snwprd, double* tend_s_snwevmlt, double* tend_q,
+                       const double* prdprec, const double* cldfrc, double deltat,
+                       double* prec, double* snow, double* ntprprd, double* ntsnprd,
+                       double* flxprec, double* flxsnow, void* stream);
+
+/* replaces momtran (zm_conv.F90:2315-2319; call site zm_conv_intr.F90:822-826).
+ * il1g = 1, il2g = lengath[c].  q/dqdt/pguall/pgdall/icwu/icwd are (pcols,pver,ncnst). */
+int zm_momtran_batch(int nchunks, const int* ncol, const int* domomtran, const double* q, int ncnst,
+                     const double* mu, const double* md, const double* du, const double* eu,
+                     const double* ed, const double* dp, const double* dsubcld,
+                     const int* jt, const int* mx, const int* ideep, const int* lengath,
+                     double* dqdt, double* pguall, double* pgdall, double* icwu, double* icwd,
+                     double dt, double* seten);
+int zm_momtran_batch_dev(int nchunks, const int* ncol, const int* domomtran, const double* q, int ncnst,
+                     const double* mu, const double* md, const double* du, const double* eu,
+                     const double* ed, const double* dp, const double* dsubcld,
+                     const int* jt, const int* mx, const int* ideep, const int* lengath,
+                     double* dqdt, double* pguall, double* pgdall, double* icwu, double* icwd,
+                     double dt, double* seten, void* stream);
+
+/* replaces convtran (zm_conv.F90:1976-1980; call sites zm_conv_intr.F90:875-879, 1020-1024).
+ * doconvtran[ncnst] / cnst_is_dry[ncnst] are HOST int flags in both variants
+ * (cnst_is_dry replaces the external cnst_get_type_byind(m).eq.'dry', zm_conv.F90:2087).
+ * dqdt(:,:,m) is written (zero + scatter) only for active m >= 2, like the reference. */
+int zm_convtran_batch(int nchunks, const int* doconvtran, const double* q, int ncnst,
+                      const double* mu, const double* md, const double* du, const double* eu,
+                      const double* ed, const double* dp, const double* dsubcld,
+                      const int* jt, const int* mx, const int* ideep, const int* lengath,
+                      const double* fracis, double* dqdt, const double* dpdry, double dt,
+                      const int* cnst_is_dry);
+int zm_convtran_batch_dev(int nchunks, const int* doconvtran, const double* q, int ncnst,
+                      const double* mu, const double* md, const double* du, const double* eu,
+                      const double* ed, const double* dp, const double* dsubcld,
+                      const int* jt, const int* mx, const int* ideep, const int* lengath,
+                      const double* fracis, double* dqdt, const double* dpdry, double dt,
+                      const int* cnst_is_dry, void* stream);
+
+/* Synchronises `stream` (NULL = the calling thread's library stream) and returns the number of
+ * Brent non-convergence events of this thread's last zm_convr_batch_dev call (0 = clean). */
+int zm_sync_check(void* stream);
+
+/* ---- diagnostics used by tests and bench (not part of the reference surface) ------------ */
+/* evaluates the portable math library on the DEVICE: id 0 log,1 log10,2 exp,3 10**x,4 x**y */
+int zm_math_eval_dev(int id, int n, const double* x_host, const double* y_host, double* out_host);
+/* same functions evaluated by the host build of zm_math.h */
+int zm_math_eval_host(int id, int n, const double* x, const double* y, double* out);
+/* device scalar thermodynamics, one call per element (host arrays in/out):
+ * id 0: entropy(t,p,q)  1: enthalpy(t,p,q,z)  2: ientropy(s,p,q,tfg)->t,qst
+ * 3: ienthalpy(s,p,z,q,tfg)->t,qst  4: qsat_hPa(t,p)->es,q  5: table qsat(t,pPa)->es,qs */
+int zm_thermo_eval_dev(int id, int n, const double* a, const double* b, const double* c,
+                       const double* d, const double* e, double* out0, double* out1);
+/* FP64 FMA-chain microbenchmark on the current device: returns achieved FLOP/s (FMA = 2). */
+double zm_fp64_peak_flops(int iters);
+/* per-kernel device time (ms) of the last zm_convr_batch[_dev] call made with profiling on:
+ * names/ms arrays of length *n (max 16). */
+int zm_set_profiling(int on);
+int zm_get_kernel_times(int* n, const char** names, float* ms);
+/* number of kernel launches issued by this thread since the last call (bench's gpu_launches) */
+long long zm_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,116 @@
+/* zm_oracle.h -- TEST INFRASTRUCTURE.  C interface of the CPU oracle (oracle/zm_oracle.cpp):
+ * a line-faithful restatement of /root/reference/physics/zm_conv.F90 (CAM-Nor ZM deep
+ * convection).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load it.  The product library never links or calls this.
+ *
+ * Array conventions are the Fortran ones: every (pcols,pver[,n]) array is column-major,
+ * element (i,k) at (i-1) + pcols*(k-1); indices stored in integer outputs are 1-based.
+ */
+#ifndef ZM_ORACLE_H
+#define ZM_ORACLE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zmo_params {
+  /* ppgrid */
+  int pcols, pver;
+  /* zm_convi arguments, zm_conv.F90:115-120 */
+  int limcnv, num_cin;
+  int zm_org, microp, no_deep_pbl, lparcel_pbl;
+  /* cam_physpkg_is('cam3') (zm_conv.F90:871) and masterproc (zm_conv.F90:185,213) */
+  int cam3, masterproc;
+  double c0_lnd, c0_ocn, ke, ke_lnd, momcu, momcd;
+  double tiedke_add, capelmt, dmpdz, tau;
+  /* physconst, zm_conv.F90:19-20 */
+  double cpair, epsilo, gravit, latice, latvap, tmelt, rair, cpwv, cpliq, rh2o, cpvir, zvir;
+} zmo_params_t;
+
+/* fills CAM6-default namelist values + shr_const physconst for the given grid */
+void zmo_params_default(zmo_params_t* p, int pcols, int pver, int limcnv);
+const char* zmo_math_backend(void);
+
+/* zm_convi (zm_conv.F90:115).  Returns 0, or nonzero for the reference's endrun conditions. */
+int zmo_convi(const zmo_params_t* p);
+
+/* zm_convr (zm_conv.F90:231) -- argument order of the Fortran dummy list, minus
+ * org/orgt/org2d/conv/aero (zm_org and zmconv_microp are out of scope).
+ * Returns 0, or the number of Brent non-convergence events (reference: endrun). */
+int zmo_convr(int lchnk, int ncol,
+              const double* t, const double* qh, double* prec, double* jctop, double* jcbot,
+              const double* pblh, const double* zm, const double* geos, const double* zi,
+              double* qtnd, double* heat, const double* pap, const double* paph, const double* dpp,
+              double delt, double* mcon, double* cme, double* cape, double* eurt,
+              const double* tpert, double* dlf, double* pflx, double* zdu, double* rprd,
+              double* mu, double* md, double* du, double* eu, double* ed,
+              double* dp, double* dsubcld, int* jt, int* maxg, int* ideep, int* lengath,
+              double* ql, double* rliq, const double* landfrac,
+              double* dif, double* dnlf, double* dnif, double* rice);
+
+/* buoyan_dilute (zm_conv.F90:4425) on already-converted inputs (p, pf in hPa; z absolute).
+ * dmpdz is (pcols,pver). Used for stage-level parity tests. */
+int zmo_buoyan_dilute(int lchnk, int ncol,
+                      const double* q, const double* t, const double* p, const double* z,
+                      const double* pf, double* tp, double* qstp, double* tl, double* cape,
+                      double* cin, const double* pblt, int* lcl, int* lel, int* lon, int* mx,
+                      const double* zi, const double* zs, const double* tpert,
+                      const double* landfrac, const double* dmpdz);
+
+/* zm_conv_evap (zm_conv.F90:1712); prdsnow absent (old_snow = .true.). */
+void zmo_conv_evap(int ncol, int lchnk,
+                   const double* t, const double* pmid, const double* pdel, const double* q,
+                   const double* landfrac,
+                   double* tend_s, double* tend_s_snwprd, double* tend_s_snwevmlt, double* tend_q,
+                   const double* prdprec, const double* cldfrc, double deltat,
+                   double* prec, double* snow, double* ntprprd, double* ntsnprd,
+                   double* flxprec, double* flxsnow);
+
+/* convtran (zm_conv.F90:1976).  doconvtran[ncnst] logical as int; cnst_is_dry[ncnst]
+ * replaces the external cnst_get_type_byind(m).eq.'dry'. */
+void zmo_convtran(int lchnk, const int* doconvtran, const double* q, int ncnst,
+                  const double* mu, const double* md, const double* du, const double* eu,
+                  const double* ed, const double* dp, const double* dsubcld,
+                  const int* jt, const int* mx, const int* ideep, int il1g, int il2g,
+                  int nstep, const double* fracis, double* dqdt, const double* dpdry, double dt,
+                  const int* cnst_is_dry);
+
+/* momtran (zm_conv.F90:2315). */
+void zmo_momtran(int lchnk, int ncol, const int* domomtran, const double* q, int ncnst,
+                 const double* mu, const double* md, const double* du, const double* eu,
+                 const double* ed, const double* dp, const double* dsubcld,
+                 const int* jt, const int* mx, const int* ideep, int il1g, int il2g,
+                 int nstep, double* dqdt, double* pguall, double* pgdall,
+                 double* icwu, double* icwd, double dt, double* seten);
+
+/* scalar helpers exposed for property tests (zm_conv.F90:5280,5440,5304,5460,5421) */
+double zmo_entropy(double tk, double p, double qtot);
+double zmo_enthalpy(double tk, double p, double qtot, double z);
+int zmo_ientropy(double s, double p, double qt, double tfg, double* t, double* qst);
+int zmo_ienthalpy(double s, double p, double z, double qt, double tfg, double* t, double* qst);
+void zmo_qsat_hpa(double t, double p, double* es, double* qm);
+/* table qsat used by zm_conv_evap (external wv_saturation::qsat), p in Pa */
+void zmo_qsat_table(double t, double p, double* es, double* qs);
+
+/* operation counters for the roofline flop figure (per-thread; reset then read) */
+void zmo_counters_reset(void);
+/* out[0]=qsat_hPa calls, [1]=entropy, [2]=enthalpy, [3]=ientropy, [4]=ienthalpy,
+ * [5]=log, [6]=log10, [7]=pow10, [8]=exp, [9]=pow  */
+void zmo_counters_get(long long* out10);
+
+/* chunk-loop drivers (OpenMP over chunks, mirroring physpkg.F90:1147) used for timing and
+ * for whole-grid parity.  All arrays are [chunk][k][i] i.e. Fortran chunks back-to-back. */
+int zmo_convr_batch(int nchunks, const int* ncol,
+                    const double* t, const double* qh, double* prec, double* jctop, double* jcbot,
+                    const double* pblh, const double* zm, const double* geos, const double* zi,
+                    double* qtnd, double* heat, const double* pap, const double* paph,
+                    const double* dpp, double delt, double* mcon, double* cme, double* cape,
+                    double* eurt, const double* tpert, double* dlf, double* pflx, double* zdu,
+                    double* rprd, double* mu, double* md, double* du, double* eu, double* ed,
+                    double* dp, double* dsubcld, int* jt, int* maxg, int* ideep, int* lengath,
+                    double* ql, double* rliq, const double* landfrac,
+                    double* dif, double* dnlf, double* dnif, double* rice, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
