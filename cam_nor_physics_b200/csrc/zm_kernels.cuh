@@ -175,11 +175,15 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
     const int k = mx;                        // launch level (zm_conv.F90:5002-5038, 5180-5200)
     t_p = IN2(t, k); q_p = IN2(qh, k); p_p = IN2(pap, k) * 0.01; z_p = IN2(zm, k) + zs;
     double dum;
-    if (P.lparcel_pbl) { qtp0 = ql; sp0 = enthalpy_q(tl, pl, qtp0, zl, dum); }
-    else               { qtp0 = q_p; sp0 = enthalpy_q(t_p, p_p, qtp0, z_p, dum); }
-    smix_p = sp0; qtmix_p = qtp0;
     tmix1_p = t_p;
-    qsmix1_p = qsat_hPa_q(tmix1_p, p_p);
+    if (P.lparcel_pbl) {
+      qtp0 = ql; sp0 = enthalpy_q(tl, pl, qtp0, zl, dum);
+      (void)enthalpy_q(tmix1_p, p_p, qtp0, z_p, qsmix1_p);     // qsmix = qsat_hPa(tmix, p)
+    } else {
+      // enthalpy(t,p,..) evaluates qsat_hPa(t,p) internally: same arguments as zm_conv.F90:5031
+      qtp0 = q_p; sp0 = enthalpy_q(t_p, p_p, qtp0, z_p, qsmix1_p);
+    }
+    smix_p = sp0; qtmix_p = qtp0;
     qsmix2_p = qsmix1_p;
     double tpk = tmix1_p, qstpk = q_p;
     double tpv = (tpk + tpert) * (1.0 + qstpk / eps1) / (1.0 + qstpk);

@@ -83,10 +83,11 @@ size_t convr_work_bytes(size_t ncolpad, int pver) {
 }
 
 // enqueue the whole zm_convr pipeline on stream s (no host synchronisation)
-int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOut& o) {
+int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOut& o,
+                 bool own_arena = true) {
   const int pcols = g_params.pcols, pver = g_params.pver;
   const size_t ncolpad = (size_t)in.nchunks * pcols;
-  if (ws.ensure(convr_work_bytes(ncolpad, pver))) return -100;
+  if (own_arena && ws.ensure(convr_work_bytes(ncolpad, pver))) return -100;
   ConvrWork w;
   w.cape = ws.take<double>(ncolpad); w.cin = ws.take<double>(ncolpad); w.tl = ws.take<double>(ncolpad);
   w.dmpdz = ws.take<double>(ncolpad);
@@ -191,10 +192,10 @@ int evap_launch(cudaStream_t s, const EvapArgs& a) {
   return 0;
 }
 
-int momtran_launch(Workspace& ws, cudaStream_t s, MomArgs a) {
+int momtran_launch(Workspace& ws, cudaStream_t s, MomArgs a, bool own_arena = true) {
   const int pcols = g_params.pcols, pver = g_params.pver;
   const int ncolpad = a.nchunks * pcols;
-  if (ws.ensure(2 * al(a.nchunks, 4) + 1024)) return -100;
+  if (own_arena && ws.ensure(2 * al(a.nchunks, 4) + 1024)) return -100;
   int* ktm = ws.take<int>(a.nchunks); int* kbm = ws.take<int>(a.nchunks);
   a.ktm = ktm; a.kbm = kbm;
   k_chunk_bounds<<<(a.nchunks * 32 + 127) / 128, 128, 0, s>>>(a.nchunks, a.jt, a.mx, a.lengath, ktm, kbm);
@@ -240,6 +241,81 @@ int convtran_launch(Workspace& ws, cudaStream_t s, TranArgs a, const int* doconv
   return 0;
 }
 
+// ---- zm_conv_tend glue (zm_conv_intr.F90:662-836) ------------------------------------------------
+// state1 after physics_update(ptend_loc of zm_convr): physics_types.F90:322-329 (q + qneg3 clip at
+// qmin(1)=1e-12) and :427 (t += s*dt/cpair); winds(:,:,1:2) = state1%u,v (zm_conv_intr.F90:815-816)
+__global__ void k_state_update(int n2, int nper, const double* t, const double* q, const double* heat,
+                               const double* qtnd, const double* u, const double* v, double ztodt,
+                               double* t1, double* q1, double* winds) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += gridDim.x * blockDim.x) {
+    t1[e] = t[e] + heat[e] * ztodt / P.cpair;
+    double qn = q[e] + qtnd[e] * ztodt;
+    q1[e] = (qn < 1.e-12) ? 1.e-12 : qn;
+    int c = e / nper, r = e - c * nper;            // nper = pcols*pver
+    winds[(size_t)c * 2 * nper + r] = u[e];
+    winds[(size_t)c * 2 * nper + nper + r] = v[e];
+  }
+}
+// ptend_all = sum of the three ptend_loc (physics_ptend_sum, physics_types.F90:698-844) and the
+// mcon unit conversion mb/s -> kg/m2/s (zm_conv_intr.F90:693)
+__global__ void k_tend_finalize(int n2, int n2p, int nper, const double* heat, const double* qtnd,
+                                const double* ev_s, const double* ev_q, const double* seten,
+                                const double* wtend, double* ps, double* pq, double* pu, double* pv,
+                                double* evapcdp, double* mcon) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n2p; e += gridDim.x * blockDim.x) {
+    mcon[e] = mcon[e] * 100.0 / P.gravit;
+    if (e < n2) {
+      ps[e] = (heat[e] + ev_s[e]) + seten[e];
+      pq[e] = qtnd[e] + ev_q[e];
+      int c = e / nper, r = e - c * nper;
+      pu[e] = wtend[(size_t)c * 2 * nper + r];
+      pv[e] = wtend[(size_t)c * 2 * nper + nper + r];
+      evapcdp[e] = ev_q[e];
+    }
+  }
+}
+
+// ---- global water / energy budget terms (what check_energy_chng tests after ZM, physpkg.F90:2865) --
+// Deterministic two-stage reduction: one partial per block, then a single block adds them in order.
+__global__ void k_conservation_partial(int nchunks, const int* ncol, const double* pdel, const double* pq,
+                                       const double* ps, const double* prec, const double* snow,
+                                       const double* rliq, const int* lengath, double* partial) {
+  __shared__ double sh[6][128];
+  const int pcols = P.pcols, pver = P.pver;
+  double a[6] = {0, 0, 0, 0, 0, 0};
+  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < nchunks * pcols; col += gridDim.x * blockDim.x) {
+    const int c = col / pcols, i = col - c * pcols;
+    if (i >= ncol[c]) continue;
+    double wq = 0.0, ws = 0.0;
+    for (int k = 0; k < pver; ++k) {
+      size_t e = cidx(c, k, i, pver);
+      wq += pdel[e] / P.gravit * pq[e];
+      ws += pdel[e] / P.gravit * ps[e];
+    }
+    a[0] += wq;
+    a[1] += 1000.0 * (prec[col] + rliq[col]);
+    a[2] += ws;
+    a[3] += 1000.0 * (P.latvap * (prec[col] + rliq[col]) + P.latice * snow[col]);
+    a[5] += 1.0;
+    if (i == 0) a[4] += (double)lengath[c];
+  }
+  for (int j = 0; j < 6; ++j) sh[j][threadIdx.x] = a[j];
+  __syncthreads();
+  for (int off = 64; off; off >>= 1) {
+    if (threadIdx.x < off)
+      for (int j = 0; j < 6; ++j) sh[j][threadIdx.x] += sh[j][threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) partial[blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
+}
+__global__ void k_conservation_final(int nblocks, const double* partial, double* out6) {
+  if (threadIdx.x < 6) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partial[b * 6 + threadIdx.x];
+    out6[threadIdx.x] = s;
+  }
+}
+
 // ---- diagnostics kernels ----------------------------------------------------------------------
 __global__ void k_math_eval(int id, int n, const double* x, const double* y, double* o) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,6 +342,30 @@ __global__ void k_thermo_eval(int id, int n, const double* a, const double* b, c
     default: qsat_table(a[i], b[i], r0, r1); break;
   }
   o0[i] = r0; o1[i] = r1;
+}
+// single-warp latency microbenchmark (cycles per dependent call), see zm_microbench
+__global__ void k_microbench(double* out, long long* cyc, int n) {
+  double x = 290.0 + threadIdx.x * 0.01, acc = 0.0, q;
+  long long t0, t1;
+  int j = 0;
+#define MB(expr)                                      \
+  t0 = clock64();                                     \
+  for (int i = 0; i < n; ++i) { expr; }               \
+  t1 = clock64();                                     \
+  if (threadIdx.x == 0) cyc[j] = (t1 - t0) / n;       \
+  ++j;
+  MB(x = 300.0 + 1e-3 * (373.16 / x));                                   // 0 division
+  MB(x = 300.0 + 1e-3 * zmm::log_(x));                                   // 1 log
+  MB(x = 300.0 + 1e-3 * zmm::log10_(x));                                 // 2 log10
+  MB(x = 300.0 + 1e-3 * zmm::pow10_(x * 1e-2));                          // 3 pow10
+  MB(x = 300.0 + 1e-3 * zmm::exp_(x * 1e-2));                            // 4 exp
+  MB(x = 300.0 + 1e-6 * gg_svp_water(x));                                // 5 goff-gratch
+  MB(x = 300.0 + 1e-9 * state_fn(1, x, 900.0, 0.015, 500.0, q));         // 6 enthalpy
+  MB(x = 300.0 + 1e-6 * state_fn(0, x, 900.0, 0.015, 0.0, q));           // 7 entropy
+  MB(invert_k(1, 3.5e5 + x, 900.0, 500.0, 0.015, 295.0, acc, q); x = 290.0 + 1e-3 * acc);  // 8 ienthalpy
+  MB(invert_k(0, 250.0 + 1e-3 * x, 900.0, 0.0, 0.015, 295.0, acc, q); x = 290.0 + 1e-3 * acc);  // 9 ientropy
+  MB(x = 300.0 + 1e-3 * zmm::pow_(x, 0.2857));                           // 10 pow
+  out[threadIdx.x] = x + acc;
 }
 __global__ void k_fp64_peak(double* out, int iters) {
   double a0 = 1.0 + threadIdx.x * 1e-9, a1 = 1.1, a2 = 1.2, a3 = 1.3, a4 = 1.4, a5 = 1.5, a6 = 1.6, a7 = 1.7;
@@ -588,6 +688,122 @@ int zm_convtran_batch(int nchunks, const int* doconvtran, const double* q, int n
   return S.flush();
 }
 
+// zm_conv_tend (zm_conv_intr.F90:390-951, microphysics/org/convtran1 parts excluded): zm_convr ->
+// physics_update -> zm_conv_evap -> momtran, everything resident on the device.
+int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
+                           const double* v, const double* pmid, const double* pint, const double* pdel,
+                           const double* zm, const double* zi, const double* phis, const double* pblh,
+                           const double* tpert, const double* landfrac, const double* cld, double ztodt,
+                           double* ptend_s, double* ptend_q, double* ptend_u, double* ptend_v, double* mcon,
+                           double* cme, double* pflx, double* zdu, double* rliq, double* rice, double* jctop,
+                           double* jcbot, double* prec, double* snow, double* ql, double* rprd,
+                           double* evapcdp, double* flxprec, double* flxsnow, double* dlf, double* mu,
+                           double* md, double* du, double* eu, double* ed, double* dp, double* dsubcld,
+                           int* jt, int* maxg, int* ideep, int* lengath, double* cape, void* stream) {
+  NEED_INIT();
+  if (nchunks <= 0) return 0;
+  const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc;
+  const size_t n2 = nc * L, n2p = nc * (L + 1);
+  Workspace& ws = tls_work;
+  if (ws.ensure(convr_work_bytes(nc, (int)L) + 18 * al(n2, 8) + 6 * al(2 * n2, 8) + 2 * al(nchunks, 4) + 8192))
+    return -100;
+  cudaStream_t s = stream ? (cudaStream_t)stream : ws.stream;
+  double *heat = ws.take<double>(n2), *qtnd = ws.take<double>(n2), *eurt = ws.take<double>(n2),
+         *dif = ws.take<double>(n2), *dnlf = ws.take<double>(n2), *dnif = ws.take<double>(n2),
+         *t1 = ws.take<double>(n2), *q1 = ws.take<double>(n2), *ev_s = ws.take<double>(n2),
+         *ev_q = ws.take<double>(n2), *snwprd = ws.take<double>(n2), *snwevmlt = ws.take<double>(n2),
+         *ntprprd = ws.take<double>(n2), *ntsnprd = ws.take<double>(n2), *seten = ws.take<double>(n2);
+  double *winds = ws.take<double>(2 * n2), *wtend = ws.take<double>(2 * n2), *pgu = ws.take<double>(2 * n2),
+         *pgd = ws.take<double>(2 * n2), *icwu = ws.take<double>(2 * n2), *icwd = ws.take<double>(2 * n2);
+  ConvrIn in{nchunks, ncol, t, q, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac, 0.5 * ztodt};
+  ConvrOut o{prec, jctop, jcbot, qtnd, heat, mcon, cme, cape, eurt, dlf, pflx, zdu, rprd,
+             mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, lengath, ql, rliq, dif, dnlf, dnif, rice};
+  int rc = convr_launch(ws, s, in, o, false);
+  if (rc) return rc;
+  const int nper = (int)(pc * L);
+  k_state_update<<<1184, 256, 0, s>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
+  ++tls_launches;
+  tick(ws, s, "state_update");
+  EvapArgs ea{nchunks, ncol, t1, pmid, pdel, q1, landfrac, rprd, cld, ev_s, snwprd, snwevmlt, ev_q,
+              prec, snow, ntprprd, ntsnprd, flxprec, flxsnow, ztodt};
+  rc = evap_launch(s, ea);
+  if (rc) return rc;
+  tick(ws, s, "zm_conv_evap");
+  MomArgs ma;
+  ma.nchunks = nchunks; ma.ncnst = 2; ma.ncol = ncol; ma.jt = jt; ma.mx = maxg; ma.ideep = ideep;
+  ma.lengath = lengath; ma.ktm = nullptr; ma.kbm = nullptr; ma.domom[0] = 1; ma.domom[1] = 1;
+  ma.q = winds; ma.mu = mu; ma.md = md; ma.du = du; ma.eu = eu; ma.ed = ed; ma.dp = dp;
+  ma.dqdt = wtend; ma.pguall = pgu; ma.pgdall = pgd; ma.icwu = icwu; ma.icwd = icwd; ma.seten = seten;
+  ma.dt = ztodt;
+  rc = momtran_launch(ws, s, ma, false);
+  if (rc) return rc;
+  tick(ws, s, "momtran");
+  k_tend_finalize<<<1184, 256, 0, s>>>((int)n2, (int)n2p, nper, heat, qtnd, ev_s, ev_q, seten, wtend, ptend_s,
+                                       ptend_q, ptend_u, ptend_v, evapcdp, mcon);
+  ++tls_launches;
+  tick(ws, s, "tend_finalize");
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
+                       const double* v, const double* pmid, const double* pint, const double* pdel,
+                       const double* zm, const double* zi, const double* phis, const double* pblh,
+                       const double* tpert, const double* landfrac, const double* cld, double ztodt,
+                       double* ptend_s, double* ptend_q, double* ptend_u, double* ptend_v, double* mcon,
+                       double* cme, double* pflx, double* zdu, double* rliq, double* rice, double* jctop,
+                       double* jcbot, double* prec, double* snow, double* ql, double* rprd, double* evapcdp,
+                       double* flxprec, double* flxsnow, double* dlf, double* mu, double* md, double* du,
+                       double* eu, double* ed, double* dp, double* dsubcld, int* jt, int* maxg, int* ideep,
+                       int* lengath, double* cape) {
+  NEED_INIT();
+  if (nchunks <= 0) return 0;
+  const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc;
+  const size_t n2 = nc * L, n2p = nc * (L + 1);
+  Workspace& st = tls_stage;
+  if (st.ensure(al(nchunks, 4) + 24 * al(n2, 8) + 6 * al(n2p, 8) + 14 * al(nc, 8) + 4 * al(nc, 4) + 8192))
+    return -100;
+  Stager S(st);
+  const int* d_ncol = S.in(ncol, nchunks);
+  const double *d_t = S.in(t, n2), *d_q = S.in(q, n2), *d_u = S.in(u, n2), *d_v = S.in(v, n2),
+               *d_pmid = S.in(pmid, n2), *d_pint = S.in(pint, n2p), *d_pdel = S.in(pdel, n2),
+               *d_zm = S.in(zm, n2), *d_zi = S.in(zi, n2p), *d_phis = S.in(phis, nc),
+               *d_pblh = S.in(pblh, nc), *d_tpert = S.in(tpert, nc), *d_lf = S.in(landfrac, nc),
+               *d_cld = S.in(cld, n2);
+  int rc = zm_conv_tend_batch_dev(
+      nchunks, d_ncol, d_t, d_q, d_u, d_v, d_pmid, d_pint, d_pdel, d_zm, d_zi, d_phis, d_pblh, d_tpert, d_lf,
+      d_cld, ztodt, S.out(ptend_s, n2), S.out(ptend_q, n2), S.out(ptend_u, n2), S.out(ptend_v, n2),
+      S.out(mcon, n2p), S.out(cme, n2), S.out(pflx, n2p), S.out(zdu, n2), S.out(rliq, nc), S.out(rice, nc),
+      S.out(jctop, nc), S.out(jcbot, nc), S.out(prec, nc), S.out(snow, nc), S.out(ql, n2), S.out(rprd, n2),
+      S.out(evapcdp, n2), S.out(flxprec, n2p), S.out(flxsnow, n2p), S.out(dlf, n2), S.out(mu, n2),
+      S.out(md, n2), S.out(du, n2), S.out(eu, n2), S.out(ed, n2), S.out(dp, n2), S.out(dsubcld, nc),
+      S.out(jt, nc), S.out(maxg, nc), S.out(ideep, nc), S.out(lengath, (size_t)nchunks), S.out(cape, nc),
+      (void*)st.stream);
+  if (rc) return rc;
+  if (S.flush()) return -100;
+  return read_failures(tls_work, st.stream);
+}
+
+// Per-rank budget terms for the global conservation check (device pointers; out6 on device):
+// [0] sum pdel/g*ptend_q  [1] sum 1000*(prec+rliq)  [2] sum pdel/g*ptend_s
+// [3] sum 1000*(latvap*(prec+rliq)+latice*snow)  [4] convective columns  [5] columns
+int zm_conservation_dev(int nchunks, const int* ncol, const double* pdel, const double* ptend_q,
+                        const double* ptend_s, const double* prec, const double* snow, const double* rliq,
+                        const int* lengath, double* out6, void* stream) {
+  NEED_INIT();
+  static thread_local double* partial = nullptr;
+  const int nb = 296;
+  if (!partial) CK(cudaMalloc(&partial, nb * 6 * sizeof(double)));
+  Workspace& ws = tls_work;
+  if (!ws.stream && ws.ensure(0)) return -100;
+  cudaStream_t s = stream ? (cudaStream_t)stream : ws.stream;
+  k_conservation_partial<<<nb, 128, 0, s>>>(nchunks, ncol, pdel, ptend_q, ptend_s, prec, snow, rliq, lengath, partial);
+  k_conservation_final<<<1, 32, 0, s>>>(nb, partial, out6);
+  tls_launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // ---- diagnostics ---------------------------------------------------------------------------------
 int zm_math_eval_host(int id, int n, const double* x, const double* y, double* o) {
   for (int i = 0; i < n; ++i) {
@@ -623,6 +839,19 @@ int zm_thermo_eval_dev(int id, int n, const double* a, const double* b, const do
   k_thermo_eval<<<(n + 127) / 128, 128, 0, st.stream>>>(id, n, da, db, dc, dd, de, o0, o1); ++tls_launches;
   CK(cudaGetLastError());
   return S.flush();
+}
+
+// cycles per dependent call, one warp: 0 div,1 log,2 log10,3 pow10,4 exp,5 goff-gratch,
+// 6 enthalpy,7 entropy,8 ienthalpy,9 ientropy,10 pow
+int zm_microbench(long long* cycles11, int n) {
+  NEED_INIT();
+  double* d; long long* c;
+  CK(cudaMalloc(&d, 32 * sizeof(double))); CK(cudaMalloc(&c, 16 * sizeof(long long)));
+  CK(cudaMemset(c, 0, 16 * sizeof(long long)));
+  k_microbench<<<1, 32>>>(d, c, n); ++tls_launches;
+  CK(cudaMemcpy(cycles11, c, 11 * sizeof(long long), cudaMemcpyDeviceToHost));
+  cudaFree(d); cudaFree(c);
+  return 0;
 }
 
 double zm_fp64_peak_flops(int iters) {

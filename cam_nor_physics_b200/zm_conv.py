@@ -70,6 +70,7 @@ EXPORTS = [
     "zm_params_default", "zm_init", "zm_finalize", "zm_last_error", "zm_convr_batch",
     "zm_convr_batch_dev", "zm_conv_evap_batch", "zm_conv_evap_batch_dev", "zm_momtran_batch",
     "zm_momtran_batch_dev", "zm_convtran_batch", "zm_convtran_batch_dev", "zm_sync_check",
+    "zm_conv_tend_batch", "zm_conv_tend_batch_dev", "zm_microbench", "zm_conservation_dev",
     "zm_math_eval_dev", "zm_math_eval_host", "zm_thermo_eval_dev", "zm_fp64_peak_flops",
     "zm_set_profiling", "zm_get_kernel_times", "zm_launch_count",
 ]
@@ -227,6 +228,47 @@ def convtran(doconvtran, q, mu, md, du, eu, ed, dp, dsubcld, jt, mx, ideep, leng
         _dp(fracis), _dp(dqdt), _dp(dpdry), C.c_double(dt), _ip(_i(cnst_is_dry)))
     _check(rc, "convtran")
     return dqdt
+
+
+TEND_OUT_2D = ["ptend_s", "ptend_q", "ptend_u", "ptend_v", "cme", "zdu", "ql", "rprd", "evapcdp", "dlf",
+               "mu", "md", "du", "eu", "ed", "dp"]
+TEND_OUT_2DP = ["mcon", "pflx", "flxprec", "flxsnow"]
+TEND_OUT_1D = ["rliq", "rice", "jctop", "jcbot", "prec", "snow", "dsubcld", "cape"]
+TEND_OUT_INT = ["jt", "maxg", "ideep"]
+# order of the output pointers in zm_conv_tend_batch[_dev] (include/zmconv_b200.h)
+TEND_ARG_ORDER = ["ptend_s", "ptend_q", "ptend_u", "ptend_v", "mcon", "cme", "pflx", "zdu", "rliq", "rice",
+                  "jctop", "jcbot", "prec", "snow", "ql", "rprd", "evapcdp", "flxprec", "flxsnow", "dlf",
+                  "mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg", "ideep", "lengath", "cape"]
+TEND_IN_ORDER = ["t", "q", "u", "v", "pmid", "pint", "pdel", "zm", "zi", "phis", "pblh", "tpert",
+                 "landfrac", "cld"]
+
+
+def zm_conv_tend(ncol, state: dict, ztodt: float, out: dict | None = None):
+    """zm_conv_tend (zm_conv_intr.F90:390) over host arrays: zm_convr -> physics_update ->
+    zm_conv_evap -> momtran with everything resident on the device in between.
+    `state` holds t,q,u,v,pmid,pint,pdel,zm,zi,phis,pblh,tpert,landfrac,cld in chunk layout."""
+    pc, L = _grid()
+    ncol = _i(ncol)
+    nch = ncol.shape[0]
+    if out is None:
+        out = {}
+        for k in TEND_OUT_2D:
+            out[k] = np.zeros((nch, L, pc))
+        for k in TEND_OUT_2DP:
+            out[k] = np.zeros((nch, L + 1, pc))
+        for k in TEND_OUT_1D:
+            out[k] = np.zeros((nch, pc))
+        for k in TEND_OUT_INT:
+            out[k] = np.zeros((nch, pc), np.int32)
+        out["lengath"] = np.zeros(nch, np.int32)
+    ins = [_f(state[k]) for k in TEND_IN_ORDER]
+    args = [C.c_int(nch), _ip(ncol)] + [_dp(a) for a in ins] + [C.c_double(ztodt)]
+    for k in TEND_ARG_ORDER:
+        a = out[k]
+        args.append(_ip(a) if a.dtype == np.int32 else _dp(a))
+    rc = lib().zm_conv_tend_batch(*args)
+    _check(rc, "zm_conv_tend")
+    return out
 
 
 # ---- diagnostics ---------------------------------------------------------------------------------

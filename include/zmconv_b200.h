@@ -120,6 +120,45 @@ int zm_convtran_batch_dev(int nchunks, const int* doconvtran, const double* q, i
                       const double* fracis, double* dqdt, const double* dpdry, double dt,
                       const int* cnst_is_dry, void* stream);
 
+/* The reference's driver for this path, zm_conv_tend (zm_conv_intr.F90:390-951), batched and kept on
+ * the device end to end: zm_convr (delt = 0.5*ztodt, :666) -> physics_update of state1 (t += s*dt/cpair,
+ * q(:,:,1) += qtnd*dt clipped at qmin=1e-12; physics_types.F90:322-329,427) -> zm_conv_evap (:764) ->
+ * momtran on (u,v) (:822) -> ptend_all = sum of the three ptend_loc (:736,803,833).  mcon is returned
+ * in kg/m2/s (:693).  convtran1 (:875), zm_org and zmconv_microp are separate / out of scope.
+ * State in: t,q(wv),u,v,pmid,pint,pdel,zm,zi,phis + pblh,tpert,landfrac,cld(pbuf 'CLD').
+ * Out: ptend_all%s,q(:,:,1),u,v; the dummy outputs mcon,cme,pflx,zdu,rliq,rice,jctop,jcbot; and the
+ * pbuf fields the reference fills (prec_dp, snow_dp, icwmrdp=ql, rprddp=rprd, nevapr_dpcu=evapcdp,
+ * DP_FLXPRC/SNW, dlfzm, ZM_MU..ZM_IDEEP) + cape + lengath. */
+int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
+                       const double* v, const double* pmid, const double* pint, const double* pdel,
+                       const double* zm, const double* zi, const double* phis, const double* pblh,
+                       const double* tpert, const double* landfrac, const double* cld, double ztodt,
+                       double* ptend_s, double* ptend_q, double* ptend_u, double* ptend_v, double* mcon,
+                       double* cme, double* pflx, double* zdu, double* rliq, double* rice, double* jctop,
+                       double* jcbot, double* prec, double* snow, double* ql, double* rprd, double* evapcdp,
+                       double* flxprec, double* flxsnow, double* dlf, double* mu, double* md, double* du,
+                       double* eu, double* ed, double* dp, double* dsubcld, int* jt, int* maxg, int* ideep,
+                       int* lengath, double* cape);
+int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
+                       const double* v, const double* pmid, const double* pint, const double* pdel,
+                       const double* zm, const double* zi, const double* phis, const double* pblh,
+                       const double* tpert, const double* landfrac, const double* cld, double ztodt,
+                       double* ptend_s, double* ptend_q, double* ptend_u, double* ptend_v, double* mcon,
+                       double* cme, double* pflx, double* zdu, double* rliq, double* rice, double* jctop,
+                       double* jcbot, double* prec, double* snow, double* ql, double* rprd, double* evapcdp,
+                       double* flxprec, double* flxsnow, double* dlf, double* mu, double* md, double* du,
+                       double* eu, double* ed, double* dp, double* dsubcld, int* jt, int* maxg, int* ideep,
+                       int* lengath, double* cape, void* stream);
+
+/* Per-rank terms of the global water/energy budget check (the quantities check_energy_chng compares
+ * after ZM, physpkg.F90:2865-2867); all pointers are device pointers, out6 receives
+ * [sum pdel/g*ptend_q, sum 1000*(prec+rliq), sum pdel/g*ptend_s,
+ *  sum 1000*(latvap*(prec+rliq)+latice*snow), #convective columns, #columns].
+ * Multi-GPU runs all-reduce these six doubles over NCCL; nothing else crosses GPUs. */
+int zm_conservation_dev(int nchunks, const int* ncol, const double* pdel, const double* ptend_q,
+                        const double* ptend_s, const double* prec, const double* snow, const double* rliq,
+                        const int* lengath, double* out6, void* stream);
+
 /* Synchronises `stream` (NULL = the calling thread's library stream) and returns the number of
  * Brent non-convergence events of this thread's last zm_convr_batch_dev call (0 = clean). */
 int zm_sync_check(void* stream);
@@ -136,6 +175,9 @@ int zm_thermo_eval_dev(int id, int n, const double* a, const double* b, const do
                        const double* d, const double* e, double* out0, double* out1);
 /* FP64 FMA-chain microbenchmark on the current device: returns achieved FLOP/s (FMA = 2). */
 double zm_fp64_peak_flops(int iters);
+/* single-warp latency microbenchmark: cycles per dependent call of
+ * 0 div,1 log,2 log10,3 10**x,4 exp,5 Goff-Gratch es,6 enthalpy,7 entropy,8 ienthalpy,9 ientropy,10 pow */
+int zm_microbench(long long* cycles11, int n);
 /* per-kernel device time (ms) of the last zm_convr_batch[_dev] call made with profiling on:
  * names/ms arrays of length *n (max 16). */
 int zm_set_profiling(int on);

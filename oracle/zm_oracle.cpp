@@ -1962,4 +1962,86 @@ int zmo_convr_batch(int nchunks, const int* ncol, const double* t, const double*
   return fails;
 }
 
+// ---- zm_conv_tend sequence (zm_conv_intr.F90:662-836), one chunk ------------------------------
+// zm_convr(delt=0.5*ztodt) -> mcon unit conversion (:693) -> physics_update(state1) [t, q(:,:,1) with
+// the external qneg3 clip at qmin(1)=1e-12; physics_types.F90:322-329,427] -> zm_conv_evap (:764) ->
+// momtran (:822) -> ptend_all = physics_ptend_sum of the three ptend_loc (:736,803,833).
+static int conv_tend_chunk(int lchnk, int ncol, const double* t, const double* q, const double* u,
+                           const double* v, const double* pmid, const double* pint, const double* pdel,
+                           const double* zm, const double* zi, const double* phis, const double* pblh,
+                           const double* tpert, const double* landfrac, const double* cld, double ztodt,
+                           double* ptend_s, double* ptend_q, double* ptend_u, double* ptend_v, double* mcon,
+                           double* cme, double* pflx, double* zdu, double* rliq, double* rice, double* jctop,
+                           double* jcbot, double* prec, double* snow, double* ql, double* rprd,
+                           double* evapcdp, double* flxprec, double* flxsnow, double* dlf, double* mu,
+                           double* md, double* du, double* eu, double* ed, double* dp, double* dsubcld,
+                           int* jt, int* maxg, int* ideep, int* lengath, double* cape) {
+  const int pcols = g.pcols, pver = g.pver, pverp = g.pverp;
+  const size_t n2 = (size_t)pcols * pver;
+  std::vector<double> heat(n2), qtnd(n2), eurt(n2), dif(n2), dnlf(n2), dnif(n2), t1(n2), q1(n2), ev_s(n2),
+      ev_q(n2), snwprd(n2), snwevmlt(n2), ntprprd(n2), ntsnprd(n2), seten(n2), winds(2 * n2), wtend(2 * n2),
+      pgu(2 * n2), pgd(2 * n2), icwu(2 * n2), icwd(2 * n2);
+  int fails = convr(lchnk, ncol, t, q, prec, jctop, jcbot, pblh, zm, phis, zi, qtnd.data(), heat.data(), pmid,
+                    pint, pdel, 0.5 * ztodt, mcon, cme, cape, eurt.data(), tpert, dlf, pflx, zdu, rprd, mu, md,
+                    du, eu, ed, dp, dsubcld, jt, maxg, ideep, lengath, ql, rliq, landfrac, dif.data(),
+                    dnlf.data(), dnif.data(), rice);
+  for (int k = 1; k <= pverp; ++k)
+    for (int i = 1; i <= ncol; ++i) {
+      size_t e = (size_t)(i - 1) + (size_t)pcols * (k - 1);
+      mcon[e] = mcon[e] * 100.0 / g.gravit;
+    }
+  for (size_t e = 0; e < n2; ++e) {
+    t1[e] = t[e] + heat[e] * ztodt / g.cpair;
+    double qn = q[e] + qtnd[e] * ztodt;
+    q1[e] = (qn < 1.e-12) ? 1.e-12 : qn;
+    winds[e] = u[e];
+    winds[n2 + e] = v[e];
+  }
+  zmo_conv_evap(ncol, lchnk, t1.data(), pmid, pdel, q1.data(), landfrac, ev_s.data(), snwprd.data(),
+                snwevmlt.data(), ev_q.data(), rprd, cld, ztodt, prec, snow, ntprprd.data(), ntsnprd.data(),
+                flxprec, flxsnow);
+  const int domom[2] = {1, 1};
+  zmo_momtran(lchnk, ncol, domom, winds.data(), 2, mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, 1,
+              *lengath, 0, wtend.data(), pgu.data(), pgd.data(), icwu.data(), icwd.data(), ztodt, seten.data());
+  for (size_t e = 0; e < n2; ++e) {
+    ptend_s[e] = (heat[e] + ev_s[e]) + seten[e];
+    ptend_q[e] = qtnd[e] + ev_q[e];
+    ptend_u[e] = wtend[e];
+    ptend_v[e] = wtend[n2 + e];
+    evapcdp[e] = ev_q[e];
+  }
+  return fails;
+}
+
+int zmo_conv_tend_batch(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
+                        const double* v, const double* pmid, const double* pint, const double* pdel,
+                        const double* zm, const double* zi, const double* phis, const double* pblh,
+                        const double* tpert, const double* landfrac, const double* cld, double ztodt,
+                        double* ptend_s, double* ptend_q, double* ptend_u, double* ptend_v, double* mcon,
+                        double* cme, double* pflx, double* zdu, double* rliq, double* rice, double* jctop,
+                        double* jcbot, double* prec, double* snow, double* ql, double* rprd, double* evapcdp,
+                        double* flxprec, double* flxsnow, double* dlf, double* mu, double* md, double* du,
+                        double* eu, double* ed, double* dp, double* dsubcld, int* jt, int* maxg, int* ideep,
+                        int* lengath, double* cape, int nthreads) {
+  const size_t pc = g.pcols, L = (size_t)g.pcols * g.pver, Lp = (size_t)g.pcols * g.pverp;
+  int fails = 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+  (void)nthreads;
+#endif
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : fails)
+  for (int c = 0; c < nchunks; ++c) {
+    fails += conv_tend_chunk(
+        c + 1, ncol[c], t + c * L, q + c * L, u + c * L, v + c * L, pmid + c * L, pint + c * Lp, pdel + c * L,
+        zm + c * L, zi + c * Lp, phis + c * pc, pblh + c * pc, tpert + c * pc, landfrac + c * pc, cld + c * L,
+        ztodt, ptend_s + c * L, ptend_q + c * L, ptend_u + c * L, ptend_v + c * L, mcon + c * Lp, cme + c * L,
+        pflx + c * Lp, zdu + c * L, rliq + c * pc, rice + c * pc, jctop + c * pc, jcbot + c * pc, prec + c * pc,
+        snow + c * pc, ql + c * L, rprd + c * L, evapcdp + c * L, flxprec + c * Lp, flxsnow + c * Lp,
+        dlf + c * L, mu + c * L, md + c * L, du + c * L, eu + c * L, ed + c * L, dp + c * L, dsubcld + c * pc,
+        jt + c * pc, maxg + c * pc, ideep + c * pc, lengath + c, cape + c * pc);
+  }
+  return fails;
+}
+
 }  // extern "C"

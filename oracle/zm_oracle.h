@@ -110,6 +110,19 @@ int zmo_convr_batch(int nchunks, const int* ncol,
                     double* ql, double* rliq, const double* landfrac,
                     double* dif, double* dnlf, double* dnif, double* rice, int nthreads);
 
+/* zm_conv_tend sequence (zm_conv_intr.F90:662-836) chunk by chunk under OpenMP: zm_convr ->
+ * physics_update(state1) -> zm_conv_evap -> momtran -> ptend_all sums; mcon in kg/m2/s. */
+int zmo_conv_tend_batch(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
+                        const double* v, const double* pmid, const double* pint, const double* pdel,
+                        const double* zm, const double* zi, const double* phis, const double* pblh,
+                        const double* tpert, const double* landfrac, const double* cld, double ztodt,
+                        double* ptend_s, double* ptend_q, double* ptend_u, double* ptend_v, double* mcon,
+                        double* cme, double* pflx, double* zdu, double* rliq, double* rice, double* jctop,
+                        double* jcbot, double* prec, double* snow, double* ql, double* rprd, double* evapcdp,
+                        double* flxprec, double* flxsnow, double* dlf, double* mu, double* md, double* du,
+                        double* eu, double* ed, double* dp, double* dsubcld, int* jt, int* maxg, int* ideep,
+                        int* lengath, double* cape, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

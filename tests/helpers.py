@@ -1,0 +1,88 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+from cam_nor_physics_b200 import soundings as S
+
+INT_KEYS = ["lengath", "ideep", "jt", "maxg"]
+GATHERED_2D = ["mu", "md", "du", "eu", "ed", "dp"]
+GATHERED_1D = ["dsubcld", "jt", "maxg"]
+RTOL, ATOL = 1e-10, 1e-14          # BASELINE.json north_star tolerance for r8 outputs
+
+
+def get_oracle(math, pcols, pver, **overrides):
+    from oracle_lib import Oracle
+    o = Oracle(math)
+    p = o.default_params(pcols, pver, S.limcnv_for(pver))
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    rc = o.convi(p)
+    return o, p, rc
+
+
+def init_cuda(pcols, pver, **overrides):
+    from cam_nor_physics_b200 import zm_conv as Z
+    p = Z.default_params(pcols, pver, S.limcnv_for(pver))
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    Z.zm_init(p)
+    return Z
+
+
+def state_of(ch):
+    return dict(t=ch.t, q=ch.q, u=ch.u, v=ch.v, pmid=ch.pmid, pint=ch.pint, pdel=ch.pdel, zm=ch.zm, zi=ch.zi,
+                phis=ch.phis, pblh=ch.pblh, tpert=ch.tpert, landfrac=ch.landfrac, cld=ch.cld)
+
+
+def gather_mask(lengath, pcols):
+    return np.arange(pcols)[None, :] < np.asarray(lengath)[:, None]
+
+
+def masked(out, key, lengath, pcols):
+    """Gathered outputs are only defined for rows < lengath (reference leaves the rest undefined)."""
+    m = gather_mask(lengath, pcols)
+    a = out[key]
+    return a * (m[:, None, :] if a.ndim == 3 else m)
+
+
+def assert_same(out, ref, keys, pcols, exact=True, what=""):
+    bad = []
+    for k in keys:
+        a, b = out[k], ref[k]
+        if k in GATHERED_2D or k in GATHERED_1D:
+            a, b = masked(out, k, ref["lengath"], pcols), masked(ref, k, ref["lengath"], pcols)
+        if exact or a.dtype.kind == "i":
+            if not np.array_equal(a, b):
+                d = np.abs(a.astype(float) - b.astype(float))
+                bad.append(f"{k}: {int((a != b).sum())} elements differ (max abs {d.max():.3e})")
+        else:
+            if not np.allclose(a, b, rtol=RTOL, atol=ATOL):
+                d = np.abs(a - b)
+                bad.append(f"{k}: max abs {d.max():.3e}, max rel {(d / np.maximum(np.abs(b), 1e-300))[d > ATOL].max():.3e}")
+    assert not bad, what + " mismatch:\n  " + "\n  ".join(bad)
+
+
+def near_threshold_columns(cape, capelmt=70.0):
+    """Columns whose CAPE lies within 1e-12 relative of the trigger threshold (BASELINE: reported, not failed)."""
+    return np.argwhere(np.abs(cape / capelmt - 1.0) <= 1e-12)
+
+
+CONVR_KEYS = ["lengath", "ideep", "cape", "prec", "jctop", "jcbot", "qtnd", "heat", "mcon", "cme", "eurt", "dlf",
+              "pflx", "zdu", "rprd", "ql", "rliq", "rice", "mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt",
+              "maxg", "dif", "dnlf", "dnif"]
+TEND_KEYS = ["lengath", "ideep", "cape", "prec", "snow", "jctop", "jcbot", "ptend_s", "ptend_q", "ptend_u",
+             "ptend_v", "mcon", "cme", "pflx", "zdu", "rliq", "rice", "ql", "rprd", "evapcdp", "flxprec",
+             "flxsnow", "dlf", "mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg"]
+
+
+def cuda_convr(Z, ch):
+    return Z.zm_convr(ch.ncol, ch.t, ch.q, ch.pblh, ch.zm, ch.phis, ch.zi, ch.pmid, ch.pint, ch.pdel,
+                      0.5 * ch.ztodt, ch.tpert, ch.landfrac)
+
+
+def dpdry_gathered(ch, ref, pdeldry):
+    """dpdry(i,:) = pdeldry(ideep(i),:)/100 (zm_conv_intr.F90:1014-1017)."""
+    dpdry = np.zeros_like(ch.pdel)
+    for c in range(ch.nchunks):
+        n = int(ref["lengath"][c])
+        idx = ref["ideep"][c][:n] - 1
+        dpdry[c][:, :n] = pdeldry[c][:, idx] / 100.0
+    return dpdry

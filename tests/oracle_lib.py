@@ -191,3 +191,33 @@ class Oracle:
                              C.c_int(0), _dp(o["dqdt"]), _dp(o["pguall"]), _dp(o["pgdall"]), _dp(o["icwu"]),
                              _dp(o["icwd"]), C.c_double(dt), _dp(o["seten"]))
         return o
+
+    def conv_tend_batch(self, ch, nthreads=0):
+        """zm_conv_tend sequence on soundings.Chunks; same output names as zm_conv.zm_conv_tend."""
+        P = self.params
+        nch, L, pc = ch.nchunks, P.pver, P.pcols
+        out = {}
+        for k in ["ptend_s", "ptend_q", "ptend_u", "ptend_v", "cme", "zdu", "ql", "rprd", "evapcdp", "dlf",
+                  "mu", "md", "du", "eu", "ed", "dp"]:
+            out[k] = np.zeros((nch, L, pc))
+        for k in ["mcon", "pflx", "flxprec", "flxsnow"]:
+            out[k] = np.zeros((nch, L + 1, pc))
+        for k in ["rliq", "rice", "jctop", "jcbot", "prec", "snow", "dsubcld", "cape"]:
+            out[k] = np.zeros((nch, pc))
+        for k in ["jt", "maxg", "ideep"]:
+            out[k] = np.zeros((nch, pc), np.int32)
+        out["lengath"] = np.zeros(nch, np.int32)
+        order = ["ptend_s", "ptend_q", "ptend_u", "ptend_v", "mcon", "cme", "pflx", "zdu", "rliq", "rice",
+                 "jctop", "jcbot", "prec", "snow", "ql", "rprd", "evapcdp", "flxprec", "flxsnow", "dlf",
+                 "mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg", "ideep", "lengath", "cape"]
+        ins = [ch.t, ch.q, ch.u, ch.v, ch.pmid, ch.pint, ch.pdel, ch.zm, ch.zi, ch.phis, ch.pblh, ch.tpert,
+               ch.landfrac, ch.cld]
+        ins = [_f(a) for a in ins]
+        ncol = np.ascontiguousarray(ch.ncol, dtype=np.int32)
+        args = [C.c_int(nch), _ip(ncol)] + [_dp(a) for a in ins] + [C.c_double(ch.ztodt)]
+        for k in order:
+            a = out[k]
+            args.append(_ip(a) if a.dtype == np.int32 else _dp(a))
+        args.append(C.c_int(nthreads))
+        out["rc"] = self.lib.zmo_conv_tend_batch(*args)
+        return out

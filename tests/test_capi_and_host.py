@@ -1,0 +1,79 @@
+"""CPU tests of the product's host side: the C-ABI library builds for sm_100a, loads without a GPU and
+exports every symbol include/zmconv_b200.h declares; portable math accuracy; soundings generator."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cam_nor_physics_b200 import soundings as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    from cam_nor_physics_b200 import zm_conv as Z
+    hdr = open(os.path.join(ROOT, "include", "zmconv_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(?:int|void|double|long long)\s+(zm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    lib = Z.lib()
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(Z.EXPORTS) <= names | {"zm_params_default"}
+
+
+def test_sm100a_code_is_embedded(built):
+    import subprocess
+    from cam_nor_physics_b200 import build
+    out = subprocess.run(["cuobjdump", "-lelf", build.LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_uninitialised_call_fails_loudly(built):
+    from cam_nor_physics_b200 import zm_conv as Z
+    Z.lib().zm_finalize()
+    rc = Z.lib().zm_sync_check(None)
+    assert rc == 0
+    buf = np.zeros(4)
+    rc = Z.lib().zm_thermo_eval_dev(0, 1, *(buf.ctypes.data_as(ctypes.c_void_p),) * 7)
+    assert rc == -1 and "zm_init" in Z.last_error()
+
+
+def test_portable_math_accuracy_host(built):
+    """zm_math.h (host build inside the library) is < 1 ulp against mpmath."""
+    import mpmath as mp
+    from cam_nor_physics_b200 import zm_conv as Z
+    mp.mp.prec = 120
+    rng = np.random.default_rng(11)
+    n = 3000
+    cases = [(0, np.exp(rng.uniform(-20, 20, n)), None, lambda x, y: mp.log(x)),
+             (1, rng.uniform(1.0, 3.0, n), None, lambda x, y: mp.log10(x)),
+             (2, rng.uniform(-30, 30, n), None, lambda x, y: mp.exp(x)),
+             (3, rng.uniform(-8, 8, n), None, lambda x, y: mp.power(10, x)),
+             (4, rng.uniform(0.9, 30, n), np.full(n, 287.04 / 1004.64), lambda x, y: mp.power(x, y))]
+    for fid, x, y, f in cases:
+        got = Z.math_eval(fid, x, y, device=False)
+        yy = x if y is None else y
+        worst = 0.0
+        for g, a, b in zip(got, x, yy):
+            e = f(mp.mpf(float(a)), mp.mpf(float(b)))
+            worst = max(worst, float(abs(mp.mpf(float(g)) - e) / math.ulp(float(e))))
+        assert worst < 1.0, (fid, worst)
+
+
+def test_soundings_are_shard_independent():
+    a = S.make_chunks(64, 32, 16, p_conv=0.5)
+    b = S.make_chunks(32, 32, 16, p_conv=0.5, col0=32)
+    for k in ["t", "q", "pmid", "pint", "zm", "zi", "u", "cld"]:
+        assert np.array_equal(getattr(a, k)[2:], getattr(b, k)), k
+    assert np.array_equal(a.phis[2:], b.phis)
+    assert S.limcnv_for(32) == 3
+    # hydrostatic and monotone
+    assert np.all(np.diff(a.pint, axis=1) > 0) and np.all(np.diff(a.zi, axis=1) < 0)
+    assert np.all(a.q >= 1e-12)
+    # ragged last chunk
+    c = S.make_chunks(40, 32, 16)
+    assert list(c.ncol) == [16, 16, 8]

@@ -1,0 +1,229 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI
+(include/zmconv_b200.h) via cam_nor_physics_b200.zm_conv.  The checker is the CPU oracle:
+  * oracle built with the same portable math header  -> bit-exact comparison of every output;
+  * oracle built with glibc libm / committed golden vectors -> integer outputs exact, r8 outputs within
+    1e-10 relative / 1e-14 absolute (BASELINE.json north_star), near-threshold columns reported."""
+import os
+
+import numpy as np
+import pytest
+
+from cam_nor_physics_b200 import soundings as S
+from helpers import (get_oracle, init_cuda, state_of, assert_same, cuda_convr, dpdry_gathered, CONVR_KEYS,
+                     TEND_KEYS, near_threshold_columns)
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_portable_math_device_equals_host(built):
+    from cam_nor_physics_b200 import zm_conv as Z
+    rng = np.random.default_rng(0)
+    n = 200000
+    for fid, x, y in [(0, np.exp(rng.uniform(-40, 40, n)), None), (1, rng.uniform(0.5, 4, n), None),
+                      (2, rng.uniform(-60, 60, n), None), (3, rng.uniform(-9, 9, n), None),
+                      (4, rng.uniform(0.3, 50, n), rng.uniform(-3, 3, n))]:
+        assert np.array_equal(Z.math_eval(fid, x, y, device=True), Z.math_eval(fid, x, y, device=False)), fid
+
+
+def test_thermo_scalars_match_oracle(built):
+    Z = init_cuda(16, 32)
+    o, _, _ = get_oracle("pm", 16, 32)
+    rng = np.random.default_rng(5)
+    n = 400
+    T = rng.uniform(190, 315, n); p = rng.uniform(100, 1020, n); q = rng.uniform(1e-6, 0.025, n)
+    z = rng.uniform(0, 1.6e4, n); tfg = T + rng.uniform(-6, 6, n)
+    s0, _ = Z.thermo_eval(0, T, p, q)
+    h0, _ = Z.thermo_eval(1, T, p, q, z)
+    assert np.array_equal(s0, [o.entropy(*a) for a in zip(T, p, q)])
+    assert np.array_equal(h0, [o.enthalpy(*a) for a in zip(T, p, q, z)])
+    t1, q1 = Z.thermo_eval(2, s0, p, q, tfg)
+    ref = [o.ientropy(*a) for a in zip(s0, p, q, tfg)]
+    assert np.array_equal(t1, [r[1] for r in ref]) and np.array_equal(q1, [r[2] for r in ref])
+    t2, q2 = Z.thermo_eval(3, h0, p, z, q, tfg)
+    ref = [o.ienthalpy(*a) for a in zip(h0, p, z, q, tfg)]
+    assert np.array_equal(t2, [r[1] for r in ref]) and np.array_equal(q2, [r[2] for r in ref])
+    es, qs = Z.thermo_eval(5, T, p * 100.0)
+    ref = [o.qsat_table(a, b * 100.0) for a, b in zip(T, p)]
+    assert np.array_equal(es, [r[0] for r in ref]) and np.array_equal(qs, [r[1] for r in ref])
+
+
+@pytest.mark.parametrize("ncols,pconv,pver,over", [
+    (16, 1.0, 32, {}),                          # BASELINE config 1: one pcols=16 chunk of tropical soundings
+    (4096, 0.5, 32, {}),                        # mixed grid
+    (1000, 0.6, 32, {}),                        # ragged: last chunk has 8 of 16 columns
+    (320, 0.0, 32, {}),                         # no convection anywhere (lengath = 0 in every chunk)
+    (2048, 0.6, 58, {"lparcel_pbl": 1}),        # L58 with the PBL-mixed launch parcel (BASELINE config 5 setup)
+    (1024, 0.7, 32, {"num_cin": 3}),            # several negative-buoyancy regions allowed
+    (1024, 0.7, 32, {"no_deep_pbl": 1}),
+    (1024, 0.7, 32, {"masterproc": 0, "dmpdz": -0.5e-3}),   # tentrm quirk (zm_conv.F90:213)
+])
+def test_zm_convr_bit_exact_vs_oracle(built, ncols, pconv, pver, over):
+    Z = init_cuda(16, pver, **over)
+    o, _, rc = get_oracle("pm", 16, pver, **over)
+    assert rc == 0
+    ch = S.make_chunks(ncols, pver, 16, p_conv=pconv)
+    ref = o.convr_batch(ch)
+    assert ref["rc"] == 0
+    out = cuda_convr(Z, ch)
+    assert_same(out, ref, CONVR_KEYS, 16, exact=True, what=f"zm_convr {ncols}x{pver} {over}")
+    if pconv == 0.0:
+        assert out["lengath"].sum() == 0
+    else:
+        assert out["lengath"].sum() > 0
+
+
+def test_large_pcols_chunk(built):
+    """pcols = 128 (CAM allows large pcols): compaction spans several warp sweeps."""
+    Z = init_cuda(128, 32)
+    o, _, _ = get_oracle("pm", 128, 32)
+    ch = S.make_chunks(128 * 6 - 37, 32, 128, p_conv=0.5)
+    ref = o.convr_batch(ch)
+    out = cuda_convr(Z, ch)
+    assert_same(out, ref, CONVR_KEYS, 128, exact=True, what="pcols=128")
+
+
+@pytest.mark.parametrize("name", ["config1_L32_pcols16", "mixed4_L32_pcols16"])
+def test_against_golden_vectors(built, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    Z = init_cuda(16, 32)
+    st = {k[3:]: g[k] for k in g.files if k.startswith("in_") and k[3:] in Z.TEND_IN_ORDER}
+    out = Z.zm_conv_tend(g["in_ncol"], st, float(g["in_ztodt"]))
+    ref = {k[5:]: g[k] for k in g.files if k.startswith("tend_")}
+    assert len(near_threshold_columns(ref["cape"])) == 0
+    assert_same(out, ref, TEND_KEYS, 16, exact=False, what=f"CUDA zm_conv_tend vs golden {name}")
+    dq = Z.convtran(g["in_doconvtran"], g["in_tracers"], ref["mu"], ref["md"], ref["du"], ref["eu"], ref["ed"],
+                    ref["dp"], ref["dsubcld"], ref["jt"], ref["maxg"], ref["ideep"], ref["lengath"],
+                    g["in_fracis"], g["in_dpdry"], float(g["in_ztodt"]), g["in_cnst_is_dry"])
+    assert np.allclose(dq, g["convtran_dqdt"], rtol=1e-10, atol=1e-30)
+
+
+def test_evap_momtran_convtran_bit_exact(built):
+    Z = init_cuda(16, 32)
+    o, p, _ = get_oracle("pm", 16, 32)
+    ch = S.make_chunks(1500, 32, 16, p_conv=0.6)
+    ref = o.convr_batch(ch)
+    nch = ch.nchunks
+    t1 = ch.t + ref["heat"] * ch.ztodt / p.cpair
+    q1 = np.maximum(ch.q + ref["qtnd"] * ch.ztodt, 1e-12)
+    ev = Z.zm_conv_evap(ch.ncol, t1, ch.pmid, ch.pdel, q1, ch.landfrac, ref["rprd"], ch.cld, ch.ztodt, ref["prec"])
+    for c in range(nch):
+        r = o.conv_evap(int(ch.ncol[c]), t1[c], ch.pmid[c], ch.pdel[c], q1[c], ch.landfrac[c], ref["rprd"][c],
+                        ch.cld[c], ch.ztodt, ref["prec"][c])
+        n = int(ch.ncol[c])
+        for k in r:
+            assert np.array_equal(ev[k][c][..., :n], r[k][..., :n]), (c, k)
+    winds = np.stack([ch.u, ch.v], axis=1)
+    mo = Z.momtran(ch.ncol, [1, 1], winds, ref["mu"], ref["md"], ref["du"], ref["eu"], ref["ed"], ref["dp"],
+                   ref["dsubcld"], ref["jt"], ref["maxg"], ref["ideep"], ref["lengath"], ch.ztodt)
+    for c in range(nch):
+        r = o.momtran(int(ch.ncol[c]), [1, 1], winds[c], ref["mu"][c], ref["md"][c], ref["du"][c], ref["eu"][c],
+                      ref["ed"][c], ref["dp"][c], ref["dsubcld"][c], ref["jt"][c], ref["maxg"][c], ref["ideep"][c],
+                      ref["lengath"][c], ch.ztodt)
+        n = int(ch.ncol[c])
+        for k in r:
+            assert np.array_equal(mo[k][c][..., :n], r[k][..., :n]), (c, k)
+    ncnst = 9
+    q, fracis, pdeldry = S.make_tracers(ch, ncnst)
+    do = [0, 1, 1, 0, 1, 1, 0, 1, 1]
+    dry = [0, 0, 1, 0, 0, 1, 1, 0, 1]
+    dpdry = dpdry_gathered(ch, ref, pdeldry)
+    sentinel = np.full_like(q, 7.25)
+    dq = Z.convtran(do, q, ref["mu"], ref["md"], ref["du"], ref["eu"], ref["ed"], ref["dp"], ref["dsubcld"],
+                    ref["jt"], ref["maxg"], ref["ideep"], ref["lengath"], fracis, dpdry, ch.ztodt, dry, dqdt=sentinel)
+    for c in range(nch):
+        r = o.convtran(do, q[c], ref["mu"][c], ref["md"][c], ref["du"][c], ref["eu"][c], ref["ed"][c], ref["dp"][c],
+                       ref["dsubcld"][c], ref["jt"][c], ref["maxg"][c], ref["ideep"][c], ref["lengath"][c],
+                       fracis[c], dpdry[c], ch.ztodt, dry)
+        for m in range(ncnst):
+            if do[m] and m >= 1:
+                assert np.array_equal(dq[c, m], r[m]), (c, m)
+            else:
+                assert np.all(dq[c, m] == 7.25)          # inactive constituents are not touched (zm_conv.F90:2298)
+    assert np.count_nonzero(dq[:, 1]) > 0
+    # lengath = 0 everywhere: transport returns zeros for active constituents
+    zero = np.zeros_like(ref["lengath"])
+    dq0 = Z.convtran(do, q, ref["mu"], ref["md"], ref["du"], ref["eu"], ref["ed"], ref["dp"], ref["dsubcld"],
+                     ref["jt"], ref["maxg"], ref["ideep"], zero, fracis, dpdry, ch.ztodt, dry)
+    assert np.all(dq0 == 0.0)
+
+
+def test_f09_full_step_vs_oracle(built):
+    """BASELINE configs 2-3 at full size: 55,296 columns L32 through zm_conv_tend (convr+evap+momtran)."""
+    Z = init_cuda(16, 32)
+    o, _, _ = get_oracle("pm", 16, 32)
+    ch = S.make_chunks(55296, 32, 16, p_conv=0.35)
+    ref = o.conv_tend_batch(ch)
+    assert ref["rc"] == 0
+    out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
+    assert_same(out, ref, TEND_KEYS, 16, exact=True, what="f09 zm_conv_tend")
+    frac = ref["lengath"].sum() / 55296
+    assert 0.2 < frac < 0.5
+    # and against the glibc-libm flavour (the gfortran-like one): tolerance of the north star
+    o2, _, _ = get_oracle("libm", 16, 32)
+    ref2 = o2.conv_tend_batch(ch)
+    near = near_threshold_columns(ref2["cape"])
+    print("near-threshold columns (reported):", near.tolist())
+    if len(near) == 0:
+        assert_same(out, ref2, TEND_KEYS, 16, exact=False, what="f09 zm_conv_tend vs libm oracle")
+
+
+def test_sharding_invariance_and_properties_L58_large(built):
+    """BASELINE config 5 shard (131,072 columns L58, 10-60% convective): size-independent properties --
+    chunk partition invariance, water closure, sorted ideep, zero rows outside the cloud."""
+    Z = init_cuda(16, 58, lparcel_pbl=1)
+    n = 131072
+    ch = S.make_chunks(n, 58, 16, p_conv=0.4)
+    out = cuda_convr(Z, ch)
+    half = n // 2
+    a = cuda_convr(Z, S.make_chunks(half, 58, 16, p_conv=0.4))
+    b = cuda_convr(Z, S.make_chunks(half, 58, 16, p_conv=0.4, col0=half))
+    for k in ["qtnd", "heat", "prec", "ideep", "lengath", "mu", "jt", "cape", "pflx"]:
+        assert np.array_equal(np.concatenate([a[k], b[k]]), out[k]), k
+    frac = out["lengath"].sum() / n
+    assert 0.1 < frac < 0.6
+    g = 9.80616
+    col = (ch.pdel * (out["qtnd"] + out["dlf"])).sum(axis=1) / g + 1000.0 * out["prec"]
+    conv = out["prec"] > 0
+    assert np.all(np.abs(col[conv]) <= 1e-10 * 1000.0 * out["prec"][conv] + 1e-18)
+    nz = np.arange(16)[None, :] < out["lengath"][:, None]
+    srt = np.where(nz, out["ideep"], 1 << 20)
+    assert np.all(np.diff(srt, axis=1)[nz[:, 1:]] > 0)
+    assert np.all(out["ideep"][~nz] == 0)
+    nonconv = np.ones((ch.nchunks, 16), bool)
+    ci, gi = np.nonzero(nz)
+    nonconv[ci, out["ideep"][ci, gi] - 1] = False
+    assert np.all(out["qtnd"].transpose(0, 2, 1)[nonconv] == 0.0)
+    assert np.all(out["jctop"][nonconv] == 58) and np.all(out["jcbot"][nonconv] == 1)
+
+
+def test_error_conventions(built):
+    from cam_nor_physics_b200 import zm_conv as Z
+    with pytest.raises(Z.ZmEndrun):
+        init_cuda(16, 32, num_cin=6)                       # zm_conv.F90:200
+    with pytest.raises(Z.ZmError):
+        init_cuda(16, 32, microp=1)
+    Z = init_cuda(16, 32)
+    ch = S.make_chunks(16, 32, 16)
+    t = ch.t.copy(); t[0, :, 3] = np.nan                  # NaN sounding -> Brent cannot converge -> endrun
+    with pytest.raises(Z.ZmEndrun) as e:
+        Z.zm_convr(ch.ncol, t, ch.q, ch.pblh, ch.zm, ch.phis, ch.zi, ch.pmid, ch.pint, ch.pdel, 900.0, ch.tpert, ch.landfrac)
+    assert "icol=4" in str(e.value)
+
+
+def test_device_resident_path_and_conservation(built):
+    import torch
+    from cam_nor_physics_b200.device import DeviceTend
+    Z = init_cuda(16, 32)
+    o, _, _ = get_oracle("pm", 16, 32)
+    ch = S.make_chunks(4096, 32, 16, p_conv=0.5)
+    ref = o.conv_tend_batch(ch)
+    dev = DeviceTend(ch)
+    dev.step(); cons = dev.conservation(); assert dev.check() == 0
+    for k in ["ptend_s", "ptend_q", "ptend_u", "prec", "snow", "mcon", "ideep", "lengath"]:
+        assert np.array_equal(dev.out[k].cpu().numpy(), ref[k]), k
+    c = cons.cpu().numpy()
+    g = 9.80616
+    assert np.isclose(c[0], (ch.pdel / g * ref["ptend_q"]).sum(), rtol=1e-12)
+    assert np.isclose(c[1], 1000.0 * (ref["prec"] + ref["rliq"]).sum(), rtol=1e-12)
+    assert c[4] == ref["lengath"].sum() and c[5] == 4096

@@ -1,0 +1,144 @@
+"""CPU tests of the oracle: golden vectors, property tests derived from the reference code
+(SURVEY.md section 4), agreement of the two math flavours, error conventions."""
+import os
+import numpy as np
+import pytest
+
+from cam_nor_physics_b200 import soundings as S
+from helpers import (get_oracle, state_of, assert_same, TEND_KEYS, CONVR_KEYS, masked, dpdry_gathered,
+                     near_threshold_columns, RTOL, ATOL)
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class _Ch:
+    """Rebuilds a soundings.Chunks-like object from a golden file."""
+    def __init__(self, g):
+        for k in ["t", "q", "u", "v", "pmid", "pint", "pdel", "zm", "zi", "phis", "pblh", "tpert", "landfrac", "cld"]:
+            setattr(self, k, g["in_" + k])
+        self.ncol = g["in_ncol"]; self.ztodt = float(g["in_ztodt"])
+        self.nchunks = self.t.shape[0]; self.pver = self.t.shape[1]; self.pcols = self.t.shape[2]
+        self.ncols_total = int(self.ncol.sum())
+
+
+@pytest.mark.parametrize("name", ["config1_L32_pcols16", "mixed4_L32_pcols16"])
+@pytest.mark.parametrize("math", ["libm", "pm"])
+def test_oracle_matches_golden(built, name, math):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    ch = _Ch(g)
+    o, p, rc = get_oracle(math, 16, 32)
+    assert rc == 0
+    out = o.conv_tend_batch(ch)
+    assert out["rc"] == 0
+    ref = {k[5:]: g[k] for k in g.files if k.startswith("tend_")}
+    # integer outputs exact; reals within the BASELINE tolerance (libm flavour reproduces bit for bit
+    # on the same glibc; the portable-math flavour differs by <= 1 ulp per transcendental)
+    assert_same(out, ref, TEND_KEYS, 16, exact=False, what=f"oracle[{math}] vs golden {name}")
+    cv = o.convr_batch(ch)
+    refc = {k[6:]: g[k] for k in g.files if k.startswith("convr_")}
+    assert_same(cv, refc, CONVR_KEYS, 16, exact=False, what=f"oracle[{math}] convr vs golden {name}")
+    dq = np.stack([o.convtran(g["in_doconvtran"], g["in_tracers"][c], ref["mu"][c], ref["md"][c], ref["du"][c],
+                              ref["eu"][c], ref["ed"][c], ref["dp"][c], ref["dsubcld"][c], ref["jt"][c],
+                              ref["maxg"][c], ref["ideep"][c], ref["lengath"][c], g["in_fracis"][c],
+                              g["in_dpdry"][c], ch.ztodt, g["in_cnst_is_dry"]) for c in range(ch.nchunks)])
+    assert np.allclose(dq, g["convtran_dqdt"], rtol=RTOL, atol=1e-30)
+
+
+def test_math_flavours_agree(built):
+    """oracle(glibc libm) vs oracle(portable zm_math.h): ints exact, reals within 1e-10 rel / 1e-14 abs."""
+    ch = S.make_chunks(16 * 40, 32, 16, p_conv=0.6)
+    a, _, _ = get_oracle("libm", 16, 32)
+    b, _, _ = get_oracle("pm", 16, 32)
+    ra, rb = a.conv_tend_batch(ch), b.conv_tend_batch(ch)
+    assert ra["rc"] == 0 and rb["rc"] == 0
+    assert len(near_threshold_columns(ra["cape"])) == 0
+    assert_same(rb, ra, TEND_KEYS, 16, exact=False, what="pm vs libm")
+
+
+def test_inverse_identities(oracle_libm):
+    """ienthalpy(enthalpy(T)) ~ T and ientropy(entropy(T)) ~ T within Brent's tol (zm_conv.F90:5027-5028,5342)."""
+    o = oracle_libm
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        T = rng.uniform(200.0, 310.0); p = rng.uniform(150.0, 1000.0); q = rng.uniform(1e-5, 0.02); z = rng.uniform(0, 1.5e4)
+        tfg = T + rng.uniform(-5, 5)
+        rc, t1, qs1 = o.ientropy(o.entropy(T, p, q), p, q, tfg)
+        assert rc == 0 and abs(t1 - T) < 2e-3
+        rc, t2, qs2 = o.ienthalpy(o.enthalpy(T, p, q, z), p, z, q, tfg)
+        assert rc == 0 and abs(t2 - T) < 2e-3
+        es, qs = o.qsat_hpa(t2, p)
+        assert qs == qs2            # T is a point where F was evaluated: qst is qsat_hPa(T,p)
+
+
+def test_water_closure_and_zero_rows(oracle_libm):
+    """prec = max(0, -sum dpp*dq - sum dpp*dlf*2dt)/(g*2dt*1000) (zm_conv.F90:1629-1638) =>
+    sum dpp*(qtnd+dlf)/g + 1000*prec = 0 when unclipped; rows above jt are exactly zero."""
+    o = oracle_libm
+    ch = S.make_chunks(16 * 20, 32, 16, p_conv=0.8)
+    r = o.convr_batch(ch)
+    g = o.params.gravit
+    col = (ch.pdel * (r["qtnd"] + r["dlf"])).sum(axis=1) / g + 1000.0 * r["prec"]
+    conv = r["prec"] > 0
+    assert conv.sum() > 50
+    assert np.all(np.abs(col[conv]) <= 1e-10 * 1000.0 * r["prec"][conv] + 1e-18)
+    for c in range(ch.nchunks):
+        for gi in range(int(r["lengath"][c])):
+            i = r["ideep"][c, gi] - 1
+            jt, mx = r["jt"][c, gi], r["maxg"][c, gi]
+            assert np.all(r["qtnd"][c, : jt - 1, i] == 0.0) and np.all(r["heat"][c, : jt - 1, i] == 0.0)
+            assert np.all(r["mu"][c, :jt, gi] == 0.0)          # mu(jt) = 0 (zm_conv.F90:3640-3644)
+            assert r["jctop"][c, i] == jt and r["jcbot"][c, i] == mx
+            # below the launch level tendencies repeat the launch-level value (zm_conv.F90:4413-4416)
+            assert np.all(r["qtnd"][c, mx - 1:, i] == r["qtnd"][c, mx - 1, i])
+    # ideep is strictly increasing over 1..lengath and zero beyond (zm_conv.F90:906-915)
+    for c in range(ch.nchunks):
+        n = int(r["lengath"][c])
+        assert np.all(np.diff(r["ideep"][c, :n]) > 0) and np.all(r["ideep"][c, n:] == 0)
+
+
+def test_no_convection_defaults(oracle_libm):
+    """lengath = 0 => all tendencies 0, jctop = pver, jcbot = 1 (zm_conv.F90:559-563, 781-782, 917)."""
+    o = oracle_libm
+    ch = S.make_chunks(32, 32, 16, p_conv=0.0)
+    r = o.convr_batch(ch)
+    assert r["lengath"].sum() == 0 and np.all(r["ideep"] == 0)
+    for k in ["qtnd", "heat", "mcon", "dlf", "pflx", "cme", "rprd", "zdu", "ql", "prec", "rliq", "eurt"]:
+        assert np.all(r[k] == 0.0), k
+    assert np.all(r["jctop"] == 32) and np.all(r["jcbot"] == 1)
+
+
+def test_transport_zero_outside_cloud(oracle_libm):
+    """convtran / momtran give exactly 0 tendency above jt and below mx (zm_conv.F90:2249-2252)."""
+    o = oracle_libm
+    ch = S.make_chunks(64, 32, 16, p_conv=0.7)
+    r = o.conv_tend_batch(ch)
+    q, fracis, pdeldry = S.make_tracers(ch, 4)
+    dpdry = dpdry_gathered(ch, r, pdeldry)
+    for c in range(ch.nchunks):
+        dq = o.convtran([0, 1, 1, 1], q[c], r["mu"][c], r["md"][c], r["du"][c], r["eu"][c], r["ed"][c], r["dp"][c],
+                        r["dsubcld"][c], r["jt"][c], r["maxg"][c], r["ideep"][c], r["lengath"][c], fracis[c],
+                        dpdry[c], ch.ztodt, [0, 0, 1, 0])
+        assert np.all(dq[0] == 0.0)                       # constituent 1 is never transported (m = 2, ncnst)
+        for gi in range(int(r["lengath"][c])):
+            i = r["ideep"][c, gi] - 1
+            jt, mx = r["jt"][c, gi], r["maxg"][c, gi]
+            assert np.all(dq[1:, : jt - 1, i] == 0.0) and np.all(dq[1:, mx:, i] == 0.0)
+            assert np.any(dq[1:, jt - 1: mx, i] != 0.0)
+        nonconv = np.setdiff1d(np.arange(16), r["ideep"][c][: r["lengath"][c]] - 1)
+        assert np.all(dq[:, :, nonconv] == 0.0)
+        assert np.all(r["ptend_u"][c][:, nonconv] == 0.0)
+
+
+def test_zm_convi_error_conventions(built):
+    _, _, rc = get_oracle("libm", 16, 32, num_cin=6)
+    assert rc != 0                                        # endrun: NUM_CIN must not exceed 5 (zm_conv.F90:200)
+    _, _, rc = get_oracle("libm", 16, 32, microp=1)
+    assert rc != 0                                        # zmconv_microp is out of scope
+    get_oracle("libm", 16, 32)
+
+
+def test_brent_failure_is_reported(built):
+    """Non-convergence is fatal in the reference (zm_conv.F90:5401-5410): the oracle returns a count."""
+    o, _, _ = get_oracle("libm", 16, 32)
+    rc, t, qs = o.ientropy(250.0, 900.0, 0.01, float("nan"))   # NaN first guess never converges
+    assert rc == 1
