@@ -71,7 +71,9 @@ __global__ void k_convr_init(ConvrIn in, ConvrOut o, ConvrWork w) {
   for (size_t e = tid; e < ncolpad * pverp; e += nth) { o.mcon[e] = 0.0; o.pflx[e] = 0.0; }
   for (size_t e = tid; e < ncolpad; e += nth) {
     o.prec[e] = 0.0; o.rliq[e] = 0.0; o.rice[e] = 0.0; o.cape[e] = 0.0; o.dsubcld[e] = 0.0;
-    o.jctop[e] = (double)pver; o.jcbot[e] = 1.0;
+    // jctop = pver, jcbot = 1 for i <= ncol (zm_conv.F90:781-782); padding lanes are zero-filled
+    const bool real_col = (int)(e % pcols) < in.ncol[e / pcols];
+    o.jctop[e] = real_col ? (double)pver : 0.0; o.jcbot[e] = real_col ? 1.0 : 0.0;
     o.jt[e] = 0; o.maxg[e] = 0; o.ideep[e] = 0;
     w.dmpdz[e] = -P.tentrm;
   }

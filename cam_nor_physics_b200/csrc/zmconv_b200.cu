@@ -483,8 +483,7 @@ int zm_get_kernel_times(int* n, const char** names, float* ms) {
 // sync the thread's stream and return the Brent failure count of the last zm_convr_batch_dev
 int zm_sync_check(void* stream) {
   Workspace& ws = tls_work;
-  cudaStream_t s = stream ? (cudaStream_t)stream : ws.stream;
-  if (!s) return 0;
+  cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
   return read_failures(ws, s);
 }
 
@@ -502,7 +501,7 @@ int zm_convr_batch_dev(int nchunks, const int* ncol, const double* t, const doub
   if (nchunks <= 0) return 0;
   Workspace& ws = tls_work;
   if (ws.ensure(0)) return -100;
-  cudaStream_t s = stream ? (cudaStream_t)stream : ws.stream;
+  cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
   ConvrIn in{nchunks, ncol, t, qh, pap, paph, dpp, zm, zi, geos, pblh, tpert, landfrac, delt};
   ConvrOut o{prec, jctop, jcbot, qtnd, heat, mcon, cme, cape, eurt, dlf, pflx, zdu, rprd,
              mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, lengath, ql, rliq, dif, dnlf, dnif, rice};
@@ -556,7 +555,7 @@ int zm_conv_evap_batch_dev(int nchunks, const int* ncol, const double* t, const 
   if (nchunks <= 0) return 0;
   Workspace& ws = tls_work;
   if (!ws.stream && ws.ensure(0)) return -100;
-  cudaStream_t s = stream ? (cudaStream_t)stream : ws.stream;
+  cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
   EvapArgs a{nchunks, ncol, t, pmid, pdel, q, landfrac, prdprec, cldfrc, tend_s, tend_s_snwprd,
              tend_s_snwevmlt, tend_q, prec, snow, ntprprd, ntsnprd, flxprec, flxsnow, deltat};
   return evap_launch(s, a);
@@ -602,7 +601,7 @@ int zm_momtran_batch_dev(int nchunks, const int* ncol, const int* domomtran, con
   if (ncnst != 2) { tls_err = "momtran: ncnst must be 2 (u,v), as at its only call site zm_conv_intr.F90:822"; return -6; }
   Workspace& ws = tls_work;
   if (!ws.stream && ws.ensure(0)) return -100;
-  cudaStream_t s = stream ? (cudaStream_t)stream : ws.stream;
+  cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
   MomArgs a;
   a.nchunks = nchunks; a.ncnst = ncnst; a.ncol = ncol; a.jt = jt; a.mx = mx; a.ideep = ideep;
   a.lengath = lengath; a.ktm = nullptr; a.kbm = nullptr;
@@ -654,7 +653,7 @@ int zm_convtran_batch_dev(int nchunks, const int* doconvtran, const double* q, i
   if (nchunks <= 0) return 0;
   Workspace& ws = tls_work;
   if (!ws.stream && ws.ensure(0)) return -100;
-  cudaStream_t s = stream ? (cudaStream_t)stream : ws.stream;
+  cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
   TranArgs a;
   a.nchunks = nchunks; a.ncnst = ncnst; a.nactive = 0; a.jt = jt; a.mx = mx; a.ideep = ideep;
   a.lengath = lengath; a.ktm = nullptr; a.kbm = nullptr; a.active = nullptr; a.is_dry = nullptr;
@@ -707,7 +706,7 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
   Workspace& ws = tls_work;
   if (ws.ensure(convr_work_bytes(nc, (int)L) + 18 * al(n2, 8) + 6 * al(2 * n2, 8) + 2 * al(nchunks, 4) + 8192))
     return -100;
-  cudaStream_t s = stream ? (cudaStream_t)stream : ws.stream;
+  cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
   double *heat = ws.take<double>(n2), *qtnd = ws.take<double>(n2), *eurt = ws.take<double>(n2),
          *dif = ws.take<double>(n2), *dnlf = ws.take<double>(n2), *dnif = ws.take<double>(n2),
          *t1 = ws.take<double>(n2), *q1 = ws.take<double>(n2), *ev_s = ws.take<double>(n2),
@@ -796,7 +795,7 @@ int zm_conservation_dev(int nchunks, const int* ncol, const double* pdel, const 
   if (!partial) CK(cudaMalloc(&partial, nb * 6 * sizeof(double)));
   Workspace& ws = tls_work;
   if (!ws.stream && ws.ensure(0)) return -100;
-  cudaStream_t s = stream ? (cudaStream_t)stream : ws.stream;
+  cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
   k_conservation_partial<<<nb, 128, 0, s>>>(nchunks, ncol, pdel, ptend_q, ptend_s, prec, snow, rliq, lengath, partial);
   k_conservation_final<<<1, 32, 0, s>>>(nb, partial, out6);
   tls_launches += 2;

@@ -14,7 +14,7 @@
  *
  * Every *_batch entry point takes HOST pointers and does its own H2D/D2H; the *_batch_dev
  * twins take DEVICE pointers and only enqueue work on `stream` (a cudaStream_t cast to void*,
- * NULL = the library's own stream) -- callers that keep physics_state resident use those.
+ * NULL = the CUDA default stream) -- callers that keep physics_state resident use those.
  * Return value: 0 on success; >0 = number of Brent non-convergence events (the reference's
  * endrun at zm_conv.F90:5401-5410, 5557-5566; details via zm_last_error); <0 = API/CUDA error.
  * The library is re-entrant across host threads after zm_init (per-thread workspaces).
@@ -159,7 +159,7 @@ int zm_conservation_dev(int nchunks, const int* ncol, const double* pdel, const 
                         const double* ptend_s, const double* prec, const double* snow, const double* rliq,
                         const int* lengath, double* out6, void* stream);
 
-/* Synchronises `stream` (NULL = the calling thread's library stream) and returns the number of
+/* Synchronises `stream` (NULL = the CUDA default stream) and returns the number of
  * Brent non-convergence events of this thread's last zm_convr_batch_dev call (0 = clean). */
 int zm_sync_check(void* stream);
 
