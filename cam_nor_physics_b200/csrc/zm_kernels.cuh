@@ -84,7 +84,7 @@ __global__ void k_convr_init(ConvrIn in, ConvrOut o, ConvrWork w) {
 // ---- buoyan_dilute + parcel_dilute, one thread per column ----------------------------------
 // zm_conv.F90:4425-4819 and 4824-5277.  PASS 1: every column.  PASS 2: worklist wl1 only.
 template <int PASS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   extern __shared__ double sm_buoy[];               // [pver+2][blockDim.x]
   const int pcols = P.pcols, pver = P.pver, msg = P.msg;

@@ -4,7 +4,7 @@
 // Host side: per-thread workspaces (device arena + stream), no global mutable state after
 // zm_init => re-entrant from OpenMP threads like the reference (physpkg.F90:1147-1161).
 #include "../../include/zmconv_b200.h"
-#include "zm_plume.cuh"
+#include "zm_plume_warp.cuh"
 #include "zm_transport.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -103,13 +103,14 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   const int nblk_cols = (int)((ncolpad + TB - 1) / TB);
   const size_t smem = (size_t)(pver + 2) * TB * sizeof(double);
   const int nwarpblk = (int)(((size_t)in.nchunks * 32 + 127) / 128);
-  const int PB = 64;
-  const int nblk_pl = (int)((ncolpad + PB - 1) / PB);
+  const int nblk_pl = (int)((ncolpad + PL_WARPS - 1) / PL_WARPS);     // one warp per convective column
+  const size_t smem_pl = plume_smem_bytes(pver);
+  CK(cudaFuncSetAttribute(k_cldprp_pass1_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
+  CK(cudaFuncSetAttribute(k_plume_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
   if (smem > 48 * 1024) {
     CK(cudaFuncSetAttribute(k_buoyan_dilute<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_buoyan_dilute<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  const int L = lmax_for(pver);
   tick(ws, s, "start");
   k_convr_init<<<592, 256, 0, s>>>(in, o, w); ++tls_launches;
   tick(ws, s, "convr_init");
@@ -117,18 +118,14 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   tick(ws, s, "buoyan_dilute_pass1");
   k_trigger<0><<<nwarpblk, 128, 0, s>>>(in, o, w); ++tls_launches;
   tick(ws, s, "trigger_pass1");
-  if (L == 32)       k_cldprp_pass1<32><<<nblk_pl, PB, 0, s>>>(in, w);
-  else if (L == 64)  k_cldprp_pass1<64><<<nblk_pl, PB, 0, s>>>(in, w);
-  else               k_cldprp_pass1<128><<<nblk_pl, PB, 0, s>>>(in, w);
+  k_cldprp_pass1_w<<<nblk_pl, 32 * PL_WARPS, smem_pl, s>>>(in, w);
   ++tls_launches;
   tick(ws, s, "cldprp_pass1");
   k_buoyan_dilute<2><<<nblk_cols, TB, smem, s>>>(in, w); ++tls_launches;
   tick(ws, s, "buoyan_dilute_pass2");
   k_trigger<1><<<nwarpblk, 128, 0, s>>>(in, o, w); ++tls_launches;
   tick(ws, s, "trigger_final");
-  if (L == 32)       k_plume<32><<<nblk_pl, PB, 0, s>>>(in, o, w);
-  else if (L == 64)  k_plume<64><<<nblk_pl, PB, 0, s>>>(in, o, w);
-  else               k_plume<128><<<nblk_pl, PB, 0, s>>>(in, o, w);
+  k_plume_w<<<nblk_pl, 32 * PL_WARPS, smem_pl, s>>>(in, o, w);
   ++tls_launches;
   tick(ws, s, "plume_closure_q1q2");
   CK(cudaGetLastError());
