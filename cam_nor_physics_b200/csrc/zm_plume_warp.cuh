@@ -20,7 +20,7 @@ enum PlumeArr {
   A_MU, A_EU, A_DU, A_MD, A_ED, A_SD, A_QD, A_MC, A_QU, A_SU, A_QST, A_HMN, A_HSAT, A_QL, A_CMEG,
   A_PFLX, A_EVP, A_CU, A_RPRD, A_QCDE,
   A_GAMMA, A_HU, A_HD, A_EPS, A_F, A_K1, A_I2, A_I3, A_I4, A_QSTHAT, A_HSTHAT, A_GAMHAT, A_QDS,
-  A_MCP, A_MRL, A_TU, A_TD, A_W1, A_W2, A_W3,
+  A_MCP, A_MRL, A_TU, A_TD, A_W1, A_W2, A_W3, A_DPP,
   A_COUNT
 };
 
@@ -42,7 +42,9 @@ __device__ __forceinline__ double gather_column_w(const PlumeSh& S, const ConvrI
   PAR(k, 1, pver) {
     size_t e = cidx(c, k - 1, i, pver);
     double qk = in.qh[e], tk = in.t[e];
-    S(A_DP, k) = 0.01 * in.dpp[e];
+    const double dppk = in.dpp[e];
+    S(A_DPP, k) = dppk;
+    S(A_DP, k) = 0.01 * dppk;
     S(A_Q, k) = qk;
     S(A_T, k) = tk;
     S(A_P, k) = in.pap[e] * 0.01;
@@ -676,15 +678,14 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
   // precipitation and reserved liquid (zm_conv.F90:1629-1649), serial sums in the reference's order
   double prec = 0.0, rliq = 0.0;
   for (int k = pver; k >= msg + 1; --k) {
-    const size_t e = cidx(c, k - 1, i, pver);
-    const double dppk = in.dpp[e], qhk = in.qh[e];
+    const double dppk = S(A_DPP, k), qhk = S(A_Q, k);
     const double qnew = qhk + 2.0 * delt * S(A_W2, k);
     prec = prec - dppk * (qnew - qhk) - dppk * (S(A_W3, k) + 0.0) * 2.0 * delt;
   }
   prec = P.rgrav * fmax2(prec, 0.0) / (2.0 * delt) / 1000.0;
   for (int k = 1; k <= pver; ++k) {
     const double dlfk = (k >= msg + 1) ? S(A_W3, k) : 0.0;
-    rliq = rliq + (dlfk + 0.0) * in.dpp[cidx(c, k - 1, i, pver)] / P.gravit;
+    rliq = rliq + (dlfk + 0.0) * S(A_DPP, k) / P.gravit;
   }
   rliq = rliq / 1000.0;
   if (lane == 0) {

@@ -121,116 +121,143 @@ __global__ void k_momtran_init(MomArgs a) {
   for (size_t e = tid; e < n2; e += nth) a.seten[e] = 0.0;
 }
 
-template <int LMAX>
-__global__ void __launch_bounds__(64)
-k_momtran(MomArgs a) {
+// One warp per gathered (convective) column, lane == level; the two order-dependent recurrences
+// (in-cloud updraft wind bottom-up, downdraft wind top-down; zm_conv.F90:2562-2589) run redundantly
+// on every lane in the reference's order, everything else is level parallel.
+#define MOM_WARPS 2
+enum MomArr { M_MU, M_MD, M_DU, M_EU, M_ED, M_DP, M_C, M_CHAT, M_CONU, M_COND, M_PGU, M_PGD, M_DCONDT,
+              M_MFLUX0, M_MFLUX1, M_WIND00, M_WIND01, M_WINDF0, M_WINDF1, M_COUNT };
+inline size_t momtran_smem_bytes(int pver) { return (size_t)MOM_WARPS * M_COUNT * (pver + 2) * sizeof(double); }
+
+__global__ void __launch_bounds__(32 * MOM_WARPS)
+k_momtran_w(MomArgs a) {
+  extern __shared__ double sm_mom[];
   const int pcols = P.pcols, pver = P.pver;
-  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int slot = blockIdx.x * MOM_WARPS + wib;
   if (slot >= a.nchunks * pcols) return;
   const int c = slot / pcols, gi = slot - c * pcols;
   if (gi >= a.lengath[c]) return;
+  const int ld = pver + 2;
+  double* B = sm_mom + (size_t)wib * M_COUNT * ld;
+#define MS(n, k) B[(n) * ld + (k)]
+#define MPAR(k, lo, hi) for (int k = (lo) + lane; k <= (hi); k += 32)
   const int ii = a.ideep[slot] - 1;            // ungathered column (0-based)
-  const int jt = a.jt[slot], mx = a.mx[slot];
-  (void)jt;
+  const int mx = a.mx[slot];
   const int ktm = a.ktm[c], kbm = a.kbm[c];
   const double mbsth = 1.e-15, dt = a.dt;
-  double mu[LMAX + 2], md[LMAX + 2], du[LMAX + 2], eu[LMAX + 2], ed[LMAX + 2], dp[LMAX + 2];
-  double cnst[LMAX + 2], chat[LMAX + 2], conu[LMAX + 2], cond[LMAX + 2], pgu[LMAX + 2], pgd[LMAX + 2],
-      dcondt[LMAX + 2];
-  double mflux[2][LMAX + 3], wind0[2][LMAX + 2], windf[2][LMAX + 2];
-  for (int k = 1; k <= pver; ++k) {
-    size_t e = cidx(c, k - 1, gi, pver);
-    mu[k] = a.mu[e]; md[k] = a.md[e]; du[k] = a.du[e]; eu[k] = a.eu[e]; ed[k] = a.ed[e]; dp[k] = a.dp[e];
+  MPAR(k, 1, pver + 1) {
+    if (k <= pver) {
+      const size_t e = cidx(c, k - 1, gi, pver);
+      MS(M_MU, k) = a.mu[e]; MS(M_MD, k) = a.md[e]; MS(M_DU, k) = a.du[e]; MS(M_EU, k) = a.eu[e];
+      MS(M_ED, k) = a.ed[e]; MS(M_DP, k) = a.dp[e];
+      MS(M_WIND00, k) = 0.0; MS(M_WIND01, k) = 0.0; MS(M_WINDF0, k) = 0.0; MS(M_WINDF1, k) = 0.0;
+    }
+    MS(M_MFLUX0, k) = 0.0; MS(M_MFLUX1, k) = 0.0;
   }
-  for (int m = 0; m < 2; ++m)
-    for (int k = 1; k <= pver + 1; ++k) { mflux[m][k] = 0.0; if (k <= pver) { wind0[m][k] = 0.0; windf[m][k] = 0.0; } }
-
+  __syncwarp();
   for (int m = 0; m < a.ncnst && m < 2; ++m) {
     if (!a.domom[m]) continue;
     const size_t mb = ((size_t)c * a.ncnst + m) * pver;       // base level index of constituent m
-    for (int k = 1; k <= pver; ++k) {
-      cnst[k] = a.q[(mb + k - 1) * pcols + ii];
-      wind0[m][k] = cnst[k];
+    const int MF = m ? M_MFLUX1 : M_MFLUX0, W0 = m ? M_WIND01 : M_WIND00, WF = m ? M_WINDF1 : M_WINDF0;
+    MPAR(k, 1, pver) {
+      const double v = a.q[(mb + k - 1) * pcols + ii];
+      MS(M_C, k) = v; MS(W0, k) = v;
     }
-    for (int k = 1; k <= pver; ++k) {
-      int km1 = max(1, k - 1);
-      chat[k] = 0.5 * (cnst[k] + cnst[km1]);
-      conu[k] = chat[k];
-      cond[k] = chat[k];
-      dcondt[k] = 0.0;
+    __syncwarp();
+    MPAR(k, 1, pver) {
+      const int km1 = max(1, k - 1), kp1 = min(pver, k + 1);
+      const double ck = MS(M_C, k), cm = MS(M_C, km1);
+      const double chat = 0.5 * (ck + cm);
+      MS(M_CHAT, k) = chat; MS(M_CONU, k) = chat; MS(M_COND, k) = chat; MS(M_DCONDT, k) = 0.0;
+      double pgu, pgd;
+      if (k == 1) {
+        pgu = 0.0; pgd = 0.0;
+      } else if (k <= pver - 1) {
+        const double cp1 = MS(M_C, kp1);
+        const double mududp = (MS(M_MU, k) * (ck - cm) / MS(M_DP, km1) + MS(M_MU, kp1) * (cp1 - ck) / MS(M_DP, k));
+        pgu = -P.momcu * 0.5 * mududp;
+        const double mddudp = (MS(M_MD, k) * (ck - cm) / MS(M_DP, km1) + MS(M_MD, kp1) * (cp1 - ck) / MS(M_DP, k));
+        pgd = -P.momcd * 0.5 * mddudp;
+      } else {
+        const double mududp = MS(M_MU, k) * (ck - cm) / MS(M_DP, km1);
+        pgu = -P.momcu * mududp;
+        const double mddudp = MS(M_MD, k) * (ck - cm) / MS(M_DP, km1);
+        pgd = -P.momcd * mddudp;
+      }
+      MS(M_PGU, k) = pgu; MS(M_PGD, k) = pgd;
     }
-    pgu[1] = 0.0; pgd[1] = 0.0;
-    for (int k = 2; k <= pver - 1; ++k) {
-      int km1 = max(1, k - 1), kp1 = min(pver, k + 1);
-      double mududp = (mu[k] * (cnst[k] - cnst[km1]) / dp[km1] + mu[kp1] * (cnst[kp1] - cnst[k]) / dp[k]);
-      pgu[k] = -P.momcu * 0.5 * mududp;
-      double mddudp = (md[k] * (cnst[k] - cnst[km1]) / dp[km1] + md[kp1] * (cnst[kp1] - cnst[k]) / dp[k]);
-      pgd[k] = -P.momcd * 0.5 * mddudp;
-    }
+    __syncwarp();
     {
-      int k = pver, km1 = max(1, k - 1);
-      double mududp = mu[k] * (cnst[k] - cnst[km1]) / dp[km1];
-      pgu[k] = -P.momcu * mududp;
-      double mddudp = md[k] * (cnst[k] - cnst[km1]) / dp[km1];
-      pgd[k] = -P.momcd * mddudp;
-    }
-    {
-      int k = 2, km1 = 1, kk = pver;
-      double mupdudp = mu[kk] + du[kk] * dp[kk];
-      if (mupdudp > mbsth) conu[kk] = (+eu[kk] * cnst[kk] * dp[kk] + pgu[kk] * dp[kk]) / mupdudp;
-      // operator precedence exactly as written in the reference (zm_conv.F90:2554)
-      if (md[k] < -mbsth) cond[k] = (-ed[km1] * cnst[km1] * dp[km1]) - pgd[km1] * dp[km1] / md[k];
-    }
-    for (int kk = pver - 1; kk >= 1; --kk) {
-      int kkp1 = min(pver, kk + 1);
-      double mupdudp = mu[kk] + du[kk] * dp[kk];
+      const int k = 2, km1 = 1, kk = pver;
+      const double mupdudp = MS(M_MU, kk) + MS(M_DU, kk) * MS(M_DP, kk);
       if (mupdudp > mbsth)
-        conu[kk] = (mu[kkp1] * conu[kkp1] + eu[kk] * cnst[kk] * dp[kk] + pgu[kk] * dp[kk]) / mupdudp;
+        MS(M_CONU, kk) = (+MS(M_EU, kk) * MS(M_C, kk) * MS(M_DP, kk) + MS(M_PGU, kk) * MS(M_DP, kk)) / mupdudp;
+      // operator precedence exactly as written in the reference (zm_conv.F90:2554)
+      if (MS(M_MD, k) < -mbsth)
+        MS(M_COND, k) = (-MS(M_ED, km1) * MS(M_C, km1) * MS(M_DP, km1)) - MS(M_PGD, km1) * MS(M_DP, km1) / MS(M_MD, k);
     }
-    for (int k = 3; k <= pver; ++k) {
-      int km1 = max(1, k - 1);
-      if (md[k] < -mbsth)
-        cond[k] = (md[km1] * cond[km1] - ed[km1] * cnst[km1] * dp[km1] - pgd[km1] * dp[km1]) / md[k];
+    // the two recurrences are independent of each other: interleaved in one loop
+    for (int s = 0; s < pver - 1; ++s) {
+      const int kk = pver - 1 - s;                 // updraft: pver-1 .. 1
+      if (kk >= 1) {
+        const int kkp1 = min(pver, kk + 1);
+        const double mupdudp = MS(M_MU, kk) + MS(M_DU, kk) * MS(M_DP, kk);
+        if (mupdudp > mbsth)
+          MS(M_CONU, kk) = (MS(M_MU, kkp1) * MS(M_CONU, kkp1) + MS(M_EU, kk) * MS(M_C, kk) * MS(M_DP, kk) +
+                            MS(M_PGU, kk) * MS(M_DP, kk)) / mupdudp;
+      }
+      const int k = 3 + s;                         // downdraft: 3 .. pver
+      if (k <= pver) {
+        const int km1 = k - 1;
+        if (MS(M_MD, k) < -mbsth)
+          MS(M_COND, k) = (MS(M_MD, km1) * MS(M_COND, km1) - MS(M_ED, km1) * MS(M_C, km1) * MS(M_DP, km1) -
+                           MS(M_PGD, km1) * MS(M_DP, km1)) / MS(M_MD, k);
+      }
     }
-    for (int k = ktm; k <= pver; ++k) {
-      int kp1 = min(pver, k + 1);
-      dcondt[k] = +(mu[kp1] * (conu[kp1] - chat[kp1]) - mu[k] * (conu[k] - chat[k]) +
-                    md[kp1] * (cond[kp1] - chat[kp1]) - md[k] * (cond[k] - chat[k])) / dp[k];
+    __syncwarp();
+    MPAR(k, 1, pver) {
+      double dc = 0.0;
+      if (k >= ktm) {
+        const int kp1 = min(pver, k + 1);
+        dc = +(MS(M_MU, kp1) * (MS(M_CONU, kp1) - MS(M_CHAT, kp1)) - MS(M_MU, k) * (MS(M_CONU, k) - MS(M_CHAT, k)) +
+               MS(M_MD, kp1) * (MS(M_COND, kp1) - MS(M_CHAT, kp1)) - MS(M_MD, k) * (MS(M_COND, k) - MS(M_CHAT, k))) / MS(M_DP, k);
+      }
+      if (k >= kbm && k == mx)
+        dc = (1.0 / MS(M_DP, k)) * (-MS(M_MU, k) * (MS(M_CONU, k) - MS(M_CHAT, k)) - MS(M_MD, k) * (MS(M_COND, k) - MS(M_CHAT, k)));
+      const size_t e = (mb + k - 1) * pcols + ii;
+      a.dqdt[e] = dc;
+      a.pguall[e] = -MS(M_PGU, k);
+      a.pgdall[e] = -MS(M_PGD, k);
+      a.icwu[e] = MS(M_CONU, k);
+      a.icwd[e] = MS(M_COND, k);
+      if (k >= ktm)
+        MS(MF, k) = -MS(M_MU, k) * (MS(M_CONU, k) - MS(M_CHAT, k)) - MS(M_MD, k) * (MS(M_COND, k) - MS(M_CHAT, k));
     }
-    for (int k = kbm; k <= pver; ++k)
-      if (k == mx)
-        dcondt[k] = (1.0 / dp[k]) * (-mu[k] * (conu[k] - chat[k]) - md[k] * (cond[k] - chat[k]));
-    for (int k = 1; k <= pver; ++k) {
-      size_t e = (mb + k - 1) * pcols + ii;
-      a.dqdt[e] = dcondt[k];
-      a.pguall[e] = -pgu[k];
-      a.pgdall[e] = -pgd[k];
-      a.icwu[e] = conu[k];
-      a.icwd[e] = cond[k];
-    }
-    for (int k = ktm; k <= pver; ++k)
-      mflux[m][k] = -mu[k] * (conu[k] - chat[k]) - md[k] * (cond[k] - chat[k]);
-    for (int k = ktm; k <= pver; ++k)
-      windf[m][k] = cnst[k] - (mflux[m][k + 1] - mflux[m][k]) * dt / dp[k];
+    __syncwarp();
+    MPAR(k, ktm, pver) MS(WF, k) = MS(M_C, k) - (MS(MF, k + 1) - MS(MF, k)) * dt / MS(M_DP, k);
+    __syncwarp();
   }
   // kinetic-energy dissipation heating (zm_conv.F90:2675-2712)
-  for (int k = 1; k <= pver; ++k) {
+  MPAR(k, 1, pver) {
     double gset2 = 0.0;
     if (k >= ktm) {
-      int km1 = max(1, k - 1), kp1 = min(pver, k + 1);
-      double utop = (wind0[0][k] + wind0[0][km1]) / 2.0;
-      double vtop = (wind0[1][k] + wind0[1][km1]) / 2.0;
-      double ubot = (wind0[0][kp1] + wind0[0][k]) / 2.0;
-      double vbot = (wind0[1][kp1] + wind0[1][k]) / 2.0;
-      double fket = utop * mflux[0][k] + vtop * mflux[1][k];
-      double fkeb = ubot * mflux[0][k + 1] + vbot * mflux[1][k + 1];
-      double ketend_cons = (fket - fkeb) / dp[k];
-      double ketend = ((windf[0][k] * windf[0][k] + windf[1][k] * windf[1][k]) -
-                       (wind0[0][k] * wind0[0][k] + wind0[1][k] * wind0[1][k])) * 0.5 / dt;
+      const int km1 = max(1, k - 1), kp1 = min(pver, k + 1);
+      const double utop = (MS(M_WIND00, k) + MS(M_WIND00, km1)) / 2.0;
+      const double vtop = (MS(M_WIND01, k) + MS(M_WIND01, km1)) / 2.0;
+      const double ubot = (MS(M_WIND00, kp1) + MS(M_WIND00, k)) / 2.0;
+      const double vbot = (MS(M_WIND01, kp1) + MS(M_WIND01, k)) / 2.0;
+      const double fket = utop * MS(M_MFLUX0, k) + vtop * MS(M_MFLUX1, k);
+      const double fkeb = ubot * MS(M_MFLUX0, k + 1) + vbot * MS(M_MFLUX1, k + 1);
+      const double ketend_cons = (fket - fkeb) / MS(M_DP, k);
+      const double ketend = ((MS(M_WINDF0, k) * MS(M_WINDF0, k) + MS(M_WINDF1, k) * MS(M_WINDF1, k)) -
+                             (MS(M_WIND00, k) * MS(M_WIND00, k) + MS(M_WIND01, k) * MS(M_WIND01, k))) * 0.5 / dt;
       gset2 = ketend_cons - ketend;
     }
     a.seten[cidx(c, k - 1, ii, pver)] = gset2;
   }
+#undef MS
+#undef MPAR
 }
 
 // ---- convtran --------------------------------------------------------------------------------------

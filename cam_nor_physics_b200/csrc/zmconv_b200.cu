@@ -198,11 +198,9 @@ int momtran_launch(Workspace& ws, cudaStream_t s, MomArgs a, bool own_arena = tr
   k_chunk_bounds<<<(a.nchunks * 32 + 127) / 128, 128, 0, s>>>(a.nchunks, a.jt, a.mx, a.lengath, ktm, kbm);
   ++tls_launches;
   k_momtran_init<<<592, 256, 0, s>>>(a); ++tls_launches;
-  const int L = lmax_for(pver);
-  const int nb = (ncolpad + 63) / 64;
-  if (L == 32)      k_momtran<32><<<nb, 64, 0, s>>>(a);
-  else if (L == 64) k_momtran<64><<<nb, 64, 0, s>>>(a);
-  else              k_momtran<128><<<nb, 64, 0, s>>>(a);
+  const size_t smem = momtran_smem_bytes(pver);
+  CK(cudaFuncSetAttribute(k_momtran_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_momtran_w<<<(ncolpad + MOM_WARPS - 1) / MOM_WARPS, 32 * MOM_WARPS, smem, s>>>(a);
   ++tls_launches;
   CK(cudaGetLastError());
   return 0;
