@@ -20,7 +20,7 @@ enum PlumeArr {
   A_MU, A_EU, A_DU, A_MD, A_ED, A_SD, A_QD, A_MC, A_QU, A_SU, A_QST, A_HMN, A_HSAT, A_QL, A_CMEG,
   A_PFLX, A_EVP, A_CU, A_RPRD, A_QCDE,
   A_GAMMA, A_HU, A_HD, A_EPS, A_F, A_K1, A_I2, A_I3, A_I4, A_QSTHAT, A_HSTHAT, A_GAMHAT, A_QDS,
-  A_MCP, A_MRL, A_TU, A_TD, A_W1, A_W2, A_W3, A_DPP,
+  A_MCP, A_MRL, A_TU, A_TD, A_W1, A_W2, A_W3, A_W4, A_W5, A_DPP,
   A_COUNT
 };
 
@@ -150,12 +150,14 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
   }
   WSYNC();
   // k1, i2, i3, i4 recurrences (zm_conv.F90:3430-3442) -- serial, redundant on every lane
+  PAR(k, msg + 1, pver) S(A_W1, k) = (hmn_mx - S(A_HMN, k)) * S(A_DZ, k);
+  WSYNC();
   {
     double k1p = 0.0, i2p = 0.0, i3p = 0.0, i4p = 0.0;        // values at k+1 (zero at k = jb and below)
     for (int k = pver - 1; k >= msg + 1; --k) {
       if (k < jb && k >= jt) {
         const double dz = S(A_DZ, k);
-        const double k1 = k1p + (hmn_mx - S(A_HMN, k)) * dz;
+        const double k1 = k1p + S(A_W1, k);
         const double ihat = 0.5 * (k1p + k1);
         const double i2 = i2p + ihat * dz;
         const double idag = 0.5 * (i2p + i2);
@@ -233,18 +235,36 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
       }
     }
     WSYNC();
-    // hu recurrence (zm_conv.F90:3579-3598), serial
-    for (int k = jb - 1; k >= lel; --k) {
-      if (S(A_MU, k) < 0.02) {
-        S(A_HU, k) = S(A_HMN, k);
-        S(A_MU, k) = 0.0;
-        S(A_EU, k) = 0.0;
-        S(A_DU, k) = S(A_MU, k + 1) / S(A_DZ, k);
-      } else {
-        S(A_HU, k) = S(A_MU, k + 1) / S(A_MU, k) * S(A_HU, k + 1) +
-                     S(A_DZ, k) / S(A_MU, k) * (S(A_EU, k) * S(A_HMN, k) - S(A_DU, k) * S(A_HSAT, k));
+    // hu recurrence (zm_conv.F90:3579-3598): hu(k) = A(k)*hu(k+1) + B(k) -- the coefficients are
+    // level parallel (mu(k+1) taken as the serial loop leaves it: zeroed if it was < 0.02), the
+    // chain itself is one multiply-add per level
+    PAR(k, msg + 1, pver) {
+      if (k >= lel && k <= jb - 1) {
+        const double muk = S(A_MU, k);
+        double mup = S(A_MU, k + 1);
+        if (k + 1 <= jb - 1 && mup < 0.02) mup = 0.0;
+        if (muk < 0.02) {
+          S(A_W3, k) = 1.0;
+          S(A_W4, k) = mup / S(A_DZ, k);                       // new du(k)
+        } else {
+          S(A_W3, k) = 0.0;
+          S(A_W1, k) = mup / muk;
+          S(A_W2, k) = S(A_DZ, k) / muk * (S(A_EU, k) * S(A_HMN, k) - S(A_DU, k) * S(A_HSAT, k));
+        }
       }
     }
+    WSYNC();
+    PAR(k, msg + 1, pver) {
+      if (k >= lel && k <= jb - 1 && S(A_W3, k) != 0.0) { S(A_MU, k) = 0.0; S(A_EU, k) = 0.0; S(A_DU, k) = S(A_W4, k); }
+    }
+    {
+      double hup = S(A_HU, jb);
+      for (int k = jb - 1; k >= lel; --k) {
+        hup = (S(A_W3, k) != 0.0) ? S(A_HMN, k) : S(A_W1, k) * hup + S(A_W2, k);
+        S(A_HU, k) = hup;
+      }
+    }
+    WSYNC();
   }
   {
     bool doit = true;
@@ -297,14 +317,22 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
     // su/qu recurrence (zm_conv.F90:3672-3688) evaluated speculatively for every k in (jt, jb) into
     // W1/W2 (it never feeds the saturation test's outcome back), then the saturation test runs level
     // parallel and only the levels the reference actually updated (k >= jlcl) are committed.
+    PAR(k, msg + 2, pver) {
+      if (k > jt && k < jb) {
+        const double muk = S(A_MU, k), dz = S(A_DZ, k), eu = S(A_EU, k), du = S(A_DU, k);
+        S(A_W3, k) = S(A_MU, k + 1) / muk;
+        S(A_W4, k) = dz / muk * (eu - du) * S(A_S, k);
+        S(A_W5, k) = dz / muk * (eu * S(A_Q, k) - du * S(A_QST, k));
+      }
+    }
+    WSYNC();
     {
       double sup = S(A_SU, jb), qup = S(A_QU, jb);
       for (int k = jb - 1; k > jt && k >= msg + 2; --k) {
-        const double muk = S(A_MU, k), mup = S(A_MU, k + 1), dz = S(A_DZ, k), eu = S(A_EU, k), du = S(A_DU, k);
-        const double su = mup / muk * sup + dz / muk * (eu - du) * S(A_S, k);
-        const double qu = mup / muk * qup + dz / muk * (eu * S(A_Q, k) - du * S(A_QST, k));
-        S(A_W1, k) = su; S(A_W2, k) = qu;
-        sup = su; qup = qu;
+        const double a = S(A_W3, k);
+        sup = a * sup + S(A_W4, k);
+        qup = a * qup + S(A_W5, k);
+        S(A_W1, k) = sup; S(A_W2, k) = qup;
       }
     }
     WSYNC();
@@ -352,21 +380,43 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
   }
   // rain production (zm_conv.F90:3846-3870), serial
   double totpcp = 0.0, totevp = 0.0;
-  for (int k = pver; k >= msg + 2; --k) {
+  PAR(k, msg + 2, pver) {
     S(A_RPRD, k) = 0.0;
     if (k >= jt && k < jb && eps0 > 0.0 && S(A_MU, k) >= 0.0) {
-      const double muk = S(A_MU, k), dz = S(A_DZ, k), du = S(A_DU, k), qlp = S(A_QL, k + 1), cu = S(A_CU, k);
-      double ql = 0.0;
-      if (muk > 0.0) {
-        const double ql1 = 1.0 / muk * (S(A_MU, k + 1) * qlp - dz * du * qlp + dz * cu);
-        ql = ql1 / (1.0 + dz * c0mask);
+      const double muk = S(A_MU, k), dz = S(A_DZ, k);
+      S(A_W1, k) = (muk > 0.0) ? 1.0 / muk : 0.0;
+      S(A_W2, k) = dz * S(A_DU, k);
+      S(A_W3, k) = dz * S(A_CU, k);
+      S(A_W4, k) = 1.0 + dz * c0mask;
+    }
+  }
+  WSYNC();
+  {
+    double qlp = S(A_QL, pver + 1);
+    for (int k = pver; k >= msg + 2; --k) {
+      if (k >= jt && k < jb && eps0 > 0.0 && S(A_MU, k) >= 0.0) {
+        double ql = 0.0;
+        if (S(A_MU, k) > 0.0) {
+          const double ql1 = S(A_W1, k) * (S(A_MU, k + 1) * qlp - S(A_W2, k) * qlp + S(A_W3, k));
+          ql = ql1 / S(A_W4, k);
+        }
+        S(A_QL, k) = ql;
+        totpcp = totpcp + S(A_DZ, k) * (S(A_CU, k) - S(A_DU, k) * qlp);
+        qlp = ql;
+      } else {
+        qlp = S(A_QL, k);
       }
-      S(A_QL, k) = ql;
-      totpcp = totpcp + dz * (cu - du * qlp);
-      S(A_RPRD, k) = c0mask * muk * ql;
+    }
+  }
+  WSYNC();
+  PAR(k, msg + 2, pver) {
+    if (k >= jt && k < jb && eps0 > 0.0 && S(A_MU, k) >= 0.0) {
+      const double ql = S(A_QL, k);
+      S(A_RPRD, k) = c0mask * S(A_MU, k) * ql;
       S(A_QCDE, k) = ql;
     }
   }
+  WSYNC();
   // downdraft (zm_conv.F90:3880-3975)
   const double alfa = P.alfadet;
   double epsm = 0.0;
@@ -404,9 +454,20 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
       if (k >= jt) S(A_ED, k - 1) = (S(A_MD, k - 1) - S(A_MD, k)) / S(A_DZ, k - 1);
     }
     WSYNC();
-    for (int k = max(jt, msg + 1); k <= pver; ++k) {
-      const double mdt = fmin2(S(A_MD, k), -small);
-      S(A_HD, k) = (S(A_MD, k - 1) * S(A_HD, k - 1) - S(A_DZ, k - 1) * S(A_ED, k - 1) * S(A_HMN, k - 1)) / mdt;
+    PAR(k, msg + 1, pver) {
+      if (k >= jt) {
+        S(A_W1, k) = S(A_DZ, k - 1) * S(A_ED, k - 1) * S(A_HMN, k - 1);
+        S(A_W2, k) = fmin2(S(A_MD, k), -small);
+      }
+    }
+    WSYNC();
+    {
+      const int k0 = max(jt, msg + 1);
+      double hdp = S(A_HD, k0 - 1);
+      for (int k = k0; k <= pver; ++k) {
+        hdp = (S(A_MD, k - 1) * hdp - S(A_W1, k)) / S(A_W2, k);
+        S(A_HD, k) = hdp;
+      }
     }
     WSYNC();
     if (jd < jb) {
@@ -433,17 +494,28 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
   }
   if (eps0 > 0.0) {
     const double small = 1.e-20;
-    for (int k = max(jd, msg + 2); k < jb; ++k) {
-      const double qdn = S(A_QDS, k + 1);
-      S(A_QD, k + 1) = qdn;
-      const double dz = S(A_DZ, k), ed = S(A_ED, k), md = S(A_MD, k), qd = S(A_QD, k);
-      double ev = -ed * S(A_Q, k) + (md * qd - S(A_MD, k + 1) * qdn) / dz;
-      ev = fmax2(ev, 0.0);
-      S(A_EVP, k) = ev;
-      const double mdt = fmin2(S(A_MD, k + 1), -small);
-      S(A_SD, k + 1) = (((1.0 - dcol * (S(A_TD, k) - tmelt)) * rl / ((1.0 + cpvir * qd) * cp) * ev - ed * S(A_S, k)) * dz +
-                        md * S(A_SD, k)) / mdt;
-      totevp = totevp - dz * ed * S(A_Q, k);
+    const int k0 = max(jd, msg + 2);
+    WSYNC();
+    PAR(k, msg + 2, pver) {
+      if (k >= k0 && k < jb) {
+        const double qdn = S(A_QDS, k + 1);
+        const double qd = S(A_QDS, k);                      // qd(k): qd(jd) = qds(jd), qd(k>jd) = qds(k)
+        S(A_QD, k + 1) = qdn;
+        const double dz = S(A_DZ, k), ed = S(A_ED, k), md = S(A_MD, k);
+        double ev = -ed * S(A_Q, k) + (md * qd - S(A_MD, k + 1) * qdn) / dz;
+        ev = fmax2(ev, 0.0);
+        S(A_EVP, k) = ev;
+        S(A_W1, k) = ((1.0 - dcol * (S(A_TD, k) - tmelt)) * rl / ((1.0 + cpvir * qd) * cp) * ev - ed * S(A_S, k)) * dz;
+        S(A_W2, k) = fmin2(S(A_MD, k + 1), -small);
+        S(A_W3, k) = dz * ed * S(A_Q, k);
+      }
+    }
+    WSYNC();
+    double sdp = S(A_SD, k0);
+    for (int k = k0; k < jb; ++k) {
+      sdp = (S(A_W1, k) + S(A_MD, k) * sdp) / S(A_W2, k);
+      S(A_SD, k + 1) = sdp;
+      totevp = totevp - S(A_W3, k);
     }
   }
   totevp = totevp + S(A_MD, jd) * S(A_QD, jd) - S(A_MD, jb) * S(A_QD, jb);
@@ -467,9 +539,11 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
   }
   WSYNC();
   {
+    PAR(k, 1, pver) S(A_W1, k) = S(A_RPRD, k) * S(A_DZ, k);
+    WSYNC();
     double pf = 0.0;
     S(A_PFLX, 1) = 0.0;
-    for (int k = 2; k <= pverp; ++k) { pf = pf + S(A_RPRD, k - 1) * S(A_DZ, k - 1); S(A_PFLX, k) = pf; }
+    for (int k = 2; k <= pverp; ++k) { pf = pf + S(A_W1, k - 1); S(A_PFLX, k) = pf; }
   }
   PAR(k, msg + 1, pver) S(A_MC, k) = S(A_MU, k) + S(A_MD, k);
   WSYNC();
@@ -614,8 +688,9 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
   }
   // mass-flux limiter (zm_conv.F90:1285-1308)
   {
-    double mumax = 0.0;
-    for (int k = msg + 2; k <= pver; ++k) mumax = fmax2(mumax, S(A_MU, k) / S(A_DP, k));
+    double mumax = 0.0;                        // max is exact in any order: lane-parallel + shuffle
+    PAR(k, msg + 2, pver) mumax = fmax2(mumax, S(A_MU, k) / S(A_DP, k));
+    for (int off = 16; off; off >>= 1) mumax = fmax2(mumax, __shfl_xor_sync(0xffffffffu, mumax, off));
     if (mumax > 0.0) mb = fmin2(mb, 0.5 / (delt * mumax));
     else mb = 0.0;
     if (P.no_deep_pbl)
@@ -677,16 +752,19 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
   }
   // precipitation and reserved liquid (zm_conv.F90:1629-1649), serial sums in the reference's order
   double prec = 0.0, rliq = 0.0;
-  for (int k = pver; k >= msg + 1; --k) {
+  WSYNC();
+  PAR(k, 1, pver) {
     const double dppk = S(A_DPP, k), qhk = S(A_Q, k);
-    const double qnew = qhk + 2.0 * delt * S(A_W2, k);
-    prec = prec - dppk * (qnew - qhk) - dppk * (S(A_W3, k) + 0.0) * 2.0 * delt;
-  }
-  prec = P.rgrav * fmax2(prec, 0.0) / (2.0 * delt) / 1000.0;
-  for (int k = 1; k <= pver; ++k) {
     const double dlfk = (k >= msg + 1) ? S(A_W3, k) : 0.0;
-    rliq = rliq + (dlfk + 0.0) * S(A_DPP, k) / P.gravit;
+    const double qnew = qhk + 2.0 * delt * ((k >= msg + 1) ? S(A_W2, k) : 0.0);
+    S(A_W4, k) = dppk * (qnew - qhk);
+    S(A_W5, k) = dppk * (dlfk + 0.0) * 2.0 * delt;
+    S(A_W1, k) = (dlfk + 0.0) * dppk / P.gravit;
   }
+  WSYNC();
+  for (int k = pver; k >= msg + 1; --k) prec = prec - S(A_W4, k) - S(A_W5, k);
+  prec = P.rgrav * fmax2(prec, 0.0) / (2.0 * delt) / 1000.0;
+  for (int k = 1; k <= pver; ++k) rliq = rliq + S(A_W1, k);
   rliq = rliq / 1000.0;
   if (lane == 0) {
     o.pflx[cidx(c, pverp - 1, i, pverp)] = S(A_PFLX, pverp);
