@@ -76,9 +76,11 @@ k_conv_evap(EvapArgs a) {
   a.snow[col] = flxsnow / 1000.0;
 }
 
-// ---- chunk-wide ktm / kbm (zm_conv.F90:2076-2081): one warp per chunk ----------------------------
+// ---- chunk-wide ktm / kbm (zm_conv.F90:2076-2081) + compact list of convective slots: warp per chunk --
+// slots[0..count) lists the gathered slots (chunk*pcols + gathered position) that hold a convective
+// column, so the transport kernels run dense warps; the order of the list does not matter.
 __global__ void k_chunk_bounds(int nchunks, const int* jt, const int* mx, const int* lengath, int* ktm,
-                               int* kbm) {
+                               int* kbm, int* slots, int* count) {
   const int lane = threadIdx.x & 31;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= nchunks) return;
@@ -92,13 +94,16 @@ __global__ void k_chunk_bounds(int nchunks, const int* jt, const int* mx, const 
     a = min(a, __shfl_xor_sync(0xffffffffu, a, off));
     b = min(b, __shfl_xor_sync(0xffffffffu, b, off));
   }
-  if (lane == 0) { ktm[c] = a; kbm[c] = b; }
+  int base = 0;
+  if (lane == 0) { ktm[c] = a; kbm[c] = b; base = n ? atomicAdd(count, n) : 0; }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int i = lane; i < n; i += 32) slots[base + i] = c * pcols + i;
 }
 
 // ---- momtran -------------------------------------------------------------------------------------
 struct MomArgs {
   int nchunks, ncnst;
-  const int *ncol, *jt, *mx, *ideep, *lengath, *ktm, *kbm;
+  const int *ncol, *jt, *mx, *ideep, *lengath, *ktm, *kbm, *slots, *count;
   int domom[2];
   const double *q, *mu, *md, *du, *eu, *ed, *dp;
   double *dqdt, *pguall, *pgdall, *icwu, *icwd, *seten;
@@ -121,259 +126,305 @@ __global__ void k_momtran_init(MomArgs a) {
   for (size_t e = tid; e < n2; e += nth) a.seten[e] = 0.0;
 }
 
-// One warp per gathered (convective) column, lane == level; the two order-dependent recurrences
-// (in-cloud updraft wind bottom-up, downdraft wind top-down; zm_conv.F90:2562-2589) run redundantly
-// on every lane in the reference's order, everything else is level parallel.
-#define MOM_WARPS 2
-enum MomArr { M_MU, M_MD, M_DU, M_EU, M_ED, M_DP, M_C, M_CHAT, M_CONU, M_COND, M_PGU, M_PGD, M_DCONDT,
-              M_MFLUX0, M_MFLUX1, M_WIND00, M_WIND01, M_WINDF0, M_WINDF1, M_COUNT };
-inline size_t momtran_smem_bytes(int pver) { return (size_t)MOM_WARPS * M_COUNT * (pver + 2) * sizeof(double); }
-
-__global__ void __launch_bounds__(32 * MOM_WARPS)
-k_momtran_w(MomArgs a) {
-  extern __shared__ double sm_mom[];
+// Thread per gathered (convective) column, registers only: sweep 1 runs bottom-up (pressure-gradient
+// term + in-cloud updraft wind, zm_conv.F90:2497-2575) and parks conu in the icwu output; sweep 2 runs
+// top-down (downdraft wind 2579-2589) and finishes level k-1 (tendency 2596-2627, momentum flux and
+// end-of-step wind 2646-2666, KE-dissipation heating 2675-2712) as soon as level k is known.  Both
+// wind components advance together.  No per-level arrays: every input is read twice from L2/HBM,
+// nothing is staged in local memory (an array-based version spent its time in local-memory misses).
+__global__ void __launch_bounds__(64)
+k_momtran_t(MomArgs a) {
   const int pcols = P.pcols, pver = P.pver;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int slot = blockIdx.x * MOM_WARPS + wib;
-  if (slot >= a.nchunks * pcols) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= *a.count) return;
+  const int slot = a.slots[tid];
   const int c = slot / pcols, gi = slot - c * pcols;
-  if (gi >= a.lengath[c]) return;
-  const int ld = pver + 2;
-  double* B = sm_mom + (size_t)wib * M_COUNT * ld;
-#define MS(n, k) B[(n) * ld + (k)]
-#define MPAR(k, lo, hi) for (int k = (lo) + lane; k <= (hi); k += 32)
-  const int ii = a.ideep[slot] - 1;            // ungathered column (0-based)
+  const int ii = a.ideep[slot] - 1;
   const int mx = a.mx[slot];
   const int ktm = a.ktm[c], kbm = a.kbm[c];
   const double mbsth = 1.e-15, dt = a.dt;
-  MPAR(k, 1, pver + 1) {
-    if (k <= pver) {
-      const size_t e = cidx(c, k - 1, gi, pver);
-      MS(M_MU, k) = a.mu[e]; MS(M_MD, k) = a.md[e]; MS(M_DU, k) = a.du[e]; MS(M_EU, k) = a.eu[e];
-      MS(M_ED, k) = a.ed[e]; MS(M_DP, k) = a.dp[e];
-      MS(M_WIND00, k) = 0.0; MS(M_WIND01, k) = 0.0; MS(M_WINDF0, k) = 0.0; MS(M_WINDF1, k) = 0.0;
+  const bool act[2] = {a.domom[0] != 0, a.domom[1] != 0};
+#define GA(arr, k) a.arr[cidx(c, (k) - 1, gi, pver)]
+#define QI(m, k) ((((size_t)c * 2 + (m)) * pver + (k) - 1) * pcols + ii)
+
+  // ---------------- sweep 1: k = pver .. 1 ----------------
+  {
+    double c_k[2], c_km1[2], c_kp1[2], conu_kp1[2];
+    double mu_k = GA(mu, pver), mu_kp1 = 0.0;
+    double dp_k = GA(dp, pver), dp_km1 = GA(dp, max(1, pver - 1));
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      c_k[m] = act[m] ? a.q[QI(m, pver)] : 0.0;
+      c_km1[m] = act[m] ? a.q[QI(m, max(1, pver - 1))] : 0.0;
+      c_kp1[m] = c_k[m]; conu_kp1[m] = 0.0;
     }
-    MS(M_MFLUX0, k) = 0.0; MS(M_MFLUX1, k) = 0.0;
+    for (int k = pver; k >= 1; --k) {
+      const double du_k = GA(du, k), eu_k = GA(eu, k);
+      const double mupdudp = mu_k + du_k * dp_k;
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        if (!act[m]) continue;
+        double pgu;
+        if (k == 1) {
+          pgu = 0.0;
+        } else if (k == pver) {
+          const double mududp = mu_k * (c_k[m] - c_km1[m]) / dp_km1;
+          pgu = -P.momcu * mududp;
+        } else {
+          const double mududp = (mu_k * (c_k[m] - c_km1[m]) / dp_km1 + mu_kp1 * (c_kp1[m] - c_k[m]) / dp_k);
+          pgu = -P.momcu * 0.5 * mududp;
+        }
+        const double chat = 0.5 * (c_k[m] + c_km1[m]);
+        double conu = chat;
+        if (mupdudp > mbsth) {
+          if (k == pver) conu = (+eu_k * c_k[m] * dp_k + pgu * dp_k) / mupdudp;
+          else           conu = (mu_kp1 * conu_kp1[m] + eu_k * c_k[m] * dp_k + pgu * dp_k) / mupdudp;
+        }
+        a.icwu[QI(m, k)] = conu;
+        a.pguall[QI(m, k)] = -pgu;
+        conu_kp1[m] = conu;
+        c_kp1[m] = c_k[m]; c_k[m] = c_km1[m];
+        if (k - 2 >= 1) c_km1[m] = a.q[QI(m, k - 2)];       // next level's km1 = max(1, (k-1)-1)
+      }
+      mu_kp1 = mu_k; dp_k = dp_km1;
+      if (k - 1 >= 1) { mu_k = GA(mu, k - 1); dp_km1 = GA(dp, max(1, k - 2)); }
+    }
   }
-  __syncwarp();
-  for (int m = 0; m < a.ncnst && m < 2; ++m) {
-    if (!a.domom[m]) continue;
-    const size_t mb = ((size_t)c * a.ncnst + m) * pver;       // base level index of constituent m
-    const int MF = m ? M_MFLUX1 : M_MFLUX0, W0 = m ? M_WIND01 : M_WIND00, WF = m ? M_WINDF1 : M_WINDF0;
-    MPAR(k, 1, pver) {
-      const double v = a.q[(mb + k - 1) * pcols + ii];
-      MS(M_C, k) = v; MS(W0, k) = v;
-    }
-    __syncwarp();
-    MPAR(k, 1, pver) {
-      const int km1 = max(1, k - 1), kp1 = min(pver, k + 1);
-      const double ck = MS(M_C, k), cm = MS(M_C, km1);
-      const double chat = 0.5 * (ck + cm);
-      MS(M_CHAT, k) = chat; MS(M_CONU, k) = chat; MS(M_COND, k) = chat; MS(M_DCONDT, k) = 0.0;
-      double pgu, pgd;
-      if (k == 1) {
-        pgu = 0.0; pgd = 0.0;
-      } else if (k <= pver - 1) {
-        const double cp1 = MS(M_C, kp1);
-        const double mududp = (MS(M_MU, k) * (ck - cm) / MS(M_DP, km1) + MS(M_MU, kp1) * (cp1 - ck) / MS(M_DP, k));
-        pgu = -P.momcu * 0.5 * mududp;
-        const double mddudp = (MS(M_MD, k) * (ck - cm) / MS(M_DP, km1) + MS(M_MD, kp1) * (cp1 - ck) / MS(M_DP, k));
-        pgd = -P.momcd * 0.5 * mddudp;
-      } else {
-        const double mududp = MS(M_MU, k) * (ck - cm) / MS(M_DP, km1);
-        pgu = -P.momcu * mududp;
-        const double mddudp = MS(M_MD, k) * (ck - cm) / MS(M_DP, km1);
-        pgd = -P.momcd * mddudp;
-      }
-      MS(M_PGU, k) = pgu; MS(M_PGD, k) = pgd;
-    }
-    __syncwarp();
-    {
-      const int k = 2, km1 = 1, kk = pver;
-      const double mupdudp = MS(M_MU, kk) + MS(M_DU, kk) * MS(M_DP, kk);
-      if (mupdudp > mbsth)
-        MS(M_CONU, kk) = (+MS(M_EU, kk) * MS(M_C, kk) * MS(M_DP, kk) + MS(M_PGU, kk) * MS(M_DP, kk)) / mupdudp;
-      // operator precedence exactly as written in the reference (zm_conv.F90:2554)
-      if (MS(M_MD, k) < -mbsth)
-        MS(M_COND, k) = (-MS(M_ED, km1) * MS(M_C, km1) * MS(M_DP, km1)) - MS(M_PGD, km1) * MS(M_DP, km1) / MS(M_MD, k);
-    }
-    // the two recurrences are independent of each other: interleaved in one loop
-    for (int s = 0; s < pver - 1; ++s) {
-      const int kk = pver - 1 - s;                 // updraft: pver-1 .. 1
-      if (kk >= 1) {
-        const int kkp1 = min(pver, kk + 1);
-        const double mupdudp = MS(M_MU, kk) + MS(M_DU, kk) * MS(M_DP, kk);
-        if (mupdudp > mbsth)
-          MS(M_CONU, kk) = (MS(M_MU, kkp1) * MS(M_CONU, kkp1) + MS(M_EU, kk) * MS(M_C, kk) * MS(M_DP, kk) +
-                            MS(M_PGU, kk) * MS(M_DP, kk)) / mupdudp;
-      }
-      const int k = 3 + s;                         // downdraft: 3 .. pver
+  // ---------------- sweep 2: k = 1 .. pver, finishing level k-1 one step late ----------------
+  {
+    double c_k[2], c_km1[2], c_j[2] = {0, 0}, c_jm1[2] = {0, 0};   // j = k-1 (level being finished)
+    double cond_km1[2] = {0, 0}, pgd_km1[2] = {0, 0};
+    double X_j[2] = {0, 0}, Y_j[2] = {0, 0}, mf_j[2] = {0, 0};
+    double md_km1 = 0.0, ed_km1 = 0.0, dp_km1 = 0.0, dp_j = 0.0;
+    double mu_k = GA(mu, 1), md_k = GA(md, 1), dp_k = GA(dp, 1);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) { c_k[m] = act[m] ? a.q[QI(m, 1)] : 0.0; c_km1[m] = c_k[m]; }
+    for (int k = 1; k <= pver + 1; ++k) {
+      double X_k[2] = {0, 0}, Y_k[2] = {0, 0}, mf_k[2] = {0, 0}, c_kp1[2] = {0, 0};
+      double mu_kp1 = 0.0, md_kp1 = 0.0, dp_kp1 = 0.0, ed_k = 0.0;
       if (k <= pver) {
-        const int km1 = k - 1;
-        if (MS(M_MD, k) < -mbsth)
-          MS(M_COND, k) = (MS(M_MD, km1) * MS(M_COND, km1) - MS(M_ED, km1) * MS(M_C, km1) * MS(M_DP, km1) -
-                           MS(M_PGD, km1) * MS(M_DP, km1)) / MS(M_MD, k);
+        ed_k = GA(ed, k);
+        if (k < pver) { mu_kp1 = GA(mu, k + 1); md_kp1 = GA(md, k + 1); dp_kp1 = GA(dp, k + 1); }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          if (!act[m]) continue;
+          c_kp1[m] = (k < pver) ? a.q[QI(m, k + 1)] : c_k[m];
+          double pgd;
+          if (k == 1) {
+            pgd = 0.0;
+          } else if (k == pver) {
+            const double mddudp = md_k * (c_k[m] - c_km1[m]) / dp_km1;
+            pgd = -P.momcd * mddudp;
+          } else {
+            const double mddudp = (md_k * (c_k[m] - c_km1[m]) / dp_km1 + md_kp1 * (c_kp1[m] - c_k[m]) / dp_k);
+            pgd = -P.momcd * 0.5 * mddudp;
+          }
+          const double chat = 0.5 * (c_k[m] + c_km1[m]);
+          double cond = chat;
+          if (k == 2) {
+            // operator precedence exactly as written in the reference (zm_conv.F90:2554)
+            if (md_k < -mbsth) cond = (-ed_km1 * c_km1[m] * dp_km1) - pgd_km1[m] * dp_km1 / md_k;
+          } else if (k >= 3) {
+            if (md_k < -mbsth)
+              cond = (md_km1 * cond_km1[m] - ed_km1 * c_km1[m] * dp_km1 - pgd_km1[m] * dp_km1) / md_k;
+          }
+          a.icwd[QI(m, k)] = cond;
+          a.pgdall[QI(m, k)] = -pgd;
+          const double conu = a.icwu[QI(m, k)];
+          X_k[m] = mu_k * (conu - chat);
+          Y_k[m] = md_k * (cond - chat);
+          mf_k[m] = (k >= ktm) ? (-X_k[m] - Y_k[m]) : 0.0;
+          cond_km1[m] = cond; pgd_km1[m] = pgd;
+        }
       }
-    }
-    __syncwarp();
-    MPAR(k, 1, pver) {
-      double dc = 0.0;
-      if (k >= ktm) {
-        const int kp1 = min(pver, k + 1);
-        dc = +(MS(M_MU, kp1) * (MS(M_CONU, kp1) - MS(M_CHAT, kp1)) - MS(M_MU, k) * (MS(M_CONU, k) - MS(M_CHAT, k)) +
-               MS(M_MD, kp1) * (MS(M_COND, kp1) - MS(M_CHAT, kp1)) - MS(M_MD, k) * (MS(M_COND, k) - MS(M_CHAT, k))) / MS(M_DP, k);
+      // ---- finish level j = k-1 ----
+      if (k >= 2) {
+        const int j = k - 1;
+        double wf[2] = {0, 0};
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          if (!act[m]) continue;
+          // kp1 = min(pver, j+1): at j = pver the "k" quantities are those of level pver again
+          const double Xp = (j < pver) ? X_k[m] : X_j[m], Yp = (j < pver) ? Y_k[m] : Y_j[m];
+          double dc = 0.0;
+          if (j >= ktm) dc = +(Xp - X_j[m] + Yp - Y_j[m]) / dp_j;
+          if (j >= kbm && j == mx) dc = (1.0 / dp_j) * (-X_j[m] - Y_j[m]);
+          a.dqdt[QI(m, j)] = dc;
+          if (j >= ktm) wf[m] = c_j[m] - (mf_k[m] - mf_j[m]) * dt / dp_j;     // mf_k = 0 at j = pver
+        }
+        double gset2 = 0.0;
+        if (j >= ktm) {
+          // wind0(kp1) with kp1 = min(pver, j+1); c_k is level j+1 (or level pver again at j = pver)
+          const double u_p = (j < pver) ? c_k[0] : c_j[0], v_p = (j < pver) ? c_k[1] : c_j[1];
+          const double utop = (c_j[0] + c_jm1[0]) / 2.0;
+          const double vtop = (c_j[1] + c_jm1[1]) / 2.0;
+          const double ubot = (u_p + c_j[0]) / 2.0;
+          const double vbot = (v_p + c_j[1]) / 2.0;
+          const double fket = utop * mf_j[0] + vtop * mf_j[1];
+          const double fkeb = ubot * mf_k[0] + vbot * mf_k[1];
+          const double ketend_cons = (fket - fkeb) / dp_j;
+          const double ketend = ((wf[0] * wf[0] + wf[1] * wf[1]) - (c_j[0] * c_j[0] + c_j[1] * c_j[1])) * 0.5 / dt;
+          gset2 = ketend_cons - ketend;
+        }
+        a.seten[cidx(c, j - 1, ii, pver)] = gset2;
       }
-      if (k >= kbm && k == mx)
-        dc = (1.0 / MS(M_DP, k)) * (-MS(M_MU, k) * (MS(M_CONU, k) - MS(M_CHAT, k)) - MS(M_MD, k) * (MS(M_COND, k) - MS(M_CHAT, k)));
-      const size_t e = (mb + k - 1) * pcols + ii;
-      a.dqdt[e] = dc;
-      a.pguall[e] = -MS(M_PGU, k);
-      a.pgdall[e] = -MS(M_PGD, k);
-      a.icwu[e] = MS(M_CONU, k);
-      a.icwd[e] = MS(M_COND, k);
-      if (k >= ktm)
-        MS(MF, k) = -MS(M_MU, k) * (MS(M_CONU, k) - MS(M_CHAT, k)) - MS(M_MD, k) * (MS(M_COND, k) - MS(M_CHAT, k));
+      // ---- shift k -> k+1 ----
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        c_jm1[m] = c_j[m];                       // wind0(max(1, j-1)) for the next j
+        if (k == 1) c_jm1[m] = c_k[m];           // j = 1: km1 = 1
+        c_j[m] = c_k[m];
+        X_j[m] = X_k[m]; Y_j[m] = Y_k[m]; mf_j[m] = mf_k[m];
+        c_km1[m] = c_k[m]; c_k[m] = c_kp1[m];
+      }
+      dp_j = dp_k;
+      md_km1 = md_k; ed_km1 = ed_k; dp_km1 = dp_k;
+      mu_k = mu_kp1; md_k = md_kp1; dp_k = dp_kp1;
     }
-    __syncwarp();
-    MPAR(k, ktm, pver) MS(WF, k) = MS(M_C, k) - (MS(MF, k + 1) - MS(MF, k)) * dt / MS(M_DP, k);
-    __syncwarp();
   }
-  // kinetic-energy dissipation heating (zm_conv.F90:2675-2712)
-  MPAR(k, 1, pver) {
-    double gset2 = 0.0;
-    if (k >= ktm) {
-      const int km1 = max(1, k - 1), kp1 = min(pver, k + 1);
-      const double utop = (MS(M_WIND00, k) + MS(M_WIND00, km1)) / 2.0;
-      const double vtop = (MS(M_WIND01, k) + MS(M_WIND01, km1)) / 2.0;
-      const double ubot = (MS(M_WIND00, kp1) + MS(M_WIND00, k)) / 2.0;
-      const double vbot = (MS(M_WIND01, kp1) + MS(M_WIND01, k)) / 2.0;
-      const double fket = utop * MS(M_MFLUX0, k) + vtop * MS(M_MFLUX1, k);
-      const double fkeb = ubot * MS(M_MFLUX0, k + 1) + vbot * MS(M_MFLUX1, k + 1);
-      const double ketend_cons = (fket - fkeb) / MS(M_DP, k);
-      const double ketend = ((MS(M_WINDF0, k) * MS(M_WINDF0, k) + MS(M_WINDF1, k) * MS(M_WINDF1, k)) -
-                             (MS(M_WIND00, k) * MS(M_WIND00, k) + MS(M_WIND01, k) * MS(M_WIND01, k))) * 0.5 / dt;
-      gset2 = ketend_cons - ketend;
-    }
-    a.seten[cidx(c, k - 1, ii, pver)] = gset2;
-  }
-#undef MS
-#undef MPAR
+#undef GA
+#undef QI
 }
 
 // ---- convtran --------------------------------------------------------------------------------------
 struct TranArgs {
   int nchunks, ncnst, nactive;
-  const int *jt, *mx, *ideep, *lengath, *ktm, *kbm;
+  const int *jt, *mx, *ideep, *lengath, *ktm, *kbm, *slots, *count;
   const int* active;        // [nactive] 0-based constituent indices with doconvtran (m >= 2)
   const int* is_dry;        // [ncnst]
   const double *q, *fracis, *mu, *md, *du, *eu, *ed, *dp, *dpdry;
   double* dqdt;
 };
 
-// dqdt(:,:,m) = 0 for every active constituent (zm_conv.F90:2298)
-__global__ void k_convtran_zero(TranArgs a) {
-  const int pcols = P.pcols, pver = P.pver;
-  const size_t per = (size_t)pcols * pver;
-  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-  const size_t total = (size_t)a.nchunks * a.nactive * per;
-  for (size_t e = tid; e < total; e += nth) {
-    size_t r = e / per, off = e - r * per;
-    size_t c = r / a.nactive, j = r - c * a.nactive;
-    a.dqdt[((size_t)c * a.ncnst + a.active[j]) * per + off] = 0.0;
-  }
+// dqdt(:,:,m) = 0 for every active constituent (zm_conv.F90:2298): one block per (chunk, active m) slice
+__global__ void __launch_bounds__(128)
+k_convtran_zero(TranArgs a) {
+  const int per = P.pcols * P.pver;
+  const int c = blockIdx.x / a.nactive, j = blockIdx.x - c * a.nactive;
+  double* d = a.dqdt + ((size_t)c * a.ncnst + a.active[j]) * per;
+  for (int e = threadIdx.x; e < per; e += blockDim.x) d[e] = 0.0;
 }
 
-// blockDim = (TX gathered columns, TY constituents); grid.x over column slots, grid.y over constituents
-template <int LMAX>
+// Interface value of the tracer between levels k-1 and k (zm_conv.F90:2119-2139)
+__device__ __forceinline__ double convtran_chat(double cm, double ck) {
+  const double small = 1.e-36;
+  const double minc = fmin2(cm, ck), maxc = fmax2(cm, ck);
+  double cdifr;
+  if (minc < 0.0) cdifr = 0.0;
+  else cdifr = fabs(ck - cm) / fmax2(maxc, small);
+  if (cdifr > 1.E-6) {
+    const double cabv = fmax2(cm, maxc * 1.e-12);
+    const double cbel = fmax2(ck, maxc * 1.e-12);
+    return zmm::log_(cabv / cbel) / (cabv - cbel) * cabv * cbel;
+  }
+  return 0.5 * (ck + cm);
+}
+
+// Thread per (gathered column, active constituent), registers only.  Sweep 1 (bottom-up) computes the
+// updraft mixing ratio conu(k) (zm_conv.F90:2152-2175) and parks it in the dqdt output slice; sweep 2
+// (top-down) computes the downdraft mixing ratio cond(k) (2178-2186) and, one level late, the limited
+// fluxes and the tendency (2189-2254).  blockDim = (32 column slots, 4 constituents): the seven
+// per-column mass-flux arrays are shared through L1 by the constituents of a column.
 __global__ void __launch_bounds__(128)
-k_convtran(TranArgs a) {
+k_convtran_t(TranArgs a) {
   const int pcols = P.pcols, pver = P.pver;
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  if (slot >= a.nchunks * pcols || j >= a.nactive) return;
+  if (tid >= *a.count || j >= a.nactive) return;
+  const int slot = a.slots[tid];
   const int c = slot / pcols, gi = slot - c * pcols;
-  if (gi >= a.lengath[c]) return;
   const int m = a.active[j];
   const int ii = a.ideep[slot] - 1;
   const int mx = a.mx[slot];
   const int ktm = a.ktm[c], kbm = a.kbm[c];
-  const double small = 1.e-36, mbsth = 1.e-15;
+  const double mbsth = 1.e-15;
   const bool dry = a.is_dry[m] != 0;
-  double mu[LMAX + 2], md[LMAX + 2], dutmp[LMAX + 2], eutmp[LMAX + 2], edtmp[LMAX + 2], dptmp[LMAX + 2];
-  double cnst[LMAX + 2], fisg[LMAX + 2], chat[LMAX + 2], conu[LMAX + 2], cond[LMAX + 2], dcondt[LMAX + 2];
   const size_t mb = ((size_t)c * a.ncnst + m) * pver;
-  for (int k = 1; k <= pver; ++k) {
-    size_t e = cidx(c, k - 1, gi, pver);
-    mu[k] = a.mu[e]; md[k] = a.md[e];
-    double du = a.du[e], eu = a.eu[e], ed = a.ed[e], dp = a.dp[e];
-    if (dry) {
-      double dpd = a.dpdry[e];
-      dptmp[k] = dpd;
-      dutmp[k] = du * dp / dpd;
-      eutmp[k] = eu * dp / dpd;
-      edtmp[k] = ed * dp / dpd;
-    } else {
-      dptmp[k] = dp; dutmp[k] = du; eutmp[k] = eu; edtmp[k] = ed;
-    }
-    cnst[k] = a.q[(mb + k - 1) * pcols + ii];
-    fisg[k] = a.fracis[(mb + k - 1) * pcols + ii];
-  }
-  for (int k = 1; k <= pver; ++k) {
-    int km1 = max(1, k - 1);
-    double minc = fmin2(cnst[km1], cnst[k]);
-    double maxc = fmax2(cnst[km1], cnst[k]);
-    double cdifr;
-    if (minc < 0.0) cdifr = 0.0;
-    else cdifr = fabs(cnst[k] - cnst[km1]) / fmax2(maxc, small);
-    if (cdifr > 1.E-6) {
-      double cabv = fmax2(cnst[km1], maxc * 1.e-12);
-      double cbel = fmax2(cnst[k], maxc * 1.e-12);
-      chat[k] = zmm::log_(cabv / cbel) / (cabv - cbel) * cabv * cbel;
-    } else {
-      chat[k] = 0.5 * (cnst[k] + cnst[km1]);
-    }
-    conu[k] = chat[k];
-    cond[k] = chat[k];
-    dcondt[k] = 0.0;
-  }
+#define GA(arr, k) a.arr[cidx(c, (k) - 1, gi, pver)]
+#define QI(k) ((mb + (k) - 1) * pcols + ii)
+  // per-level mass-flux terms with the dry/moist switch of zm_conv.F90:2087-2105
+  auto dptmp_of = [&](int k) { return dry ? GA(dpdry, k) : GA(dp, k); };
+  auto scaled = [&](double x, int k) { return dry ? x * GA(dp, k) / GA(dpdry, k) : x; };
+
+  // ---------------- sweep 1: conu, k = pver .. 1 ----------------
   {
-    int k = 2, km1 = 1, kk = pver;
-    double mupdudp = mu[kk] + dutmp[kk] * dptmp[kk];
-    if (mupdudp > mbsth) conu[kk] = (+eutmp[kk] * fisg[kk] * cnst[kk] * dptmp[kk]) / mupdudp;
-    if (md[k] < -mbsth) cond[k] = (-edtmp[km1] * fisg[km1] * cnst[km1] * dptmp[km1]) / md[k];
-  }
-  for (int kk = pver - 1; kk >= 1; --kk) {
-    int kkp1 = min(pver, kk + 1);
-    double mupdudp = mu[kk] + dutmp[kk] * dptmp[kk];
-    if (mupdudp > mbsth)
-      conu[kk] = (mu[kkp1] * conu[kkp1] + eutmp[kk] * fisg[kk] * cnst[kk] * dptmp[kk]) / mupdudp;
-  }
-  for (int k = 3; k <= pver; ++k) {
-    int km1 = max(1, k - 1);
-    if (md[k] < -mbsth)
-      cond[k] = (md[km1] * cond[km1] - edtmp[km1] * fisg[km1] * cnst[km1] * dptmp[km1]) / md[k];
-  }
-  for (int k = ktm; k <= pver; ++k) {
-    int km1 = max(1, k - 1), kp1 = min(pver, k + 1);
-    double fluxin = mu[kp1] * conu[kp1] + mu[k] * fmin2(chat[k], cnst[km1]) -
-                    (md[k] * cond[k] + md[kp1] * fmin2(chat[kp1], cnst[kp1]));
-    double fluxout = mu[k] * conu[k] + mu[kp1] * fmin2(chat[kp1], cnst[k]) -
-                     (md[kp1] * cond[kp1] + md[k] * fmin2(chat[k], cnst[k]));
-    double netflux = fluxin - fluxout;
-    if (fabs(netflux) < fmax2(fluxin, fluxout) * 1.e-12) netflux = 0.0;
-    dcondt[k] = netflux / dptmp[k];
-  }
-  for (int k = kbm; k <= pver; ++k) {
-    int km1 = max(1, k - 1);
-    if (k == mx) {
-      double fluxin = mu[k] * fmin2(chat[k], cnst[km1]) - md[k] * cond[k];
-      double fluxout = mu[k] * conu[k] - md[k] * fmin2(chat[k], cnst[k]);
-      double netflux = fluxin - fluxout;
-      if (fabs(netflux) < fmax2(fluxin, fluxout) * 1.e-12) netflux = 0.0;
-      dcondt[k] = netflux / dptmp[k];
-    } else if (k > mx) {
-      dcondt[k] = 0.0;
+    double conu_kp1 = 0.0, mu_kp1 = 0.0;
+    double c_k = a.q[QI(pver)];
+    for (int k = pver; k >= 1; --k) {
+      const double c_km1 = a.q[QI(max(1, k - 1))];
+      const double mu_k = GA(mu, k), dpt = dptmp_of(k);
+      const double dut = scaled(GA(du, k), k);
+      const double mupdudp = mu_k + dut * dpt;
+      double conu;
+      if (mupdudp > mbsth) {
+        const double eut = scaled(GA(eu, k), k), fis = a.fracis[QI(k)];
+        if (k == pver) conu = (+eut * fis * c_k * dpt) / mupdudp;
+        else           conu = (mu_kp1 * conu_kp1 + eut * fis * c_k * dpt) / mupdudp;
+      } else {
+        conu = convtran_chat(c_km1, c_k);
+      }
+      a.dqdt[QI(k)] = conu;
+      conu_kp1 = conu; mu_kp1 = mu_k; c_k = c_km1;
     }
   }
-  for (int k = 1; k <= pver; ++k) a.dqdt[(mb + k - 1) * pcols + ii] = dcondt[k];
+  // ---------------- sweep 2: cond + fluxes, k = 1 .. pver, finishing level k-1 one step late ----------------
+  {
+    double c_km1 = a.q[QI(1)], c_k = c_km1;
+    double c_jm1 = c_km1;                       // const(max(1, j-1)) of the level being finished
+    double cond_km1 = 0.0, md_km1 = 0.0, t_km1 = 0.0;   // t = edtmp*fisg*const*dptmp of level k-1
+    double chat_j = 0.0, conu_j = 0.0, cond_j = 0.0, mu_j = 0.0, md_j = 0.0, dpt_j = 1.0;
+    for (int k = 1; k <= pver + 1; ++k) {
+      double chat_k = 0.0, conu_k = 0.0, cond_k = 0.0, mu_k = 0.0, md_k = 0.0, dpt_k = 1.0, c_kp1 = c_k, t_k = 0.0;
+      if (k <= pver) {
+        chat_k = convtran_chat(c_km1, c_k);
+        conu_k = a.dqdt[QI(k)];
+        mu_k = GA(mu, k); md_k = GA(md, k); dpt_k = dptmp_of(k);
+        if (k < pver) c_kp1 = a.q[QI(k + 1)];
+        cond_k = chat_k;
+        if (k == 2) {
+          if (md_k < -mbsth) cond_k = (-t_km1) / md_k;
+        } else if (k >= 3) {
+          if (md_k < -mbsth) cond_k = (md_km1 * cond_km1 - t_km1) / md_k;
+        }
+        t_k = scaled(GA(ed, k), k) * a.fracis[QI(k)] * c_k * dpt_k;
+      }
+      if (k >= 2) {
+        const int jl = k - 1;                   // level being finished; kp1 = min(pver, jl+1)
+        const bool last = (jl == pver);
+        const double mu_p = last ? mu_j : mu_k, md_p = last ? md_j : md_k;
+        const double conu_p = last ? conu_j : conu_k, cond_p = last ? cond_j : cond_k;
+        const double chat_p = last ? chat_j : chat_k;
+        const double c_p = last ? c_km1 : c_k;  // const(kp1): c_km1 currently holds level jl
+        const double cj = c_km1;                // const(jl)
+        double dc = 0.0;
+        if (jl >= ktm) {
+          const double fluxin = mu_p * conu_p + mu_j * fmin2(chat_j, c_jm1) - (md_j * cond_j + md_p * fmin2(chat_p, c_p));
+          const double fluxout = mu_j * conu_j + mu_p * fmin2(chat_p, cj) - (md_p * cond_p + md_j * fmin2(chat_j, cj));
+          double netflux = fluxin - fluxout;
+          if (fabs(netflux) < fmax2(fluxin, fluxout) * 1.e-12) netflux = 0.0;
+          dc = netflux / dpt_j;
+        }
+        if (jl >= kbm) {
+          if (jl == mx) {
+            const double fluxin = mu_j * fmin2(chat_j, c_jm1) - md_j * cond_j;
+            const double fluxout = mu_j * conu_j - md_j * fmin2(chat_j, cj);
+            double netflux = fluxin - fluxout;
+            if (fabs(netflux) < fmax2(fluxin, fluxout) * 1.e-12) netflux = 0.0;
+            dc = netflux / dpt_j;
+          } else if (jl > mx) {
+            dc = 0.0;
+          }
+        }
+        a.dqdt[QI(jl)] = dc;
+      }
+      // shift
+      c_jm1 = (k == 1) ? c_k : c_km1;           // for the next finished level j' = k: const(max(1, k-1))
+      chat_j = chat_k; conu_j = conu_k; cond_j = cond_k; mu_j = mu_k; md_j = md_k; dpt_j = dpt_k;
+      cond_km1 = cond_k; md_km1 = md_k; t_km1 = t_k;
+      c_km1 = c_k; c_k = c_kp1;
+    }
+  }
+#undef GA
+#undef QI
 }
+

@@ -46,6 +46,8 @@ struct Workspace {
   std::vector<cudaEvent_t> tev;
   int* last_count = nullptr;          // device: [0]=n pass-1, [1]=n final, [2]=brent failures
   double* last_err = nullptr;
+  cudaStream_t side = nullptr;        // zm_conv_evap runs here, concurrently with momtran
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int ensure(size_t bytes) {
     if (!stream) CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (bytes > dcap) {
@@ -192,15 +194,15 @@ int evap_launch(cudaStream_t s, const EvapArgs& a) {
 int momtran_launch(Workspace& ws, cudaStream_t s, MomArgs a, bool own_arena = true) {
   const int pcols = g_params.pcols, pver = g_params.pver;
   const int ncolpad = a.nchunks * pcols;
-  if (own_arena && ws.ensure(2 * al(a.nchunks, 4) + 1024)) return -100;
+  if (own_arena && ws.ensure(2 * al(a.nchunks, 4) + al(ncolpad, 4) + 2048)) return -100;
   int* ktm = ws.take<int>(a.nchunks); int* kbm = ws.take<int>(a.nchunks);
-  a.ktm = ktm; a.kbm = kbm;
-  k_chunk_bounds<<<(a.nchunks * 32 + 127) / 128, 128, 0, s>>>(a.nchunks, a.jt, a.mx, a.lengath, ktm, kbm);
+  int* slots = ws.take<int>(ncolpad); int* count = ws.take<int>(1);
+  a.ktm = ktm; a.kbm = kbm; a.slots = slots; a.count = count;
+  CK(cudaMemsetAsync(count, 0, sizeof(int), s));
+  k_chunk_bounds<<<(a.nchunks * 32 + 127) / 128, 128, 0, s>>>(a.nchunks, a.jt, a.mx, a.lengath, ktm, kbm, slots, count);
   ++tls_launches;
   k_momtran_init<<<592, 256, 0, s>>>(a); ++tls_launches;
-  const size_t smem = momtran_smem_bytes(pver);
-  CK(cudaFuncSetAttribute(k_momtran_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_momtran_w<<<(ncolpad + MOM_WARPS - 1) / MOM_WARPS, 32 * MOM_WARPS, smem, s>>>(a);
+  k_momtran_t<<<(ncolpad + 63) / 64, 64, 0, s>>>(a);
   ++tls_launches;
   CK(cudaGetLastError());
   return 0;
@@ -215,22 +217,22 @@ int convtran_launch(Workspace& ws, cudaStream_t s, TranArgs a, const int* doconv
     if (doconvtran_h[m]) active.push_back(m);
   a.nactive = (int)active.size();
   if (a.nactive == 0) return 0;
-  if (ws.ensure(2 * al(a.nchunks, 4) + al(a.nactive, 4) + al(a.ncnst, 4) + 1024)) return -100;
+  if (ws.ensure(2 * al(a.nchunks, 4) + al(a.nactive, 4) + al(a.ncnst, 4) + al(ncolpad, 4) + 2048)) return -100;
   int* ktm = ws.take<int>(a.nchunks); int* kbm = ws.take<int>(a.nchunks);
+  int* slots = ws.take<int>(ncolpad); int* count = ws.take<int>(1);
+  a.slots = slots; a.count = count;
+  CK(cudaMemsetAsync(count, 0, sizeof(int), s));
   int* act_d = ws.take<int>(a.nactive); int* dry_d = ws.take<int>(a.ncnst);
   CK(cudaMemcpyAsync(act_d, active.data(), a.nactive * sizeof(int), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(dry_d, is_dry_h, a.ncnst * sizeof(int), cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));            // `active` is a stack vector: copy must finish first
   a.ktm = ktm; a.kbm = kbm; a.active = act_d; a.is_dry = dry_d;
-  k_chunk_bounds<<<(a.nchunks * 32 + 127) / 128, 128, 0, s>>>(a.nchunks, a.jt, a.mx, a.lengath, ktm, kbm);
+  k_chunk_bounds<<<(a.nchunks * 32 + 127) / 128, 128, 0, s>>>(a.nchunks, a.jt, a.mx, a.lengath, ktm, kbm, slots, count);
   ++tls_launches;
-  k_convtran_zero<<<1184, 256, 0, s>>>(a); ++tls_launches;
-  const int L = lmax_for(pver);
+  k_convtran_zero<<<a.nchunks * a.nactive, 128, 0, s>>>(a); ++tls_launches;
   dim3 blk(32, 4);
   dim3 grd((ncolpad + 31) / 32, (a.nactive + 3) / 4);
-  if (L == 32)      k_convtran<32><<<grd, blk, 0, s>>>(a);
-  else if (L == 64) k_convtran<64><<<grd, blk, 0, s>>>(a);
-  else              k_convtran<128><<<grd, blk, 0, s>>>(a);
+  k_convtran_t<<<grd, blk, 0, s>>>(a);
   ++tls_launches;
   CK(cudaGetLastError());
   return 0;
@@ -599,7 +601,7 @@ int zm_momtran_batch_dev(int nchunks, const int* ncol, const int* domomtran, con
   cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
   MomArgs a;
   a.nchunks = nchunks; a.ncnst = ncnst; a.ncol = ncol; a.jt = jt; a.mx = mx; a.ideep = ideep;
-  a.lengath = lengath; a.ktm = nullptr; a.kbm = nullptr;
+  a.lengath = lengath; a.ktm = nullptr; a.kbm = nullptr; a.slots = nullptr; a.count = nullptr;
   a.domom[0] = domomtran[0]; a.domom[1] = domomtran[1];
   a.q = q; a.mu = mu; a.md = md; a.du = du; a.eu = eu; a.ed = ed; a.dp = dp;
   a.dqdt = dqdt; a.pguall = pguall; a.pgdall = pgdall; a.icwu = icwu; a.icwd = icwd; a.seten = seten;
@@ -699,7 +701,7 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
   const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc;
   const size_t n2 = nc * L, n2p = nc * (L + 1);
   Workspace& ws = tls_work;
-  if (ws.ensure(convr_work_bytes(nc, (int)L) + 18 * al(n2, 8) + 6 * al(2 * n2, 8) + 2 * al(nchunks, 4) + 8192))
+  if (ws.ensure(convr_work_bytes(nc, (int)L) + 18 * al(n2, 8) + 6 * al(2 * n2, 8) + 2 * al(nchunks, 4) + al(nc, 4) + 8192))
     return -100;
   cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
   double *heat = ws.take<double>(n2), *qtnd = ws.take<double>(n2), *eurt = ws.take<double>(n2),
@@ -720,8 +722,21 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
   tick(ws, s, "state_update");
   EvapArgs ea{nchunks, ncol, t1, pmid, pdel, q1, landfrac, rprd, cld, ev_s, snwprd, snwevmlt, ev_q,
               prec, snow, ntprprd, ntsnprd, flxprec, flxsnow, ztodt};
-  rc = evap_launch(s, ea);
+  // zm_conv_evap and momtran both depend only on zm_convr's outputs (zm_conv_intr.F90:764, 822): evap
+  // goes to a side stream and overlaps momtran (kept serial while per-kernel profiling is on)
+  const bool fork = !g_profile;
+  if (fork) {
+    if (!ws.side) {
+      CK(cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ws.ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ws.ev_join, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(ws.ev_fork, s));
+    CK(cudaStreamWaitEvent(ws.side, ws.ev_fork, 0));
+  }
+  rc = evap_launch(fork ? ws.side : s, ea);
   if (rc) return rc;
+  if (fork) CK(cudaEventRecord(ws.ev_join, ws.side));
   tick(ws, s, "zm_conv_evap");
   MomArgs ma;
   ma.nchunks = nchunks; ma.ncnst = 2; ma.ncol = ncol; ma.jt = jt; ma.mx = maxg; ma.ideep = ideep;
@@ -732,6 +747,7 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
   rc = momtran_launch(ws, s, ma, false);
   if (rc) return rc;
   tick(ws, s, "momtran");
+  if (fork) CK(cudaStreamWaitEvent(s, ws.ev_join, 0));
   k_tend_finalize<<<1184, 256, 0, s>>>((int)n2, (int)n2p, nper, heat, qtnd, ev_s, ev_q, seten, wtend, ptend_s,
                                        ptend_q, ptend_u, ptend_v, evapcdp, mcon);
   ++tls_launches;
