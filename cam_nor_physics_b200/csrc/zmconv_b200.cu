@@ -157,17 +157,22 @@ int read_failures(Workspace& ws, cudaStream_t s) {
 struct Stager {      // host-pointer API: bump-allocate device copies of user arrays
   Workspace& ws; cudaStream_t s; int rc = 0;
   struct Out { void* h; void* d; size_t bytes; };
-  std::vector<Out> outs;
+  std::vector<Out> outs, early;
   Stager(Workspace& w) : ws(w), s(w.stream) {}
-  template <class T> const T* in(const T* h, size_t n) {
+  template <class T> const T* in(const T* h, size_t n, cudaStream_t on = nullptr) {
     T* d = ws.take<T>(n);
-    if (cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, s) != cudaSuccess) rc = -100;
+    if (cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, on ? on : s) != cudaSuccess) rc = -100;
     return d;
   }
-  template <class T> T* out(T* h, size_t n) {
+  template <class T> T* out(T* h, size_t n, bool is_early = false) {
     T* d = ws.take<T>(n);
-    outs.push_back({(void*)h, (void*)d, n * sizeof(T)});
+    (is_early ? early : outs).push_back({(void*)h, (void*)d, n * sizeof(T)});
     return d;
+  }
+  void flush_early(cudaStream_t on) {      // D2H of outputs that are final before the step ends
+    for (auto& o : early)
+      if (cudaMemcpyAsync(o.h, o.d, o.bytes, cudaMemcpyDeviceToHost, on) != cudaSuccess) rc = -100;
+    early.clear();
   }
   template <class T> T* inout(T* h, size_t n) {
     T* d = ws.take<T>(n);
@@ -686,7 +691,11 @@ int zm_convtran_batch(int nchunks, const int* doconvtran, const double* q, int n
 
 // zm_conv_tend (zm_conv_intr.F90:390-951, microphysics/org/convtran1 parts excluded): zm_convr ->
 // physics_update -> zm_conv_evap -> momtran, everything resident on the device.
-int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
+}  // extern "C"
+namespace {
+// events the host-pointer API uses to overlap PCIe copies with the kernels
+struct TendHooks { cudaEvent_t late_inputs; cudaEvent_t convr_done; };
+int conv_tend_impl(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
                            const double* v, const double* pmid, const double* pint, const double* pdel,
                            const double* zm, const double* zi, const double* phis, const double* pblh,
                            const double* tpert, const double* landfrac, const double* cld, double ztodt,
@@ -695,7 +704,8 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
                            double* jcbot, double* prec, double* snow, double* ql, double* rprd,
                            double* evapcdp, double* flxprec, double* flxsnow, double* dlf, double* mu,
                            double* md, double* du, double* eu, double* ed, double* dp, double* dsubcld,
-                           int* jt, int* maxg, int* ideep, int* lengath, double* cape, void* stream) {
+                           int* jt, int* maxg, int* ideep, int* lengath, double* cape, void* stream,
+                           const TendHooks* hooks) {
   NEED_INIT();
   if (nchunks <= 0) return 0;
   const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc;
@@ -716,6 +726,10 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
              mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, lengath, ql, rliq, dif, dnlf, dnif, rice};
   int rc = convr_launch(ws, s, in, o, false);
   if (rc) return rc;
+  if (hooks) {
+    CK(cudaEventRecord(hooks->convr_done, s));            // zm_convr outputs are final from here on
+    CK(cudaStreamWaitEvent(s, hooks->late_inputs, 0));    // u, v, cld have arrived
+  }
   const int nper = (int)(pc * L);
   k_state_update<<<1184, 256, 0, s>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
   ++tls_launches;
@@ -755,6 +769,24 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
   CK(cudaGetLastError());
   return 0;
 }
+}  // namespace
+extern "C" {
+
+int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
+                           const double* v, const double* pmid, const double* pint, const double* pdel,
+                           const double* zm, const double* zi, const double* phis, const double* pblh,
+                           const double* tpert, const double* landfrac, const double* cld, double ztodt,
+                           double* ptend_s, double* ptend_q, double* ptend_u, double* ptend_v, double* mcon,
+                           double* cme, double* pflx, double* zdu, double* rliq, double* rice, double* jctop,
+                           double* jcbot, double* prec, double* snow, double* ql, double* rprd,
+                           double* evapcdp, double* flxprec, double* flxsnow, double* dlf, double* mu,
+                           double* md, double* du, double* eu, double* ed, double* dp, double* dsubcld,
+                           int* jt, int* maxg, int* ideep, int* lengath, double* cape, void* stream) {
+  return conv_tend_impl(nchunks, ncol, t, q, u, v, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac, cld,
+                        ztodt, ptend_s, ptend_q, ptend_u, ptend_v, mcon, cme, pflx, zdu, rliq, rice, jctop, jcbot,
+                        prec, snow, ql, rprd, evapcdp, flxprec, flxsnow, dlf, mu, md, du, eu, ed, dp, dsubcld, jt,
+                        maxg, ideep, lengath, cape, stream, nullptr);
+}
 
 int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
                        const double* v, const double* pmid, const double* pint, const double* pdel,
@@ -774,23 +806,36 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   if (st.ensure(al(nchunks, 4) + 24 * al(n2, 8) + 6 * al(n2p, 8) + 14 * al(nc, 8) + 4 * al(nc, 4) + 8192))
     return -100;
   Stager S(st);
+  // PCIe overlap: inputs that only the later stages read (u, v, cld) travel on a copy stream while pass 1
+  // runs; zm_convr's final outputs start their D2H on that stream while evap/momtran still run.
+  if (!st.side) {
+    CK(cudaStreamCreateWithFlags(&st.side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&st.ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&st.ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t cp = st.side;
+  TendHooks hooks{st.ev_fork /* late inputs */, st.ev_join /* convr done */};
   const int* d_ncol = S.in(ncol, nchunks);
-  const double *d_t = S.in(t, n2), *d_q = S.in(q, n2), *d_u = S.in(u, n2), *d_v = S.in(v, n2),
-               *d_pmid = S.in(pmid, n2), *d_pint = S.in(pint, n2p), *d_pdel = S.in(pdel, n2),
-               *d_zm = S.in(zm, n2), *d_zi = S.in(zi, n2p), *d_phis = S.in(phis, nc),
-               *d_pblh = S.in(pblh, nc), *d_tpert = S.in(tpert, nc), *d_lf = S.in(landfrac, nc),
-               *d_cld = S.in(cld, n2);
-  int rc = zm_conv_tend_batch_dev(
+  const double *d_t = S.in(t, n2), *d_q = S.in(q, n2), *d_pmid = S.in(pmid, n2), *d_pint = S.in(pint, n2p),
+               *d_pdel = S.in(pdel, n2), *d_zm = S.in(zm, n2), *d_zi = S.in(zi, n2p), *d_phis = S.in(phis, nc),
+               *d_pblh = S.in(pblh, nc), *d_tpert = S.in(tpert, nc), *d_lf = S.in(landfrac, nc);
+  const double *d_u = S.in(u, n2, cp), *d_v = S.in(v, n2, cp), *d_cld = S.in(cld, n2, cp);
+  CK(cudaEventRecord(hooks.late_inputs, cp));
+  const bool E = true;      // final after zm_convr
+  int rc = conv_tend_impl(
       nchunks, d_ncol, d_t, d_q, d_u, d_v, d_pmid, d_pint, d_pdel, d_zm, d_zi, d_phis, d_pblh, d_tpert, d_lf,
       d_cld, ztodt, S.out(ptend_s, n2), S.out(ptend_q, n2), S.out(ptend_u, n2), S.out(ptend_v, n2),
-      S.out(mcon, n2p), S.out(cme, n2), S.out(pflx, n2p), S.out(zdu, n2), S.out(rliq, nc), S.out(rice, nc),
-      S.out(jctop, nc), S.out(jcbot, nc), S.out(prec, nc), S.out(snow, nc), S.out(ql, n2), S.out(rprd, n2),
-      S.out(evapcdp, n2), S.out(flxprec, n2p), S.out(flxsnow, n2p), S.out(dlf, n2), S.out(mu, n2),
-      S.out(md, n2), S.out(du, n2), S.out(eu, n2), S.out(ed, n2), S.out(dp, n2), S.out(dsubcld, nc),
-      S.out(jt, nc), S.out(maxg, nc), S.out(ideep, nc), S.out(lengath, (size_t)nchunks), S.out(cape, nc),
-      (void*)st.stream);
+      S.out(mcon, n2p), S.out(cme, n2, E), S.out(pflx, n2p, E), S.out(zdu, n2, E), S.out(rliq, nc, E),
+      S.out(rice, nc, E), S.out(jctop, nc, E), S.out(jcbot, nc, E), S.out(prec, nc), S.out(snow, nc),
+      S.out(ql, n2, E), S.out(rprd, n2, E), S.out(evapcdp, n2), S.out(flxprec, n2p), S.out(flxsnow, n2p),
+      S.out(dlf, n2, E), S.out(mu, n2, E), S.out(md, n2, E), S.out(du, n2, E), S.out(eu, n2, E), S.out(ed, n2, E),
+      S.out(dp, n2, E), S.out(dsubcld, nc, E), S.out(jt, nc, E), S.out(maxg, nc, E), S.out(ideep, nc, E),
+      S.out(lengath, (size_t)nchunks, E), S.out(cape, nc, E), (void*)st.stream, &hooks);
   if (rc) return rc;
+  CK(cudaStreamWaitEvent(cp, hooks.convr_done, 0));
+  S.flush_early(cp);
   if (S.flush()) return -100;
+  CK(cudaStreamSynchronize(cp));
   return read_failures(tls_work, st.stream);
 }
 
