@@ -314,6 +314,139 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
 #undef IN2P
 }
 
+// ---- buoyan: undilute CAPE (cam3 physics only), one thread per column ---------------------------------
+// zm_conv.F90:2719-3022, reached when cam_physpkg_is('cam3') (zm_conv.F90:871-880) as the FIRST trigger
+// pass; the second pass is buoyan_dilute like everywhere else (zm_conv.F90:1080).  The reference then
+// tests an undefined `cin` at zm_conv.F90:909 (buoyan does not set it): this build defines cin = 0 for
+// that first test.  lelten/capeten are 5 wide as the reference's `do n = 1,5` loops assume.
+__global__ void __launch_bounds__(128)
+k_buoyan_undilute(ConvrIn in, ConvrWork w) {
+  extern __shared__ double sm_buoy[];
+  const int pcols = P.pcols, pver = P.pver, msg = P.msg;
+  const int ncolpad = in.nchunks * pcols;
+  const int nthr = blockDim.x;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncolpad) return;
+  const int c = col / pcols, i = col - c * pcols;
+  if (i >= in.ncol[c]) return;
+#define BUOY(k) sm_buoy[(k) * nthr + threadIdx.x]
+#define IN2(a, k) in.a[cidx(c, (k) - 1, i, pver)]
+#define IN2P(a, k) in.a[cidx(c, (k) - 1, i, pver + 1)]
+  const double eps1 = P.eps1, grav = P.grav, cp = P.cpres, rl = P.rl, rd = P.rgas;
+  const double zs = in.geos[(size_t)c * pcols + i] * P.rgrav;
+  const double pblh = in.pblh[(size_t)c * pcols + i];
+  const double tpert = in.tpert[(size_t)c * pcols + i];
+  int pblt = pver;
+  for (int k = pver - 1; k >= msg + 1; --k) {
+    double zk = IN2(zm, k) + zs;
+    double zfk = IN2P(zi, k) + zs, zfk1 = IN2P(zi, k + 1) + zs;
+    if (fabs(zk - zs - pblh) < (zfk - zfk1) * 0.5) pblt = k;
+  }
+  const int lon = pver;
+  int mx = lon;
+  double hmax = 0.0;
+  for (int k = pver; k >= msg + 1; --k) {
+    const double hmn = cp * IN2(t, k) + grav * (IN2(zm, k) + zs) + rl * IN2(qh, k);
+    if (k >= pblt && k <= lon && hmn > hmax) { hmax = hmn; mx = k; }
+  }
+  const double t_mx = IN2(t, mx), q_mx = IN2(qh, mx), p_mx = IN2(pap, mx) * 0.01;
+  int lcl = mx;
+  const double e = p_mx * q_mx / (eps1 + q_mx);
+  double tl = 2840.0 / (3.5 * zmm::log_(t_mx) - zmm::log_(e) - 4.805) + 55.0;
+  double pl;
+  if (tl < t_mx) {
+    const double plexp = (1.0 / (0.2854 * (1.0 - 0.28 * q_mx)));
+    pl = p_mx * zmm::pow_(tl / t_mx, plexp);
+  } else {
+    tl = t_mx;
+    pl = p_mx;
+  }
+  for (int k = pver; k >= msg + 2; --k)
+    if (k <= mx && (IN2(pap, k) * 0.01 > pl && IN2(pap, k - 1) * 0.01 <= pl)) lcl = k - 1;
+  const bool plge600 = pl >= P.plclmin;
+
+  double* tp_o = w.tp + col;
+  double* qstp_o = w.qstp + col;
+  double tp_p = 0.0, qstp_p = 0.0, p_p = 0.0;        // parcel at level k+1
+  for (int k = pver; k >= 1; --k) {
+    const double tk = IN2(t, k), qk = IN2(qh, k), pk = IN2(pap, k) * 0.01;
+    double tpk = tk, qstpk = qk;                      // defaults (zm_conv.F90:2822-2823)
+    if (k >= msg + 1 && plge600) {
+      const double tv = tk * (1.0 + 1.608 * qk) / (1.0 + qk);
+      bool parcel = false;
+      double tpv = 0.0;
+      if (k > lcl && k <= mx) {                        // sub-cloud layer, zm_conv.F90:2896-2911
+        qstpk = q_mx;
+        tpk = t_mx * zmm::pow_(pk / p_mx, 0.2854 * (1.0 - 0.28 * q_mx));
+        tpv = (tpk + tpert) * (1.0 + 1.608 * q_mx) / (1.0 + q_mx);
+        parcel = true;
+      } else if (k == lcl || (k < lcl && k <= pver - 1)) {
+        double ybase;
+        if (k == lcl) {                                // zm_conv.F90:2916-2948
+          qstpk = q_mx;
+          tpk = tl * zmm::pow_(pk / pl, 0.2854 * (1.0 - 0.28 * qstpk));
+          ybase = q_mx;
+        } else {                                       // zm_conv.F90:2952-2976
+          qstpk = qstp_p;
+          tpk = tp_p * zmm::pow_(pk / p_p, 0.2854 * (1.0 - 0.28 * qstpk));
+          ybase = qstp_p;
+        }
+        double est;
+        qsat_hPa(tpk, pk, est, qstpk);
+        double a1 = cp / rl + qstpk * (1.0 + qstpk / eps1) * rl * eps1 / (rd * (tpk * tpk));
+        double a2 = .5 * (qstpk * (1.0 + 2.0 / eps1 * qstpk) * (1.0 + qstpk / eps1) * (eps1 * eps1) * rl * rl /
+                              ((rd * rd) * ((tpk * tpk) * (tpk * tpk))) -
+                          qstpk * (1.0 + qstpk / eps1) * 2.0 * eps1 * rl / (rd * ((tpk * tpk) * tpk)));
+        a1 = 1.0 / a1;
+        a2 = -a2 * ((a1 * a1) * a1);
+        const double y = ybase - qstpk;
+        tpk = tpk + a1 * y + a2 * (y * y);
+        qsat_hPa(tpk, pk, est, qstpk);
+        tpv = (tpk + tpert) * (1.0 + 1.608 * qstpk) / (1.0 + q_mx);
+        parcel = true;
+      }
+      BUOY(k) = parcel ? (tpv - tv + P.tiedke_add) : 0.0;
+    } else {
+      BUOY(k) = 0.0;
+    }
+    tp_o[(size_t)(k - 1) * ncolpad] = tpk;
+    qstp_o[(size_t)(k - 1) * ncolpad] = qstpk;
+    tp_p = tpk; qstp_p = qstpk; p_p = pk;
+  }
+  double cape = 0.0;
+  int lel = pver;
+  if (plge600) {
+    int lelten[5];
+    double capeten[5];
+#pragma unroll
+    for (int n = 0; n < 5; ++n) { lelten[n] = pver; capeten[n] = 0.0; }
+    int knt = 0;
+    for (int k = msg + 2; k <= pver; ++k)
+      if (k < lcl)
+        if (BUOY(k + 1) > 0.0 && BUOY(k) <= 0.0) {
+          knt = min(5, knt + 1);
+#pragma unroll
+          for (int n = 0; n < 5; ++n) if (n == knt - 1) lelten[n] = k;
+        }
+    for (int k = msg + 1; k <= mx; ++k) {
+      const double lg = zmm::log_((IN2P(paph, k + 1) * 0.01) / (IN2P(paph, k) * 0.01));
+      const double b = BUOY(k);
+#pragma unroll
+      for (int n = 0; n < 5; ++n)
+        if (k > lelten[n]) capeten[n] = capeten[n] + rd * b * lg;
+    }
+#pragma unroll
+    for (int n = 0; n < 5; ++n)
+      if (capeten[n] > cape) { cape = capeten[n]; lel = lelten[n]; }
+    cape = fmax2(cape, 0.0);
+  }
+  w.cape[col] = cape; w.cin[col] = 0.0; w.tl[col] = tl;
+  w.lcl[col] = lcl; w.lel[col] = lel; w.mx[col] = mx;
+#undef BUOY
+#undef IN2
+#undef IN2P
+}
+
 // ---- trigger + order-preserving compaction, one warp per chunk -------------------------------
 // zm_conv.F90:905-915 (FINAL=0: pass-1 worklist) and 1095-1111 (FINAL=1: ideep/lengath outputs).
 template <int FINAL>

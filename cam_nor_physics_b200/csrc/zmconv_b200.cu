@@ -112,11 +112,14 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   if (smem > 48 * 1024) {
     CK(cudaFuncSetAttribute(k_buoyan_dilute<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_buoyan_dilute<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_buoyan_undilute, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   tick(ws, s, "start");
   k_convr_init<<<592, 256, 0, s>>>(in, o, w); ++tls_launches;
   tick(ws, s, "convr_init");
-  k_buoyan_dilute<1><<<nblk_cols, TB, smem, s>>>(in, w); ++tls_launches;
+  if (g_params.cam3) k_buoyan_undilute<<<nblk_cols, TB, smem, s>>>(in, w);     // zm_conv.F90:871-880
+  else               k_buoyan_dilute<1><<<nblk_cols, TB, smem, s>>>(in, w);
+  ++tls_launches;
   tick(ws, s, "buoyan_dilute_pass1");
   k_trigger<0><<<nwarpblk, 128, 0, s>>>(in, o, w); ++tls_launches;
   tick(ws, s, "trigger_pass1");
@@ -404,7 +407,10 @@ int zm_init(const zm_params_t* p) {
   if (p->zm_org || p->microp) { tls_err = "zm_org / zmconv_microp are out of scope (zm_microphysics absent)"; return -2; }
   if (p->masterproc && p->num_cin > 5) { tls_err = "**** ZM_CONVI : NUM_CIN must not exceeed 5 ****"; return -3; }
   if (p->num_cin < 1 || p->num_cin > ZM_MAXCIN) { tls_err = "num_cin out of range 1..5"; return -3; }
-  if (p->cam3) { tls_err = "cam3 (undilute buoyan) path: reference reads an undefined cin (zm_conv.F90:909); not supported"; return -4; }
+  if (p->cam3 && p->num_cin != 5) {
+    // buoyan declares capeten(pcols,num_cin) but loops n = 1,5 (zm_conv.F90:2770 vs 2992,3006)
+    tls_err = "cam3 (undilute buoyan) is only well defined for num_cin = 5"; return -4;
+  }
   if (lmax_for(p->pver) == 0 || p->pcols < 1 || p->limcnv < 2 || p->limcnv > p->pver) {
     tls_err = "unsupported grid (need 1 <= pver <= 128, 2 <= limcnv <= pver)"; return -5;
   }

@@ -57,6 +57,7 @@ def test_thermo_scalars_match_oracle(built):
     (1024, 0.7, 32, {"num_cin": 3}),            # several negative-buoyancy regions allowed
     (1024, 0.7, 32, {"no_deep_pbl": 1}),
     (1024, 0.7, 32, {"masterproc": 0, "dmpdz": -0.5e-3}),   # tentrm quirk (zm_conv.F90:213)
+    (2048, 0.6, 32, {"cam3": 1, "num_cin": 5}),  # cam3: undilute buoyan as first trigger pass (zm_conv.F90:871)
 ])
 def test_zm_convr_bit_exact_vs_oracle(built, ncols, pconv, pver, over):
     Z = init_cuda(16, pver, **over)
@@ -227,3 +228,35 @@ def test_device_resident_path_and_conservation(built):
     assert np.isclose(c[0], (ch.pdel / g * ref["ptend_q"]).sum(), rtol=1e-12)
     assert np.isclose(c[1], 1000.0 * (ref["prec"] + ref["rliq"]).sum(), rtol=1e-12)
     assert c[4] == ref["lengath"].sum() and c[5] == 4096
+
+
+def test_momtran_component_flags_and_reentrancy(built):
+    """domomtran(m) = .false. leaves that component's outputs untouched (zm_conv.F90:2458); and the
+    library is re-entrant: two host threads driving different chunk sets concurrently get the same
+    answers as serial calls (reference call pattern: OpenMP threads, physpkg.F90:1147)."""
+    import threading
+    Z = init_cuda(16, 32)
+    o, _, _ = get_oracle("pm", 16, 32)
+    ch = S.make_chunks(640, 32, 16, p_conv=0.7)
+    ref = o.convr_batch(ch)
+    winds = np.stack([ch.u, ch.v], axis=1)
+    mo = Z.momtran(ch.ncol, [1, 0], winds, ref["mu"], ref["md"], ref["du"], ref["eu"], ref["ed"], ref["dp"],
+                   ref["dsubcld"], ref["jt"], ref["maxg"], ref["ideep"], ref["lengath"], ch.ztodt)
+    for c in range(ch.nchunks):
+        r = o.momtran(int(ch.ncol[c]), [1, 0], winds[c], ref["mu"][c], ref["md"][c], ref["du"][c], ref["eu"][c],
+                      ref["ed"][c], ref["dp"][c], ref["dsubcld"][c], ref["jt"][c], ref["maxg"][c], ref["ideep"][c],
+                      ref["lengath"][c], ch.ztodt)
+        for k in ["dqdt", "pguall", "pgdall", "icwu", "icwd", "seten"]:
+            assert np.array_equal(mo[k][c], r[k]), (c, k)
+    res = {}
+
+    def work(tag, lo, hi):
+        sub = S.make_chunks(16 * (hi - lo), 32, 16, p_conv=0.7, col0=16 * lo)
+        res[tag] = cuda_convr(Z, sub)
+
+    ths = [threading.Thread(target=work, args=(i, 10 * i, 10 * i + 10)) for i in range(4)]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    for i in range(4):
+        sub = {k: v[10 * i: 10 * i + 10] for k, v in ref.items() if k != "rc"}
+        assert_same(res[i], sub, ["qtnd", "heat", "prec", "ideep", "lengath", "mu", "jt", "maxg", "pflx"], 16,
+                    exact=True, what=f"thread {i}")
