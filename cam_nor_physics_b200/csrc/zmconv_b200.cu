@@ -370,6 +370,8 @@ __global__ void k_microbench(double* out, long long* cyc, int n) {
   MB(invert_k(1, 3.5e5 + x, 900.0, 500.0, 0.015, 295.0, acc, q); x = 290.0 + 1e-3 * acc);  // 8 ienthalpy
   MB(invert_k(0, 250.0 + 1e-3 * x, 900.0, 0.0, 0.015, 295.0, acc, q); x = 290.0 + 1e-3 * acc);  // 9 ientropy
   MB(x = 300.0 + 1e-3 * zmm::pow_(x, 0.2857));                           // 10 pow
+  { double f1, f2, q1, q2;
+    MB(state_fn_dual(x, 900.0, 0.015, 500.0, x + 1.0, 900.0, 0.015, f1, q1, f2, q2); x = 300.0 + 1e-9 * f1 + 1e-6 * f2); }  // 11 dual
   out[threadIdx.x] = x + acc;
 }
 __global__ void k_fp64_peak(double* out, int iters) {
@@ -910,7 +912,7 @@ int zm_microbench(long long* cycles11, int n) {
   CK(cudaMalloc(&d, 32 * sizeof(double))); CK(cudaMalloc(&c, 16 * sizeof(long long)));
   CK(cudaMemset(c, 0, 16 * sizeof(long long)));
   k_microbench<<<1, 32>>>(d, c, n); ++tls_launches;
-  CK(cudaMemcpy(cycles11, c, 11 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cycles11, c, 12 * sizeof(long long), cudaMemcpyDeviceToHost));
   cudaFree(d); cudaFree(c);
   return 0;
 }
