@@ -428,3 +428,78 @@ k_convtran_t(TranArgs a) {
 #undef QI
 }
 
+
+// ---- N4 neighbours of the path ------------------------------------------------
+// geopotential_t (physics/geopotential.F90:153-247): thread per column, bottom-up scan, registers only.
+struct GeoArgs {
+  int nchunks, dycore_lr;
+  const int* ncol;
+  const double *piln, *pint, *pmid, *pdel, *rpdel, *t, *q, *rair, *zvir;
+  double gravit;
+  double *zi, *zm;
+};
+__global__ void __launch_bounds__(128)
+k_geopotential_t(GeoArgs a) {
+  const int pcols = P.pcols, pver = P.pver, pverp = P.pverp;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= a.nchunks * pcols) return;
+  const int c = col / pcols, i = col - c * pcols;
+  if (i >= a.ncol[c]) return;
+  double zi_p = 0.0;
+  a.zi[cidx(c, pverp - 1, i, pverp)] = 0.0;
+  for (int k = pver; k >= 1; --k) {
+    const size_t e = cidx(c, k - 1, i, pver);
+    double hkl, hkk;
+    if (a.dycore_lr) {
+      hkl = a.piln[cidx(c, k, i, pverp)] - a.piln[cidx(c, k - 1, i, pverp)];
+      hkk = 1.0 - a.pint[cidx(c, k - 1, i, pverp)] * hkl * a.rpdel[e];
+    } else {
+      hkl = a.pdel[e] / a.pmid[e];
+      hkk = 0.5 * hkl;
+    }
+    const double rog = a.rair[e] / a.gravit;
+    const double tvfac = 1.0 + a.zvir[e] * a.q[e];
+    const double tv = a.t[e] * tvfac;
+    a.zm[e] = zi_p + rog * tv * hkk;
+    zi_p = zi_p + rog * tv * hkl;
+    a.zi[cidx(c, k - 1, i, pverp)] = zi_p;
+  }
+}
+
+// convect_diagnostics_calc for shallow_scheme == 'CLUBB_SGS' (physics/convect_diagnostics.F90:115-249)
+struct CdiagArgs {
+  int nchunks;
+  const int* ncol;
+  double *cmfmc, *qc, *qc2, *rliq, *rliq2, *cnt, *cnb, *cmfmc2, *rprdsh, *rprdtot, *pcnt, *pcnb;
+  const double *pmid, *rprddp;
+};
+__global__ void __launch_bounds__(128)
+k_convect_diagnostics(CdiagArgs a) {
+  const int pcols = P.pcols, pver = P.pver, pverp = P.pverp;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= a.nchunks * pcols) return;
+  const int c = col / pcols, i = col - c * pcols;
+  const bool real_col = i < a.ncol[c];
+  for (int k = 0; k < pverp; ++k) {
+    const size_t ep = cidx(c, k, i, pverp);
+    a.cmfmc2[ep] = 0.0;                                  // zeroed for all pcols (whole-array assignment)
+    if (real_col) a.cmfmc[ep] = a.cmfmc[ep] + 0.0;
+    if (k < pver) {
+      const size_t e = cidx(c, k, i, pver);
+      a.rprdsh[e] = 0.0; a.qc2[e] = 0.0;
+      if (real_col) { a.rprdtot[e] = 0.0 + a.rprddp[e]; a.qc[e] = a.qc[e] + 0.0; }
+    }
+  }
+  a.rliq2[col] = 0.0;
+  if (real_col) {
+    const double cnt2 = (double)pver, cnb2 = 1.0;
+    double cnt = a.cnt[col], cnb = a.cnb[col];
+    if (cnt2 < cnt) cnt = cnt2;
+    if (cnb2 > cnb) cnb = cnb2;
+    if (cnb == 1.0) cnb = cnt;
+    a.cnt[col] = cnt; a.cnb[col] = cnb;
+    a.pcnt[col] = a.pmid[cidx(c, (int)cnt - 1, i, pver)];
+    a.pcnb[col] = a.pmid[cidx(c, (int)cnb - 1, i, pver)];
+    a.rliq[col] = a.rliq[col] + 0.0;
+  }
+}

@@ -867,6 +867,76 @@ int zm_conservation_dev(int nchunks, const int* ncol, const double* pdel, const 
   return 0;
 }
 
+// ---- N4 neighbours: geopotential_t, convect_diagnostics_calc ----------------------------------------
+int zm_geopotential_t_batch_dev(int nchunks, const int* ncol, int dycore_lr, const double* piln,
+                                const double* pmln, const double* pint, const double* pmid, const double* pdel,
+                                const double* rpdel, const double* t, const double* q, const double* rair,
+                                double gravit, const double* zvir, double* zi, double* zm, void* stream) {
+  NEED_INIT();
+  (void)pmln;
+  if (nchunks <= 0) return 0;
+  GeoArgs a{nchunks, dycore_lr, ncol, piln, pint, pmid, pdel, rpdel, t, q, rair, zvir, gravit, zi, zm};
+  const int ncolpad = nchunks * g_params.pcols;
+  k_geopotential_t<<<(ncolpad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a); ++tls_launches;
+  CK(cudaGetLastError());
+  return 0;
+}
+int zm_geopotential_t_batch(int nchunks, const int* ncol, int dycore_lr, const double* piln, const double* pmln,
+                            const double* pint, const double* pmid, const double* pdel, const double* rpdel,
+                            const double* t, const double* q, const double* rair, double gravit,
+                            const double* zvir, double* zi, double* zm) {
+  NEED_INIT();
+  if (nchunks <= 0) return 0;
+  const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc, n2 = nc * L, n2p = nc * (L + 1);
+  Workspace& st = tls_stage;
+  if (st.ensure(al(nchunks, 4) + 8 * al(n2, 8) + 3 * al(n2p, 8) + 4096)) return -100;
+  Stager S(st);
+  const int* d_ncol = S.in(ncol, nchunks);
+  const double *d_piln = S.in(piln, n2p), *d_pint = S.in(pint, n2p), *d_pmid = S.in(pmid, n2), *d_pdel = S.in(pdel, n2),
+               *d_rpdel = S.in(rpdel, n2), *d_t = S.in(t, n2), *d_q = S.in(q, n2), *d_rair = S.in(rair, n2),
+               *d_zvir = S.in(zvir, n2);
+  double *d_zi = S.inout(zi, n2p), *d_zm = S.inout(zm, n2);
+  int rc = zm_geopotential_t_batch_dev(nchunks, d_ncol, dycore_lr, d_piln, nullptr, d_pint, d_pmid, d_pdel, d_rpdel,
+                                       d_t, d_q, d_rair, gravit, d_zvir, d_zi, d_zm, (void*)st.stream);
+  if (rc) return rc;
+  return S.flush();
+}
+
+int zm_convect_diagnostics_batch_dev(int nchunks, const int* ncol, double* cmfmc, double* qc, double* qc2,
+                                     double* rliq, double* rliq2, const double* pmid, const double* rprddp,
+                                     double* cnt, double* cnb, double* cmfmc2, double* rprdsh, double* rprdtot,
+                                     double* pcnt, double* pcnb, void* stream) {
+  NEED_INIT();
+  if (nchunks <= 0) return 0;
+  CdiagArgs a{nchunks, ncol, cmfmc, qc, qc2, rliq, rliq2, cnt, cnb, cmfmc2, rprdsh, rprdtot, pcnt, pcnb, pmid, rprddp};
+  const int ncolpad = nchunks * g_params.pcols;
+  k_convect_diagnostics<<<(ncolpad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a); ++tls_launches;
+  CK(cudaGetLastError());
+  return 0;
+}
+int zm_convect_diagnostics_batch(int nchunks, const int* ncol, double* cmfmc, double* qc, double* qc2,
+                                 double* rliq, double* rliq2, const double* pmid, const double* rprddp, double* cnt,
+                                 double* cnb, double* cmfmc2, double* rprdsh, double* rprdtot, double* pcnt,
+                                 double* pcnb) {
+  NEED_INIT();
+  if (nchunks <= 0) return 0;
+  const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc, n2 = nc * L, n2p = nc * (L + 1);
+  Workspace& st = tls_stage;
+  if (st.ensure(al(nchunks, 4) + 6 * al(n2, 8) + 2 * al(n2p, 8) + 6 * al(nc, 8) + 4096)) return -100;
+  Stager S(st);
+  const int* d_ncol = S.in(ncol, nchunks);
+  double *d_cmfmc = S.inout(cmfmc, n2p), *d_qc = S.inout(qc, n2), *d_qc2 = S.inout(qc2, n2),
+         *d_rliq = S.inout(rliq, nc), *d_rliq2 = S.inout(rliq2, nc), *d_cnt = S.inout(cnt, nc),
+         *d_cnb = S.inout(cnb, nc), *d_cmfmc2 = S.inout(cmfmc2, n2p), *d_rprdsh = S.inout(rprdsh, n2),
+         *d_rprdtot = S.inout(rprdtot, n2), *d_pcnt = S.inout(pcnt, nc), *d_pcnb = S.inout(pcnb, nc);
+  const double *d_pmid = S.in(pmid, n2), *d_rprddp = S.in(rprddp, n2);
+  int rc = zm_convect_diagnostics_batch_dev(nchunks, d_ncol, d_cmfmc, d_qc, d_qc2, d_rliq, d_rliq2, d_pmid, d_rprddp,
+                                            d_cnt, d_cnb, d_cmfmc2, d_rprdsh, d_rprdtot, d_pcnt, d_pcnb,
+                                            (void*)st.stream);
+  if (rc) return rc;
+  return S.flush();
+}
+
 // ---- diagnostics ---------------------------------------------------------------------------------
 int zm_math_eval_host(int id, int n, const double* x, const double* y, double* o) {
   for (int i = 0; i < n; ++i) {

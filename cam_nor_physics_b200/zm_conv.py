@@ -71,6 +71,8 @@ EXPORTS = [
     "zm_convr_batch_dev", "zm_conv_evap_batch", "zm_conv_evap_batch_dev", "zm_momtran_batch",
     "zm_momtran_batch_dev", "zm_convtran_batch", "zm_convtran_batch_dev", "zm_sync_check",
     "zm_conv_tend_batch", "zm_conv_tend_batch_dev", "zm_microbench", "zm_conservation_dev",
+    "zm_geopotential_t_batch", "zm_geopotential_t_batch_dev", "zm_convect_diagnostics_batch",
+    "zm_convect_diagnostics_batch_dev",
     "zm_math_eval_dev", "zm_math_eval_host", "zm_thermo_eval_dev", "zm_fp64_peak_flops",
     "zm_set_profiling", "zm_get_kernel_times", "zm_launch_count",
 ]
@@ -269,6 +271,39 @@ def zm_conv_tend(ncol, state: dict, ztodt: float, out: dict | None = None):
     rc = lib().zm_conv_tend_batch(*args)
     _check(rc, "zm_conv_tend")
     return out
+
+
+def geopotential_t(ncol, piln, pmln, pint, pmid, pdel, rpdel, t, q, rair, gravit, zvir, dycore_lr=True):
+    """geopotential_t (physics/geopotential.F90:153); returns (zi, zm)."""
+    pc, L = _grid()
+    ncol = _i(ncol)
+    nch = ncol.shape[0]
+    zi, zm = np.zeros((nch, L + 1, pc)), np.zeros((nch, L, pc))
+    piln, pmln, pint, pmid, pdel, rpdel, t, q, rair, zvir = map(_f, (piln, pmln, pint, pmid, pdel, rpdel, t, q, rair, zvir))
+    rc = lib().zm_geopotential_t_batch(C.c_int(nch), _ip(ncol), C.c_int(int(dycore_lr)), _dp(piln), _dp(pmln),
+                                       _dp(pint), _dp(pmid), _dp(pdel), _dp(rpdel), _dp(t), _dp(q), _dp(rair),
+                                       C.c_double(gravit), _dp(zvir), _dp(zi), _dp(zm))
+    _check(rc, "geopotential_t")
+    return zi, zm
+
+
+def convect_diagnostics_calc(ncol, cmfmc, qc, rliq, pmid, rprddp, cnt, cnb):
+    """convect_diagnostics_calc (physics/convect_diagnostics.F90:115) with shallow_scheme='CLUBB_SGS'.
+    Returns a dict with the updated inout fields and the outputs."""
+    pc, L = _grid()
+    ncol = _i(ncol)
+    nch = ncol.shape[0]
+    o = dict(cmfmc=_f(cmfmc).copy(), qc=_f(qc).copy(), qc2=np.ones((nch, L, pc)), rliq=_f(rliq).copy(),
+             rliq2=np.ones((nch, pc)), cnt=_f(cnt).copy(), cnb=_f(cnb).copy(), cmfmc2=np.ones((nch, L + 1, pc)),
+             rprdsh=np.ones((nch, L, pc)), rprdtot=np.zeros((nch, L, pc)), pcnt=np.zeros((nch, pc)),
+             pcnb=np.zeros((nch, pc)))
+    pmid, rprddp = _f(pmid), _f(rprddp)
+    rc = lib().zm_convect_diagnostics_batch(C.c_int(nch), _ip(ncol), _dp(o["cmfmc"]), _dp(o["qc"]), _dp(o["qc2"]),
+                                            _dp(o["rliq"]), _dp(o["rliq2"]), _dp(pmid), _dp(rprddp), _dp(o["cnt"]),
+                                            _dp(o["cnb"]), _dp(o["cmfmc2"]), _dp(o["rprdsh"]), _dp(o["rprdtot"]),
+                                            _dp(o["pcnt"]), _dp(o["pcnb"]))
+    _check(rc, "convect_diagnostics_calc")
+    return o
 
 
 # ---- diagnostics ---------------------------------------------------------------------------------

@@ -159,6 +159,31 @@ int zm_conservation_dev(int nchunks, const int* ncol, const double* pdel, const 
                         const double* ptend_s, const double* prec, const double* snow, const double* rliq,
                         const int* lengath, double* out6, void* stream);
 
+/* ---- "next" rows: neighbours of the path --------------------------------
+ * geopotential_t (physics/geopotential.F90:153-247): zm/zi from t,q,p; dycore_lr != 0 selects the FV
+ * ('LR') hydrostatic branch (:218-223), 0 the EUL/SE one (:224-233).  q is q(:,:,1); rair/zvir are
+ * (pcols,pver) like the reference's dummy arrays.  The generalized-Tv branch (:248-310) is not built. */
+int zm_geopotential_t_batch(int nchunks, const int* ncol, int dycore_lr, const double* piln, const double* pmln,
+                            const double* pint, const double* pmid, const double* pdel, const double* rpdel,
+                            const double* t, const double* q, const double* rair, double gravit,
+                            const double* zvir, double* zi, double* zm);
+int zm_geopotential_t_batch_dev(int nchunks, const int* ncol, int dycore_lr, const double* piln,
+                            const double* pmln, const double* pint, const double* pmid, const double* pdel,
+                            const double* rpdel, const double* t, const double* q, const double* rair,
+                            double gravit, const double* zvir, double* zi, double* zm, void* stream);
+/* convect_diagnostics_calc (physics/convect_diagnostics.F90:115-249) for shallow_scheme='CLUBB_SGS', the
+ * only configuration in which its locals cnt2/cnb2 are defined (:187-198): zeroes the shallow-scheme
+ * fields, merges them into cmfmc/qc/rliq, merges cloud top/bottom indices and looks up their pressures,
+ * rprdtot = rprdsh + rprddp. */
+int zm_convect_diagnostics_batch(int nchunks, const int* ncol, double* cmfmc, double* qc, double* qc2,
+                            double* rliq, double* rliq2, const double* pmid, const double* rprddp, double* cnt,
+                            double* cnb, double* cmfmc2, double* rprdsh, double* rprdtot, double* pcnt,
+                            double* pcnb);
+int zm_convect_diagnostics_batch_dev(int nchunks, const int* ncol, double* cmfmc, double* qc, double* qc2,
+                            double* rliq, double* rliq2, const double* pmid, const double* rprddp, double* cnt,
+                            double* cnb, double* cmfmc2, double* rprdsh, double* rprdtot, double* pcnt,
+                            double* pcnb, void* stream);
+
 /* Synchronises `stream` (NULL = the CUDA default stream) and returns the number of
  * Brent non-convergence events of this thread's last zm_convr_batch_dev call (0 = clean). */
 int zm_sync_check(void* stream);

@@ -2044,4 +2044,68 @@ int zmo_conv_tend_batch(int nchunks, const int* ncol, const double* t, const dou
   return fails;
 }
 
+// ---- "next" rows N4: neighbours of the path with source in the reference ----
+// geopotential_t, FV ('LR') and EUL/SE hydrostatic branches of physics/geopotential.F90:153-247
+// (the generalized-virtual-temperature branch :248-310 belongs to SE/MPAS thermodynamics: not restated).
+void zmo_geopotential_t(int ncol, int dycore_lr, const double* piln_, const double* pmln_, const double* pint_,
+                        const double* pmid_, const double* pdel_, const double* rpdel_, const double* t_,
+                        const double* q_, const double* rair_, double gravit, const double* zvir_, double* zi_,
+                        double* zm_) {
+  (void)pmln_;
+  const int pcols = g.pcols, pver = g.pver, pverp = g.pverp;
+  C2 piln{piln_, pcols}, pint{pint_, pcols}, pmid{pmid_, pcols}, pdel{pdel_, pcols}, rpdel{rpdel_, pcols},
+      t{t_, pcols}, q{q_, pcols}, rair{rair_, pcols}, zvir{zvir_, pcols};
+  A2 zi{zi_, pcols}, zm{zm_, pcols};
+  std::vector<double> hkk(ncol + 1), hkl(ncol + 1);
+  W2 rog(pcols, pver);
+  for (int k = 1; k <= pver; ++k) for (int i = 1; i <= ncol; ++i) rog(i, k) = rair(i, k) / gravit;
+  for (int i = 1; i <= ncol; ++i) zi(i, pverp) = 0.0;
+  for (int k = pver; k >= 1; --k) {
+    if (dycore_lr) {
+      for (int i = 1; i <= ncol; ++i) {
+        hkl[i] = piln(i, k + 1) - piln(i, k);
+        hkk[i] = 1.0 - pint(i, k) * hkl[i] * rpdel(i, k);
+      }
+    } else {
+      for (int i = 1; i <= ncol; ++i) {
+        hkl[i] = pdel(i, k) / pmid(i, k);
+        hkk[i] = 0.5 * hkl[i];
+      }
+    }
+    for (int i = 1; i <= ncol; ++i) {
+      double tvfac = 1.0 + zvir(i, k) * q(i, k);
+      double tv = t(i, k) * tvfac;
+      zm(i, k) = zi(i, k + 1) + rog(i, k) * tv * hkk[i];
+      zi(i, k) = zi(i, k + 1) + rog(i, k) * tv * hkl[i];
+    }
+  }
+}
+
+// convect_diagnostics_calc (physics/convect_diagnostics.F90:115-249) for shallow_scheme == 'CLUBB_SGS'
+// (the only configuration in which the routine's locals cnt2/cnb2 and the intent(out) qc2/rliq2 are
+// defined, :187-198): merges the (zeroed) shallow fields into the deep-convection outputs.
+void zmo_convect_diagnostics(int ncol, double* cmfmc_, double* qc_, double* qc2_, double* rliq_, double* rliq2_,
+                             const double* pmid_, const double* rprddp_, double* cnt_, double* cnb_,
+                             double* cmfmc2_, double* rprdsh_, double* rprdtot_, double* pcnt_, double* pcnb_) {
+  const int pcols = g.pcols, pver = g.pver, pverp = g.pverp;
+  A2 cmfmc{cmfmc_, pcols}, qc{qc_, pcols}, qc2{qc2_, pcols}, cmfmc2{cmfmc2_, pcols}, rprdsh{rprdsh_, pcols},
+      rprdtot{rprdtot_, pcols};
+  C2 pmid{pmid_, pcols}, rprddp{rprddp_, pcols};
+  std::vector<double> cnt2(pcols), cnb2(pcols);
+  for (int k = 1; k <= pverp; ++k) for (int i = 1; i <= pcols; ++i) cmfmc2(i, k) = 0.0;
+  for (int k = 1; k <= pver; ++k) for (int i = 1; i <= pcols; ++i) { rprdsh(i, k) = 0.0; qc2(i, k) = 0.0; }
+  for (int i = 1; i <= pcols; ++i) { rliq2_[i - 1] = 0.0; cnt2[i - 1] = (double)pver; cnb2[i - 1] = 1.0; }
+  for (int k = 1; k <= pverp; ++k) for (int i = 1; i <= ncol; ++i) cmfmc(i, k) = cmfmc(i, k) + cmfmc2(i, k);
+  for (int i = 1; i <= ncol; ++i) {
+    if (cnt2[i - 1] < cnt_[i - 1]) cnt_[i - 1] = cnt2[i - 1];
+    if (cnb2[i - 1] > cnb_[i - 1]) cnb_[i - 1] = cnb2[i - 1];
+    if (cnb_[i - 1] == 1.0) cnb_[i - 1] = cnt_[i - 1];
+    pcnt_[i - 1] = pmid(i, (int)cnt_[i - 1]);
+    pcnb_[i - 1] = pmid(i, (int)cnb_[i - 1]);
+  }
+  for (int k = 1; k <= pver; ++k) for (int i = 1; i <= ncol; ++i) rprdtot(i, k) = rprdsh(i, k) + rprddp(i, k);
+  for (int k = 1; k <= pver; ++k) for (int i = 1; i <= ncol; ++i) qc(i, k) = qc(i, k) + qc2(i, k);
+  for (int i = 1; i <= ncol; ++i) rliq_[i - 1] = rliq_[i - 1] + rliq2_[i - 1];
+}
+
 }  // extern "C"

@@ -123,6 +123,17 @@ int zmo_conv_tend_batch(int nchunks, const int* ncol, const double* t, const dou
                         double* eu, double* ed, double* dp, double* dsubcld, int* jt, int* maxg, int* ideep,
                         int* lengath, double* cape, int nthreads);
 
+/* N4 neighbours: geopotential_t (geopotential.F90:153-247; dycore_lr selects the FV 'LR'
+ * branch, else EUL/SE) and convect_diagnostics_calc for shallow_scheme='CLUBB_SGS'
+ * (convect_diagnostics.F90:115-249).  Single chunk, Fortran layout. */
+void zmo_geopotential_t(int ncol, int dycore_lr, const double* piln, const double* pmln, const double* pint,
+                        const double* pmid, const double* pdel, const double* rpdel, const double* t,
+                        const double* q, const double* rair, double gravit, const double* zvir, double* zi,
+                        double* zm);
+void zmo_convect_diagnostics(int ncol, double* cmfmc, double* qc, double* qc2, double* rliq, double* rliq2,
+                             const double* pmid, const double* rprddp, double* cnt, double* cnb,
+                             double* cmfmc2, double* rprdsh, double* rprdtot, double* pcnt, double* pcnb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -221,3 +221,24 @@ class Oracle:
         args.append(C.c_int(nthreads))
         out["rc"] = self.lib.zmo_conv_tend_batch(*args)
         return out
+
+    def geopotential_t(self, ncol, dycore_lr, piln, pint, pmid, pdel, rpdel, t, q, rair, gravit, zvir):
+        P = self.params
+        L, pc = P.pver, P.pcols
+        zi, zm = np.zeros((L + 1, pc)), np.zeros((L, pc))
+        self.lib.zmo_geopotential_t(C.c_int(ncol), C.c_int(int(dycore_lr)), _dp(_f(piln)), None, _dp(_f(pint)),
+                                    _dp(_f(pmid)), _dp(_f(pdel)), _dp(_f(rpdel)), _dp(_f(t)), _dp(_f(q)),
+                                    _dp(_f(rair)), C.c_double(gravit), _dp(_f(zvir)), _dp(zi), _dp(zm))
+        return zi, zm
+
+    def convect_diagnostics(self, ncol, cmfmc, qc, rliq, pmid, rprddp, cnt, cnb):
+        P = self.params
+        L, pc = P.pver, P.pcols
+        o = dict(cmfmc=_f(cmfmc).copy(), qc=_f(qc).copy(), qc2=np.ones((L, pc)), rliq=_f(rliq).copy(),
+                 rliq2=np.ones(pc), cnt=_f(cnt).copy(), cnb=_f(cnb).copy(), cmfmc2=np.ones((L + 1, pc)),
+                 rprdsh=np.ones((L, pc)), rprdtot=np.zeros((L, pc)), pcnt=np.zeros(pc), pcnb=np.zeros(pc))
+        self.lib.zmo_convect_diagnostics(C.c_int(ncol), _dp(o["cmfmc"]), _dp(o["qc"]), _dp(o["qc2"]), _dp(o["rliq"]),
+                                         _dp(o["rliq2"]), _dp(_f(pmid)), _dp(_f(rprddp)), _dp(o["cnt"]),
+                                         _dp(o["cnb"]), _dp(o["cmfmc2"]), _dp(o["rprdsh"]), _dp(o["rprdtot"]),
+                                         _dp(o["pcnt"]), _dp(o["pcnb"]))
+        return o

@@ -260,3 +260,30 @@ def test_momtran_component_flags_and_reentrancy(built):
         sub = {k: v[10 * i: 10 * i + 10] for k, v in ref.items() if k != "rc"}
         assert_same(res[i], sub, ["qtnd", "heat", "prec", "ideep", "lengath", "mu", "jt", "maxg", "pflx"], 16,
                     exact=True, what=f"thread {i}")
+
+
+def test_next_rows_geopotential_and_convect_diagnostics(built):
+    """geopotential_t (both hydrostatic branches) and convect_diagnostics_calc, bit-exact."""
+    Z = init_cuda(16, 32)
+    o, _, _ = get_oracle("pm", 16, 32)
+    ch = S.make_chunks(1000, 32, 16, p_conv=0.5)
+    zvir = np.full_like(ch.t, S.ZVIR); rair = np.full_like(ch.t, S.RAIR)
+    piln, rpdel = np.log(ch.pint), 1.0 / ch.pdel
+    for lr in (True, False):
+        zi, zm = Z.geopotential_t(ch.ncol, piln, np.log(ch.pmid), ch.pint, ch.pmid, ch.pdel, rpdel, ch.t, ch.q, rair,
+                                  S.GRAVIT, zvir, dycore_lr=lr)
+        for c in range(ch.nchunks):
+            n = int(ch.ncol[c])
+            rzi, rzm = o.geopotential_t(n, lr, piln[c], ch.pint[c], ch.pmid[c], ch.pdel[c], rpdel[c], ch.t[c], ch.q[c],
+                                        rair[c], S.GRAVIT, zvir[c])
+            assert np.array_equal(zi[c][:, :n], rzi[:, :n]) and np.array_equal(zm[c][:, :n], rzm[:, :n]), (lr, c)
+    ref = o.conv_tend_batch(ch)
+    out = Z.convect_diagnostics_calc(ch.ncol, ref["mcon"], ref["dlf"], ref["rliq"], ch.pmid, ref["rprd"], ref["jctop"],
+                                     ref["jcbot"])
+    for c in range(ch.nchunks):
+        n = int(ch.ncol[c])
+        r = o.convect_diagnostics(n, ref["mcon"][c], ref["dlf"][c], ref["rliq"][c], ch.pmid[c], ref["rprd"][c],
+                                  ref["jctop"][c], ref["jcbot"][c])
+        for k in r:
+            assert np.array_equal(out[k][c][..., :n], r[k][..., :n]), (c, k)
+    assert np.all(out["cnb"][ch.ncol[:, None] > np.arange(16)[None, :]] >= 1)

@@ -142,3 +142,16 @@ def test_brent_failure_is_reported(built):
     o, _, _ = get_oracle("libm", 16, 32)
     rc, t, qs = o.ientropy(250.0, 900.0, 0.01, float("nan"))   # NaN first guess never converges
     assert rc == 1
+
+
+def test_geopotential_reproduces_the_input_heights(oracle_libm):
+    """soundings.py builds zm/zi with the FV branch of geopotential_t (geopotential.F90:218-247); the oracle's
+    restatement must give the same heights from the same t,q,p (operation order differs only in rog*tv)."""
+    o = oracle_libm
+    ch = S.make_chunks(32, 32, 16, p_conv=0.5)
+    zvir = np.full_like(ch.t, S.ZVIR); rair = np.full_like(ch.t, S.RAIR)
+    for c in range(ch.nchunks):
+        zi, zm = o.geopotential_t(16, True, np.log(ch.pint[c]), ch.pint[c], ch.pmid[c], ch.pdel[c], 1.0 / ch.pdel[c],
+                                  ch.t[c], ch.q[c], rair[c], S.GRAVIT, zvir[c])
+        assert np.allclose(zi, ch.zi[c], rtol=1e-12, atol=1e-9) and np.allclose(zm, ch.zm[c], rtol=1e-12, atol=1e-9)
+        assert np.all(zi[-1] == 0.0)
