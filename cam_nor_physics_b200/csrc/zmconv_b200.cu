@@ -66,8 +66,18 @@ struct Workspace {
     return p;
   }
 };
+// Device-resident copy of the pbuf fields zm_conv_tend hands to zm_conv_tend_2 (ZM_MU..ZM_IDEEP,
+// zm_conv_intr.F90:113-132, 994-1004): they live in the calling thread's staging arena until its next
+// zm_conv_tend_batch call, so convtran2 needs no second H2D of them.
+struct PbufMirror {
+  int nchunks = 0;
+  const double *mu = nullptr, *md = nullptr, *du = nullptr, *eu = nullptr, *ed = nullptr, *dp = nullptr, *dsubcld = nullptr;
+  const int *jt = nullptr, *maxg = nullptr, *ideep = nullptr, *lengath = nullptr;
+};
+thread_local PbufMirror tls_mirror;
 thread_local Workspace tls_work;     // kernel work arrays
 thread_local Workspace tls_stage;    // device staging of user arrays for the host-pointer API
+thread_local Workspace tls_stage2;   // staging for zm_conv_tend_2_batch (must not disturb tls_stage: the mirror lives there)
 
 inline size_t al(size_t n, size_t sz) { return (n * sz + 255) & ~(size_t)255; }
 
@@ -169,7 +179,7 @@ struct Stager {      // host-pointer API: bump-allocate device copies of user ar
   }
   template <class T> T* out(T* h, size_t n, bool is_early = false) {
     T* d = ws.take<T>(n);
-    (is_early ? early : outs).push_back({(void*)h, (void*)d, n * sizeof(T)});
+    if (h) (is_early ? early : outs).push_back({(void*)h, (void*)d, n * sizeof(T)});   // NULL: stays on device
     return d;
   }
   void flush_early(cudaStream_t on) {      // D2H of outputs that are final before the step ends
@@ -318,6 +328,20 @@ __global__ void k_conservation_final(int nblocks, const double* partial, double*
     double s = 0.0;
     for (int b = 0; b < nblocks; ++b) s += partial[b * 6 + threadIdx.x];
     out6[threadIdx.x] = s;
+  }
+}
+
+__global__ void k_dpdry_gather(int nchunks, const int* ideep, const int* lengath, const double* pdeldry,
+                               double* dpdry) {
+  const int pcols = P.pcols, pver = P.pver;
+  const size_t n2 = (size_t)nchunks * pcols * pver;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e % pcols);
+    const size_t r = e / pcols;
+    const int k = (int)(r % pver), c = (int)(r / pver);
+    double v = 0.0;
+    if (i < lengath[c]) v = pdeldry[cidx(c, k, ideep[(size_t)c * pcols + i] - 1, pver)] / 100.0;
+    dpdry[e] = v;
   }
 }
 
@@ -830,15 +854,19 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   const double *d_u = S.in(u, n2, cp), *d_v = S.in(v, n2, cp), *d_cld = S.in(cld, n2, cp);
   CK(cudaEventRecord(hooks.late_inputs, cp));
   const bool E = true;      // final after zm_convr
+  double *d_mu = S.out(mu, n2, E), *d_md = S.out(md, n2, E), *d_du = S.out(du, n2, E), *d_eu = S.out(eu, n2, E),
+         *d_ed = S.out(ed, n2, E), *d_dp = S.out(dp, n2, E), *d_dsub = S.out(dsubcld, nc, E);
+  int *d_jt = S.out(jt, nc, E), *d_maxg = S.out(maxg, nc, E), *d_ideep = S.out(ideep, nc, E),
+      *d_len = S.out(lengath, (size_t)nchunks, E);
+  tls_mirror = PbufMirror{nchunks, d_mu, d_md, d_du, d_eu, d_ed, d_dp, d_dsub, d_jt, d_maxg, d_ideep, d_len};
   int rc = conv_tend_impl(
       nchunks, d_ncol, d_t, d_q, d_u, d_v, d_pmid, d_pint, d_pdel, d_zm, d_zi, d_phis, d_pblh, d_tpert, d_lf,
       d_cld, ztodt, S.out(ptend_s, n2), S.out(ptend_q, n2), S.out(ptend_u, n2), S.out(ptend_v, n2),
       S.out(mcon, n2p), S.out(cme, n2, E), S.out(pflx, n2p, E), S.out(zdu, n2, E), S.out(rliq, nc, E),
       S.out(rice, nc, E), S.out(jctop, nc, E), S.out(jcbot, nc, E), S.out(prec, nc), S.out(snow, nc),
       S.out(ql, n2, E), S.out(rprd, n2, E), S.out(evapcdp, n2), S.out(flxprec, n2p), S.out(flxsnow, n2p),
-      S.out(dlf, n2, E), S.out(mu, n2, E), S.out(md, n2, E), S.out(du, n2, E), S.out(eu, n2, E), S.out(ed, n2, E),
-      S.out(dp, n2, E), S.out(dsubcld, nc, E), S.out(jt, nc, E), S.out(maxg, nc, E), S.out(ideep, nc, E),
-      S.out(lengath, (size_t)nchunks, E), S.out(cape, nc, E), (void*)st.stream, &hooks);
+      S.out(dlf, n2, E), d_mu, d_md, d_du, d_eu, d_ed, d_dp, d_dsub, d_jt, d_maxg, d_ideep, d_len,
+      S.out(cape, nc, E), (void*)st.stream, &hooks);
   if (rc) return rc;
   CK(cudaStreamWaitEvent(cp, hooks.convr_done, 0));
   S.flush_early(cp);
@@ -865,6 +893,33 @@ int zm_conservation_dev(int nchunks, const int* ncol, const double* pdel, const 
   tls_launches += 2;
   CK(cudaGetLastError());
   return 0;
+}
+
+// zm_conv_tend_2 (zm_conv_intr.F90:955-1028): convtran over the constituents flagged convtran2, with the
+// mass-flux fields of this thread's last zm_conv_tend_batch taken from the device mirror.
+int zm_conv_tend_2_batch(int nchunks, const int* doconvtran, const double* q, int pcnst, const double* pdeldry,
+                         const double* fracis, double* ptend_q, double ztodt, const int* cnst_is_dry) {
+  NEED_INIT();
+  if (nchunks <= 0) return 0;
+  const PbufMirror M = tls_mirror;
+  if (M.nchunks != nchunks || !M.mu) {
+    tls_err = "zm_conv_tend_2_batch: no device mirror from a zm_conv_tend_batch call with the same nchunks on this thread";
+    return -7;
+  }
+  const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc, n2 = nc * L, n3 = n2 * pcnst;
+  Workspace& st = tls_stage2;
+  if (st.ensure(2 * al(n2, 8) + 3 * al(n3, 8) + 4096)) return -100;
+  Stager S(st);
+  const double *d_q = S.in(q, n3), *d_fr = S.in(fracis, n3), *d_pdd = S.in(pdeldry, n2);
+  double* d_dpdry = st.take<double>(n2);
+  double* d_dqdt = S.inout(ptend_q, n3);
+  // dpdry(i,:) = pdeldry(ideep(i),:)/100 for i <= lengath, else 0 (zm_conv_intr.F90:1014-1017)
+  k_dpdry_gather<<<592, 256, 0, st.stream>>>(nchunks, M.ideep, M.lengath, d_pdd, d_dpdry); ++tls_launches;
+  int rc = zm_convtran_batch_dev(nchunks, doconvtran, d_q, pcnst, M.mu, M.md, M.du, M.eu, M.ed, M.dp, M.dsubcld,
+                                 M.jt, M.maxg, M.ideep, M.lengath, d_fr, d_dqdt, d_dpdry, ztodt, cnst_is_dry,
+                                 (void*)st.stream);
+  if (rc) return rc;
+  return S.flush();
 }
 
 // ---- N4 neighbours: geopotential_t, convect_diagnostics_calc ----------------------------------------

@@ -71,7 +71,7 @@ EXPORTS = [
     "zm_convr_batch_dev", "zm_conv_evap_batch", "zm_conv_evap_batch_dev", "zm_momtran_batch",
     "zm_momtran_batch_dev", "zm_convtran_batch", "zm_convtran_batch_dev", "zm_sync_check",
     "zm_conv_tend_batch", "zm_conv_tend_batch_dev", "zm_microbench", "zm_conservation_dev",
-    "zm_geopotential_t_batch", "zm_geopotential_t_batch_dev", "zm_convect_diagnostics_batch",
+    "zm_conv_tend_2_batch", "zm_geopotential_t_batch", "zm_geopotential_t_batch_dev", "zm_convect_diagnostics_batch",
     "zm_convect_diagnostics_batch_dev",
     "zm_math_eval_dev", "zm_math_eval_host", "zm_thermo_eval_dev", "zm_fp64_peak_flops",
     "zm_set_profiling", "zm_get_kernel_times", "zm_launch_count",
@@ -245,7 +245,19 @@ TEND_IN_ORDER = ["t", "q", "u", "v", "pmid", "pint", "pdel", "zm", "zi", "phis",
                  "landfrac", "cld"]
 
 
-def zm_conv_tend(ncol, state: dict, ztodt: float, out: dict | None = None):
+def zm_conv_tend_2(doconvtran, q, pdeldry, fracis, ztodt, cnst_is_dry, ptend_q=None):
+    """zm_conv_tend_2 (zm_conv_intr.F90:955): convtran2 with the mass-flux fields taken from the device
+    mirror left by this thread's last zm_conv_tend call."""
+    q = _f(q)
+    nch, pcnst = q.shape[0], q.shape[1]
+    dq = np.zeros_like(q) if ptend_q is None else _f(ptend_q).copy()
+    rc = lib().zm_conv_tend_2_batch(C.c_int(nch), _ip(_i(doconvtran)), _dp(q), C.c_int(pcnst), _dp(_f(pdeldry)),
+                                    _dp(_f(fracis)), _dp(dq), C.c_double(ztodt), _ip(_i(cnst_is_dry)))
+    _check(rc, "zm_conv_tend_2")
+    return dq
+
+
+def zm_conv_tend(ncol, state: dict, ztodt: float, out: dict | None = None, keep_pbuf_on_device: bool = False):
     """zm_conv_tend (zm_conv_intr.F90:390) over host arrays: zm_convr -> physics_update ->
     zm_conv_evap -> momtran with everything resident on the device in between.
     `state` holds t,q,u,v,pmid,pint,pdel,zm,zi,phis,pblh,tpert,landfrac,cld in chunk layout."""
@@ -265,9 +277,13 @@ def zm_conv_tend(ncol, state: dict, ztodt: float, out: dict | None = None):
         out["lengath"] = np.zeros(nch, np.int32)
     ins = [_f(state[k]) for k in TEND_IN_ORDER]
     args = [C.c_int(nch), _ip(ncol)] + [_dp(a) for a in ins] + [C.c_double(ztodt)]
+    mirror_only = {"mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg"} if keep_pbuf_on_device else set()
     for k in TEND_ARG_ORDER:
         a = out[k]
-        args.append(_ip(a) if a.dtype == np.int32 else _dp(a))
+        if k in mirror_only:
+            args.append(None)       # stays in the device mirror for zm_conv_tend_2 (no D2H)
+        else:
+            args.append(_ip(a) if a.dtype == np.int32 else _dp(a))
     rc = lib().zm_conv_tend_batch(*args)
     _check(rc, "zm_conv_tend")
     return out

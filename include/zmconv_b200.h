@@ -184,6 +184,15 @@ int zm_convect_diagnostics_batch_dev(int nchunks, const int* ncol, double* cmfmc
                             double* cnb, double* cmfmc2, double* rprdsh, double* rprdtot, double* pcnt,
                             double* pcnb, void* stream);
 
+/* In zm_conv_tend_batch (host-pointer variant) the pbuf outputs mu, md, du, eu, ed, dp, dsubcld, jt, maxg,
+ * ideep, lengath may be NULL: they are then not copied back but stay in a device-resident mirror owned by
+ * the calling thread until its next zm_conv_tend_batch call (the reference keeps them in pbuf between
+ * tphysbc and tphysac, zm_conv_intr.F90:113-132).  zm_conv_tend_2_batch replaces zm_conv_tend_2
+ * (zm_conv_intr.F90:955-1028): dpdry gather (:1014-1017) + convtran (:1020-1024) using that mirror.
+ * q, fracis, ptend_q are (pcols,pver,pcnst); pdeldry is (pcols,pver). */
+int zm_conv_tend_2_batch(int nchunks, const int* doconvtran, const double* q, int pcnst, const double* pdeldry,
+                         const double* fracis, double* ptend_q, double ztodt, const int* cnst_is_dry);
+
 /* Synchronises `stream` (NULL = the CUDA default stream) and returns the number of
  * Brent non-convergence events of this thread's last zm_convr_batch_dev call (0 = clean). */
 int zm_sync_check(void* stream);

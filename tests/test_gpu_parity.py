@@ -287,3 +287,36 @@ def test_next_rows_geopotential_and_convect_diagnostics(built):
         for k in r:
             assert np.array_equal(out[k][c][..., :n], r[k][..., :n]), (c, k)
     assert np.all(out["cnb"][ch.ncol[:, None] > np.arange(16)[None, :]] >= 1)
+
+
+def test_conv_tend_2_uses_device_mirror(built):
+    """zm_conv_tend with the pbuf fields kept on the device, then zm_conv_tend_2 (convtran2,
+    zm_conv_intr.F90:955-1028) from that mirror: bit-exact vs oracle convtran on the oracle's fields."""
+    Z = init_cuda(16, 32)
+    o, _, _ = get_oracle("pm", 16, 32)
+    ch = S.make_chunks(800, 32, 16, p_conv=0.6)
+    ref = o.conv_tend_batch(ch)
+    out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt, keep_pbuf_on_device=True)
+    assert np.all(out["mu"] == 0.0) and np.all(out["jt"] == 0)       # not copied back
+    assert_same(out, ref, ["lengath", "ideep", "ptend_s", "ptend_q", "prec", "mcon"], 16, exact=True, what="tend")
+    pcnst = 8
+    q, fracis, pdeldry = S.make_tracers(ch, pcnst)
+    do = [0, 0, 1, 1, 0, 1, 1, 1]
+    dry = [0, 0, 1, 0, 0, 1, 0, 1]
+    dq = Z.zm_conv_tend_2(do, q, pdeldry, fracis, ch.ztodt, dry)
+    dpdry = dpdry_gathered(ch, ref, pdeldry)
+    for c in range(ch.nchunks):
+        r = o.convtran(do, q[c], ref["mu"][c], ref["md"][c], ref["du"][c], ref["eu"][c], ref["ed"][c], ref["dp"][c],
+                       ref["dsubcld"][c], ref["jt"][c], ref["maxg"][c], ref["ideep"][c], ref["lengath"][c], fracis[c],
+                       dpdry[c], ch.ztodt, dry)
+        for m in range(pcnst):
+            if do[m]:
+                assert np.array_equal(dq[c, m], r[m]), (c, m)
+            else:
+                assert np.all(dq[c, m] == 0.0)
+    assert np.count_nonzero(dq) > 0
+    # a second tend call with another nchunks invalidates the mirror for the old size
+    ch2 = S.make_chunks(160, 32, 16, p_conv=0.6)
+    Z.zm_conv_tend(ch2.ncol, state_of(ch2), ch2.ztodt)
+    with pytest.raises(Z.ZmError):
+        Z.zm_conv_tend_2(do, q, pdeldry, fracis, ch.ztodt, dry)
