@@ -87,6 +87,7 @@ template <int PASS>
 __global__ void __launch_bounds__(128, 3)
 k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   extern __shared__ double sm_buoy[];               // [pver+2][blockDim.x]
+  zmm::hot_tables_load();                            // before any early return (block-wide barrier inside)
   const int pcols = P.pcols, pver = P.pver, msg = P.msg;
   const int ncolpad = in.nchunks * pcols;
   const int nthr = blockDim.x;

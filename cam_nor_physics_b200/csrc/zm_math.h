@@ -37,18 +37,37 @@ __device__ const double d_exp2_tab[256] = ZMM_EXP2_TAB_VALUES;
 static const double h_log_tab[384] = ZMM_LOG_TAB_VALUES;
 static const double h_exp2_tab[256] = ZMM_EXP2_TAB_VALUES;
 
-ZM_HD double log_tab(int i) {
+#if defined(__CUDACC__)
+// Shared-memory copies used by the *_hot variants (one LDS.128 per entry instead of __ldg loads that each
+// need a descriptor in uniform registers).  A kernel that calls a *_hot function must call
+// hot_tables_load() with all threads of the block before its first use.
+__shared__ double2 s_log_a[128];      // (invc, logc_hi)
+__shared__ double  s_log_b[128];      // logc_lo
+__shared__ double2 s_exp2[128];       // (2^(j/128) hi, lo)
+__device__ __forceinline__ void hot_tables_load() {
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+    s_log_a[i] = make_double2(d_log_tab[3 * i], d_log_tab[3 * i + 1]);
+    s_log_b[i] = d_log_tab[3 * i + 2];
+    s_exp2[i] = make_double2(d_exp2_tab[2 * i], d_exp2_tab[2 * i + 1]);
+  }
+  __syncthreads();
+}
+#endif
+
+template <bool HOT> ZM_HD void log_entry(int i, double& invc, double& lch, double& lcl) {
 #if defined(__CUDA_ARCH__)
-  return __ldg(&d_log_tab[i]);
+  if (HOT) { const double2 a = s_log_a[i]; invc = a.x; lch = a.y; lcl = s_log_b[i]; return; }
+  invc = __ldg(&d_log_tab[3 * i]); lch = __ldg(&d_log_tab[3 * i + 1]); lcl = __ldg(&d_log_tab[3 * i + 2]);
 #else
-  return h_log_tab[i];
+  invc = h_log_tab[3 * i]; lch = h_log_tab[3 * i + 1]; lcl = h_log_tab[3 * i + 2];
 #endif
 }
-ZM_HD double exp2_tab(int i) {
+template <bool HOT> ZM_HD void exp2_entry(int j, double& th, double& tl) {
 #if defined(__CUDA_ARCH__)
-  return __ldg(&d_exp2_tab[i]);
+  if (HOT) { const double2 a = s_exp2[j]; th = a.x; tl = a.y; return; }
+  th = __ldg(&d_exp2_tab[2 * j]); tl = __ldg(&d_exp2_tab[2 * j + 1]);
 #else
-  return h_exp2_tab[i];
+  th = h_exp2_tab[2 * j]; tl = h_exp2_tab[2 * j + 1];
 #endif
 }
 
@@ -84,18 +103,23 @@ ZM_HD double u2d(uint64_t u) {
 // ---- log core: log(x) = hi + lo (unevaluated, ~2^-68 relative), x positive & finite -------------
 // x = 2^k * z, z in [0.6855, 1.371); z*invc - 1 = r with |r| < 0.004 (one fma, exact rounding);
 // log(x) = k*ln2 + logc + log1p(r), logc = -log(invc) tabulated as hi (multiple of 2^-32) + lo.
-ZM_HD void log_core(double x, double& hi, double& lo) {
+// HOT = true: x must be a positive NORMAL finite number (no subnormal scaling); same bits as HOT = false there.
+template <bool HOT> ZM_HD void log_core_t(double x, double& hi, double& lo) {
   uint64_t ix = d2u(x);
-  // subnormals: scale by 2^54 (select, no branch)
-  const bool sub = ix < 0x0010000000000000ULL;
-  const uint64_t ixs = d2u(x * 18014398509481984.0);
-  ix = sub ? ixs : ix;
+  bool sub = false;
+  if (!HOT) {
+    // subnormals: scale by 2^54 (select, no branch)
+    sub = ix < 0x0010000000000000ULL;
+    const uint64_t ixs = d2u(x * 18014398509481984.0);
+    ix = sub ? ixs : ix;
+  }
   const uint64_t tmp = ix - 0x3fe5f00000000000ULL;
   const int i = (int)((tmp >> 45) & 127);
   int k = (int)((int64_t)tmp >> 52);
-  k = sub ? k - 54 : k;
+  if (!HOT) k = sub ? k - 54 : k;
   const double z = u2d(ix - (tmp & 0xfff0000000000000ULL));
-  const double invc = log_tab(3 * i), lch = log_tab(3 * i + 1), lcl = log_tab(3 * i + 2);
+  double invc, lch, lcl;
+  log_entry<HOT>(i, invc, lch, lcl);
   const double r = fma(z, invc, -1.0);
   const double kd = (double)k;
   const double w = fma(kd, ZMM_LN2_HI32, lch);            // exact: both are multiples of 2^-32
@@ -124,6 +148,7 @@ ZM_HD void log_core(double x, double& hi, double& lo) {
   hi = s2 + l;
   lo = l - (hi - s2);
 }
+ZM_HD void log_core(double x, double& hi, double& lo) { log_core_t<false>(x, hi, lo); }
 
 // resolves x <= 0, inf, nan for the log family with selects
 ZM_HD double log_fixup(double x, double res) {
@@ -147,18 +172,35 @@ ZM_HD double log10_(double x) {
   return log_fixup(x, res);
 }
 
+// Hot variants: identical bits to log_/log10_ for positive normal finite x, no special-case selects.
+ZM_HD double log_hot(double x) {
+  double hi, lo; log_core_t<true>(x, hi, lo);
+  return hi;
+}
+ZM_HD double log10_hot(double x) {
+  double hi, lo; log_core_t<true>(x, hi, lo);
+  const double p  = hi * ZMM_INVLN10_HI;
+  const double pe = fma(hi, ZMM_INVLN10_HI, -p);
+  return p + (pe + fma(hi, ZMM_INVLN10_LO, lo * ZMM_INVLN10_HI));
+}
+
 // 2^(yh+yl), yh+yl an unevaluated sum with |yl| << |yh|; < 0.6 ulp.  Branch-free:
 // k = rint(128*yh); j = k mod 128; 2^y = 2^(k div 128) * T[j] * exp((yh - k/128 + yl) * ln2)
-ZM_HD double exp2_dd(double yh, double yl) {
-  double yc = (yh < 1100.0) ? yh : 1100.0;           // clamp (nan stays nan: fixed up by callers)
-  yc = (yc > -1100.0) ? yc : -1100.0;
+// HOT = true: |yh| < 1000 required (no clamp); same bits as HOT = false there.
+template <bool HOT> ZM_HD double exp2_dd_t(double yh, double yl) {
+  double yc = yh;
+  if (!HOT) {
+    yc = (yh < 1100.0) ? yh : 1100.0;                // clamp (nan stays nan: fixed up by callers)
+    yc = (yc > -1100.0) ? yc : -1100.0;
+  }
   const double kd = rint(yc * 128.0);
   const int k = (int)kd;
   const double f = fma(kd, -0.0078125, yc);          // exact
   const double r = (f + yl) * ZMM_LN2_HI;
   const int j = k & 127;
   const int e = (k - j) >> 7;
-  const double th = exp2_tab(2 * j), tl = exp2_tab(2 * j + 1);
+  double th, tl;
+  exp2_entry<HOT>(j, th, tl);
   // expm1(r) = r + r^2*(1/2 + r/6 + r^2/24 + r^3/120)
   const double r2 = r * r;
   const double c01 = fma(r, 0.16666666666666666, 0.5);
@@ -169,6 +211,7 @@ ZM_HD double exp2_dd(double yh, double yl) {
   const int e1 = e >> 1, e2 = e - e1;
   return (v * u2d((uint64_t)(e1 + 1023) << 52)) * u2d((uint64_t)(e2 + 1023) << 52);
 }
+ZM_HD double exp2_dd(double yh, double yl) { return exp2_dd_t<false>(yh, yl); }
 
 // exp, < 0.6 ulp
 ZM_HD double exp_(double x) {
@@ -184,6 +227,21 @@ ZM_HD double pow10_(double x) {
   const double yl = fma(x, ZMM_LOG2_10_HI, -yh) + x * ZMM_LOG2_10_LO;
   const double res = exp2_dd(yh, yl);
   return (x == x) ? res : x;
+}
+
+// 10**x for |x| < 300 (no clamp, no nan select): identical bits to pow10_ there
+ZM_HD double pow10_hot(double x) {
+  const double yh = x * ZMM_LOG2_10_HI;
+  const double yl = fma(x, ZMM_LOG2_10_HI, -yh) + x * ZMM_LOG2_10_LO;
+  return exp2_dd_t<true>(yh, yl);
+}
+
+// a / b given rb = RN(1/b) (correctly rounded reciprocal of a fixed divisor): first quotient estimate plus
+// one exact-residual correction (Markstein); equals the IEEE-754 quotient for normal-range operands.
+ZM_HD double div_rcp(double a, double b, double rb) {
+  const double q = a * rb;
+  const double rem = fma(-b, q, a);
+  return fma(rb, rem, q);
 }
 
 // x**y for x > 0 (general real power, Fortran `x**y` with real y), < 0.7 ulp.

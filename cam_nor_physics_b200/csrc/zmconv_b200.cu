@@ -347,6 +347,7 @@ __global__ void k_dpdry_gather(int nchunks, const int* ideep, const int* lengath
 
 // ---- diagnostics kernels ----------------------------------------------------------------------
 __global__ void k_math_eval(int id, int n, const double* x, const double* y, double* o) {
+  zmm::hot_tables_load();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   switch (id) {
@@ -354,11 +355,17 @@ __global__ void k_math_eval(int id, int n, const double* x, const double* y, dou
     case 1: o[i] = zmm::log10_(x[i]); break;
     case 2: o[i] = zmm::exp_(x[i]); break;
     case 3: o[i] = zmm::pow10_(x[i]); break;
+    case 5: o[i] = zmm::log_hot(x[i]); break;
+    case 6: o[i] = zmm::log10_hot(x[i]); break;
+    case 7: o[i] = zmm::pow10_hot(x[i]); break;
+    case 8: o[i] = zmm::div_rcp(x[i], y[i], 1.0 / y[i]); break;
+    case 9: o[i] = div_hot(x[i], y[i]); break;
     default: o[i] = zmm::pow_(x[i], y[i]); break;
   }
 }
 __global__ void k_thermo_eval(int id, int n, const double* a, const double* b, const double* c,
                               const double* d, const double* e, double* o0, double* o1) {
+  zmm::hot_tables_load();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double r0 = 0.0, r1 = 0.0;
@@ -374,6 +381,7 @@ __global__ void k_thermo_eval(int id, int n, const double* a, const double* b, c
 }
 // single-warp latency microbenchmark (cycles per dependent call), see zm_microbench
 __global__ void k_microbench(double* out, long long* cyc, int n) {
+  zmm::hot_tables_load();
   double x = 290.0 + threadIdx.x * 0.01, acc = 0.0, q;
   long long t0, t1;
   int j = 0;
@@ -450,6 +458,7 @@ int zm_init(const zm_params_t* p) {
   d.dcol = (p->cpliq - p->cpwv) / p->latvap;
   d.capelmt = p->capelmt; d.tiedke_add = p->tiedke_add; d.tiedke_lnd = 1.0; d.entrmn = 2e-4;
   d.alfadet = 0.1; d.plclmin = 6.e2; d.cin_threshd = 0.33; d.parcel_hscale = 0.5;
+  d.rtfreez = 1.0 / p->tmelt;
   d.tentrm = p->masterproc ? -p->dmpdz : 1e-3;          // zm_conv.F90:90,213
   d.cpair = p->cpair; d.epsilo = p->epsilo; d.gravit = p->gravit; d.latice = p->latice;
   d.latvap = p->latvap; d.tmelt = p->tmelt; d.rair = p->rair; d.cpwv = p->cpwv; d.cpliq = p->cpliq;
@@ -1000,6 +1009,11 @@ int zm_math_eval_host(int id, int n, const double* x, const double* y, double* o
       case 1: o[i] = zmm::log10_(x[i]); break;
       case 2: o[i] = zmm::exp_(x[i]); break;
       case 3: o[i] = zmm::pow10_(x[i]); break;
+      case 5: o[i] = zmm::log_hot(x[i]); break;
+      case 6: o[i] = zmm::log10_hot(x[i]); break;
+      case 7: o[i] = zmm::pow10_hot(x[i]); break;
+      case 8: o[i] = zmm::div_rcp(x[i], y[i], 1.0 / y[i]); break;
+      case 9: o[i] = x[i] / y[i]; break;
       default: o[i] = zmm::pow_(x[i], y[i]); break;
     }
   }

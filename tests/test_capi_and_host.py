@@ -64,6 +64,25 @@ def test_portable_math_accuracy_host(built):
         assert worst < 1.0, (fid, worst)
 
 
+def test_hot_math_variants_equal_general_ones_host(built):
+    """The state function uses trimmed transcendentals (no special-case selects) and constant-reciprocal
+    divisions; inside their stated domains they must return the same bits as the general ones."""
+    from cam_nor_physics_b200 import zm_conv as Z
+    rng = np.random.default_rng(5)
+    n = 400_000
+    xs = np.concatenate([np.exp(rng.uniform(-700, 700, n)), rng.uniform(0.5, 2.0, n), [1.0, 2.0, 0.5, 1e-300, 1e300]])
+    assert np.array_equal(Z.math_eval(5, xs, device=False), Z.math_eval(0, xs, device=False))      # log
+    assert np.array_equal(Z.math_eval(6, xs, device=False), Z.math_eval(1, xs, device=False))      # log10
+    assert Z.math_eval(0, np.array([1.0]), device=False)[0] == 0.0 and not np.signbit(Z.math_eval(0, np.array([1.0]), device=False)[0])
+    xp = np.concatenate([rng.uniform(-300, 300, n), rng.uniform(-3, 8, n), [0.0, -0.0]])
+    assert np.array_equal(Z.math_eval(7, xp, device=False), Z.math_eval(3, xp, device=False))      # 10**x
+    # a/b through RN(1/b) + one residual correction == IEEE division (divisors used by the state function)
+    for b in (373.16, 1000.0, 273.15, 273.16):
+        a = np.concatenate([rng.uniform(50, 1000, n), np.exp(rng.uniform(-50, 50, n))])
+        bb = np.full_like(a, b)
+        assert np.array_equal(Z.math_eval(8, a, bb, device=False), a / bb), b
+
+
 def test_soundings_are_shard_independent():
     a = S.make_chunks(64, 32, 16, p_conv=0.5)
     b = S.make_chunks(32, 32, 16, p_conv=0.5, col0=32)

@@ -24,14 +24,27 @@ def test_portable_math_device_equals_host(built):
                       (2, rng.uniform(-60, 60, n), None), (3, rng.uniform(-9, 9, n), None),
                       (4, rng.uniform(0.3, 50, n), rng.uniform(-3, 3, n))]:
         assert np.array_equal(Z.math_eval(fid, x, y, device=True), Z.math_eval(fid, x, y, device=False)), fid
+    # trimmed variants used by the state function (shared-memory tables, no special-case selects, divisions by
+    # refined reciprocals) against the GENERAL host functions / IEEE division
+    xs = np.concatenate([np.exp(rng.uniform(-700, 700, n)), rng.uniform(0.5, 2.0, n)])
+    assert np.array_equal(Z.math_eval(5, xs, device=True), Z.math_eval(0, xs, device=False))
+    assert np.array_equal(Z.math_eval(6, xs, device=True), Z.math_eval(1, xs, device=False))
+    xp = np.concatenate([rng.uniform(-300, 300, n), rng.uniform(-3, 8, n)])
+    assert np.array_equal(Z.math_eval(7, xp, device=True), Z.math_eval(3, xp, device=False))
+    a = np.concatenate([rng.uniform(50, 1000, n), np.exp(rng.uniform(-50, 50, n))])
+    for b in (373.16, 1000.0, 273.15):
+        assert np.array_equal(Z.math_eval(8, a, np.full_like(a, b), device=True), a / b), b
+    b = np.exp(rng.uniform(-50, 50, a.size))
+    assert np.array_equal(Z.math_eval(9, a, b, device=True), a / b)          # div_hot == IEEE quotient
 
 
 def test_thermo_scalars_match_oracle(built):
     Z = init_cuda(16, 32)
     o, _, _ = get_oracle("pm", 16, 32)
     rng = np.random.default_rng(5)
-    n = 400
-    T = rng.uniform(190, 315, n); p = rng.uniform(100, 1020, n); q = rng.uniform(1e-6, 0.025, n)
+    n = 3000
+    T = rng.uniform(170, 330, n); p = rng.uniform(60, 1050, n); q = rng.uniform(1e-7, 0.03, n)
+    q[::7] = np.exp(rng.uniform(np.log(1e-12), np.log(1e-6), q[::7].size))        # very dry parcels
     z = rng.uniform(0, 1.6e4, n); tfg = T + rng.uniform(-6, 6, n)
     s0, _ = Z.thermo_eval(0, T, p, q)
     h0, _ = Z.thermo_eval(1, T, p, q, z)
