@@ -84,9 +84,10 @@ __global__ void k_convr_init(ConvrIn in, ConvrOut o, ConvrWork w) {
 // ---- buoyan_dilute + parcel_dilute, one thread per column ----------------------------------
 // zm_conv.F90:4425-4819 and 4824-5277.  PASS 1: every column.  PASS 2: worklist wl1 only.
 template <int PASS>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, PASS == 1 ? 3 : 2)      // pass 2 has few warps: let it keep everything in registers
 k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   extern __shared__ double sm_buoy[];               // [pver+2][blockDim.x]
+  constexpr bool PAIR = (PASS == 2);                 // paired bracket evaluation only where latency-bound
   zmm::hot_tables_load();                            // before any early return (block-wide barrier inside)
   const int pcols = P.pcols, pver = P.pver, msg = P.msg;
   const int ncolpad = in.nchunks * pcols;
@@ -215,7 +216,7 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
     double smix_k = (sp0 + sp) / (mp0 + mp);
     double qtmix_k = (qtp0 + qtp) / (mp0 + mp);
     double tmix_k, qsmix_k;
-    if (!invert<1>(smix_k, p_k, z_k, qtmix_k, tmix1_p, tmix_k, qsmix_k)) {
+    if (!invert<1, PAIR>(smix_k, p_k, z_k, qtmix_k, tmix1_p, tmix_k, qsmix_k)) {
       ok = false; report_fail(w, 2, col, p_k, tmix1_p, qtmix_k, smix_k);
     }
     if (qsmix_k <= qtmix_k && qsmix1_p > qtmix_p) {
@@ -230,7 +231,7 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
       double slcl = smix_p + dsdp * (pl - p_p);
       double qtlcl = qtmix_p + dqtdp * (pl - p_p);
       double qslcl;
-      if (!invert<1>(slcl, pl, zl, qtlcl, tmix_k, tl, qslcl)) {
+      if (!invert<1, PAIR>(slcl, pl, zl, qtlcl, tmix_k, tl, qslcl)) {
         ok = false; report_fail(w, 3, col, pl, tmix_k, qtlcl, slcl);
       }
     }
@@ -249,7 +250,7 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
       new_s = smix2 + ds_xsh2o_k + ds_freeze_k;
       new_q = qtmix_k - xsh2o_k;
       double tfg = tmix2;
-      if (!invert<0>(new_s, p_k, 0.0, new_q, tfg, tmix2, qsmix2)) {
+      if (!invert<0, PAIR>(new_s, p_k, 0.0, new_q, tfg, tmix2, qsmix2)) {
         ok = false; report_fail(w, 4, col, p_k, tfg, new_q, new_s);
       }
     }

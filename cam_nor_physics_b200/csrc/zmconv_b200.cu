@@ -399,8 +399,8 @@ __global__ void k_microbench(double* out, long long* cyc, int n) {
   MB(x = 300.0 + 1e-6 * gg_svp_water(x));                                // 5 goff-gratch
   MB(x = 300.0 + 1e-9 * state_fn(1, x, 900.0, 0.015, 500.0, q));         // 6 enthalpy
   MB(x = 300.0 + 1e-6 * state_fn(0, x, 900.0, 0.015, 0.0, q));           // 7 entropy
-  MB(invert_k(1, 3.5e5 + x, 900.0, 500.0, 0.015, 295.0, acc, q); x = 290.0 + 1e-3 * acc);  // 8 ienthalpy
-  MB(invert_k(0, 250.0 + 1e-3 * x, 900.0, 0.0, 0.015, 295.0, acc, q); x = 290.0 + 1e-3 * acc);  // 9 ientropy
+  MB(invert_k<true>(1, 3.5e5 + x, 900.0, 500.0, 0.015, 295.0, acc, q); x = 290.0 + 1e-3 * acc);  // 8 ienthalpy
+  MB(invert_k<true>(0, 250.0 + 1e-3 * x, 900.0, 0.0, 0.015, 295.0, acc, q); x = 290.0 + 1e-3 * acc);  // 9 ientropy
   MB(x = 300.0 + 1e-3 * zmm::pow_(x, 0.2857));                           // 10 pow
   { double f1, f2, q1, q2;
     MB(state_fn_dual(x, 900.0, 0.015, 500.0, x + 1.0, 900.0, 0.015, f1, q1, f2, q2); x = 300.0 + 1e-9 * f1 + 1e-6 * f2); }  // 11 dual

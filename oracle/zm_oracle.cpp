@@ -57,6 +57,8 @@ Module g;
 
 thread_local long long cnt[10];
 thread_local int brent_fail;
+// optional trace of Brent inversions (rcall, icol, lchnk, state-function evaluations) for divergence studies
+thread_local int* trace_buf = nullptr; thread_local int trace_n = 0, trace_cap = 0;
 
 inline double fmax2(double a, double b) { return (a > b) ? a : b; }
 inline double fmin2(double a, double b) { return (a < b) ? a : b; }
@@ -142,8 +144,8 @@ double enthalpy(double TK, double p, double qtot, double z) {
 template <int KIND>
 void invert(int rcall, int icol, int lchnk, double s, double p, double z, double qt,
             double& T, double& qst, double Tfg) {
-  (void)rcall; (void)icol; (void)lchnk;
   ++cnt[3 + KIND];
+  const long long ev0 = cnt[1] + cnt[2];
   auto F = [&](double x) { return KIND == 0 ? entropy(x, p, qt) : enthalpy(x, p, qt, z); };
   double est;
   double a, b, c, d = 0.0, ebr = 0.0, fa, fb, fc, pbr, qbr, rbr, sbr, tol1, xm, tol;
@@ -210,6 +212,10 @@ void invert(int rcall, int icol, int lchnk, double s, double p, double z, double
     fb = F(b) - s;
   }
   T = b;
+  if (trace_buf && trace_n + 4 <= trace_cap) {
+    trace_buf[trace_n] = rcall; trace_buf[trace_n + 1] = icol; trace_buf[trace_n + 2] = lchnk;
+    trace_buf[trace_n + 3] = (int)(cnt[1] + cnt[2] - ev0); trace_n += 4;
+  }
   qsat_hPa(T, p, est, qst);
   if (!converged) ++brent_fail;   // reference: endrun (zm_conv.F90:5401-5410, 5557-5566)
 }
@@ -1928,6 +1934,8 @@ int zmo_ienthalpy(double s, double p, double z, double qt, double tfg, double* t
 void zmo_qsat_hpa(double t, double p, double* es, double* qm) { qsat_hPa(t, p, *es, *qm); }
 void zmo_qsat_table(double t, double p, double* es, double* qs) { g.estbl.qsat(t, p, g.epsilo, *es, *qs); }
 
+void zmo_trace_set(int* buf, int cap) { trace_buf = buf; trace_cap = cap; trace_n = 0; }
+int zmo_trace_count(void) { return trace_n / 4; }
 void zmo_counters_reset(void) { for (int i = 0; i < 10; ++i) cnt[i] = 0; }
 void zmo_counters_get(long long* out10) { for (int i = 0; i < 10; ++i) out10[i] = cnt[i]; }
 

@@ -93,6 +93,9 @@ void zmo_qsat_table(double t, double p, double* es, double* qs);
 
 /* operation counters for the roofline flop figure (per-thread; reset then read) */
 void zmo_counters_reset(void);
+/* optional per-inversion trace: 4 ints per call (rcall, icol, lchnk, state-function evaluations); single thread */
+void zmo_trace_set(int* buf, int cap);
+int zmo_trace_count(void);
 /* out[0]=qsat_hPa calls, [1]=entropy, [2]=enthalpy, [3]=ientropy, [4]=ienthalpy,
  * [5]=log, [6]=log10, [7]=pow10, [8]=exp, [9]=pow  */
 void zmo_counters_get(long long* out10);
