@@ -46,6 +46,7 @@ struct Workspace {
   std::vector<cudaEvent_t> tev;
   int* last_count = nullptr;          // device: [0]=n pass-1, [1]=n final, [2]=brent failures
   double* last_err = nullptr;
+  int chunk0 = 0;                     // first chunk of this arena's (sub-)batch, for error messages
   cudaStream_t side = nullptr;        // zm_conv_evap runs here, concurrently with momtran
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int ensure(size_t bytes) {
@@ -78,6 +79,54 @@ thread_local PbufMirror tls_mirror;
 thread_local Workspace tls_work;     // kernel work arrays
 thread_local Workspace tls_stage;    // device staging of user arrays for the host-pointer API
 thread_local Workspace tls_stage2;   // staging for zm_conv_tend_2_batch (must not disturb tls_stage: the mirror lives there)
+
+// Streams, events and per-sub-batch work arenas of the pipelined host-pointer zm_conv_tend_batch.
+struct TendPipe {
+  static const int MAXB = 8;
+  Workspace work[MAXB];
+  cudaStream_t h2d = nullptr, d2h_early = nullptr, d2h_final = nullptr;
+  cudaEvent_t in_ready[MAXB] = {}, late_ready[MAXB] = {}, convr_done[MAXB] = {}, done[MAXB] = {};
+  cudaEvent_t early_back[MAXB] = {}, final_back[MAXB] = {}, t0 = nullptr;   // timeline of the last call (zm_tend_trace)
+  int ninit = 0, last_nb = 0;
+  // ZM_TEND_SUBBATCHES (1..8, default 8); a sub-batch is never smaller than 128 chunks
+  int subbatches(int nchunks) const {
+    int nb = 8;
+    if (const char* e = getenv("ZM_TEND_SUBBATCHES")) nb = atoi(e);
+    nb = nb < 1 ? 1 : (nb > MAXB ? MAXB : nb);
+    while (nb > 1 && nchunks / nb < 128) --nb;
+    return nb;
+  }
+  static int first(int b, int nchunks, int nb) { return (int)((long long)nchunks * b / nb); }
+  int init(int nb) {
+    if (!h2d) {
+      CK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&d2h_early, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&d2h_final, cudaStreamNonBlocking));
+      CK(cudaEventCreate(&t0));
+    }
+    for (; ninit < nb; ++ninit) {
+      CK(cudaEventCreate(&in_ready[ninit]));
+      CK(cudaEventCreate(&late_ready[ninit]));
+      CK(cudaEventCreate(&convr_done[ninit]));
+      CK(cudaEventCreate(&done[ninit]));
+      CK(cudaEventCreate(&early_back[ninit]));
+      CK(cudaEventCreate(&final_back[ninit]));
+      // earlier sub-batches get higher stream priority: the first results reach the return stream sooner
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // hi = greatest priority (numerically lowest)
+      int pr = hi + ninit; if (pr > lo) pr = lo;
+      if (!work[ninit].stream) CK(cudaStreamCreateWithPriority(&work[ninit].stream, cudaStreamNonBlocking, pr));
+      if (!work[ninit].side) {
+        CK(cudaStreamCreateWithPriority(&work[ninit].side, cudaStreamNonBlocking, pr));
+        CK(cudaEventCreateWithFlags(&work[ninit].ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&work[ninit].ev_join, cudaEventDisableTiming));
+      }
+    }
+    last_nb = nb;
+    return 0;
+  }
+};
+thread_local TendPipe tls_pipe;
 
 inline size_t al(size_t n, size_t sz) { return (n * sz + 255) & ~(size_t)255; }
 
@@ -160,7 +209,7 @@ int read_failures(Workspace& ws, cudaStream_t s) {
     snprintf(b, sizeof b,
              "*** ZM_CONV: %s failed to converge (%d events); first: call#=%d lchnk=%d icol=%d "
              "P(mb)=%.2f Tfg(K)=%.2f qt(g/kg)=%.2f s(J/kg)=%.2f",
-             (int)info[0] == 4 ? "IENTROPY" : "IENTHALPY", cnt[2], (int)info[0], col / pc + 1,
+             (int)info[0] == 4 ? "IENTROPY" : "IENTHALPY", cnt[2], (int)info[0], ws.chunk0 + col / pc + 1,
              col % pc + 1, info[2], info[3], 1000.0 * info[4], info[5]);
     tls_err = b;
   }
@@ -736,7 +785,7 @@ int zm_convtran_batch(int nchunks, const int* doconvtran, const double* q, int n
 namespace {
 // events the host-pointer API uses to overlap PCIe copies with the kernels
 struct TendHooks { cudaEvent_t late_inputs; cudaEvent_t convr_done; };
-int conv_tend_impl(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
+int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t, const double* q, const double* u,
                            const double* v, const double* pmid, const double* pint, const double* pdel,
                            const double* zm, const double* zi, const double* phis, const double* pblh,
                            const double* tpert, const double* landfrac, const double* cld, double ztodt,
@@ -751,7 +800,6 @@ int conv_tend_impl(int nchunks, const int* ncol, const double* t, const double* 
   if (nchunks <= 0) return 0;
   const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc;
   const size_t n2 = nc * L, n2p = nc * (L + 1);
-  Workspace& ws = tls_work;
   if (ws.ensure(convr_work_bytes(nc, (int)L) + 18 * al(n2, 8) + 6 * al(2 * n2, 8) + 2 * al(nchunks, 4) + al(nc, 4) + 8192))
     return -100;
   cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
@@ -823,7 +871,7 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
                            double* evapcdp, double* flxprec, double* flxsnow, double* dlf, double* mu,
                            double* md, double* du, double* eu, double* ed, double* dp, double* dsubcld,
                            int* jt, int* maxg, int* ideep, int* lengath, double* cape, void* stream) {
-  return conv_tend_impl(nchunks, ncol, t, q, u, v, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac, cld,
+  return conv_tend_impl(tls_work, nchunks, ncol, t, q, u, v, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac, cld,
                         ztodt, ptend_s, ptend_q, ptend_u, ptend_v, mcon, cme, pflx, zdu, rliq, rice, jctop, jcbot,
                         prec, snow, ql, rprd, evapcdp, flxprec, flxsnow, dlf, mu, md, du, eu, ed, dp, dsubcld, jt,
                         maxg, ideep, lengath, cape, stream, nullptr);
@@ -846,42 +894,138 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   Workspace& st = tls_stage;
   if (st.ensure(al(nchunks, 4) + 24 * al(n2, 8) + 6 * al(n2p, 8) + 14 * al(nc, 8) + 4 * al(nc, 4) + 8192))
     return -100;
-  Stager S(st);
-  // PCIe overlap: inputs that only the later stages read (u, v, cld) travel on a copy stream while pass 1
-  // runs; zm_convr's final outputs start their D2H on that stream while evap/momtran still run.
-  if (!st.side) {
-    CK(cudaStreamCreateWithFlags(&st.side, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&st.ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&st.ev_join, cudaEventDisableTiming));
-  }
-  cudaStream_t cp = st.side;
-  TendHooks hooks{st.ev_fork /* late inputs */, st.ev_join /* convr done */};
-  const int* d_ncol = S.in(ncol, nchunks);
-  const double *d_t = S.in(t, n2), *d_q = S.in(q, n2), *d_pmid = S.in(pmid, n2), *d_pint = S.in(pint, n2p),
-               *d_pdel = S.in(pdel, n2), *d_zm = S.in(zm, n2), *d_zi = S.in(zi, n2p), *d_phis = S.in(phis, nc),
-               *d_pblh = S.in(pblh, nc), *d_tpert = S.in(tpert, nc), *d_lf = S.in(landfrac, nc);
-  const double *d_u = S.in(u, n2, cp), *d_v = S.in(v, n2, cp), *d_cld = S.in(cld, n2, cp);
-  CK(cudaEventRecord(hooks.late_inputs, cp));
-  const bool E = true;      // final after zm_convr
-  double *d_mu = S.out(mu, n2, E), *d_md = S.out(md, n2, E), *d_du = S.out(du, n2, E), *d_eu = S.out(eu, n2, E),
-         *d_ed = S.out(ed, n2, E), *d_dp = S.out(dp, n2, E), *d_dsub = S.out(dsubcld, nc, E);
-  int *d_jt = S.out(jt, nc, E), *d_maxg = S.out(maxg, nc, E), *d_ideep = S.out(ideep, nc, E),
-      *d_len = S.out(lengath, (size_t)nchunks, E);
+  // The batch is cut into NB sub-batches of whole chunks (columns are independent).  Sub-batch b's inputs
+  // travel host->device while sub-batch b-1 computes, and its outputs travel back while sub-batch b+1
+  // computes: PCIe (both directions) and the SMs are busy at the same time.  Every array keeps ONE
+  // device allocation for the whole batch (sub-batches are chunk slices of it), so the pbuf mirror that
+  // zm_conv_tend_2_batch reads stays contiguous.
+  TendPipe& tp = tls_pipe;
+  int NB = tp.subbatches(nchunks);
+  if (tp.init(NB)) return -100;
+  const size_t s2 = pc * L, s2p = pc * (L + 1), s1 = pc;            // per-chunk strides
+  // kind 0 in, 1 late in, 2 early out, 3 final out; per-column/per-chunk arrays are small and travel once for the
+  // whole batch (4: in, before the first sub-batch; 5: out, after the last) instead of once per sub-batch
+  struct Arr { const void* h; void* d; size_t stride, esz; int kind; };
+  std::vector<Arr> arrs; arrs.reserve(64);
+  auto dev = [&](const void* h, size_t stride, size_t esz, int kind, bool always = true) -> void* {
+    void* d = (void*)st.take<char>((size_t)nchunks * stride * esz);
+    if (stride <= pc) kind = (kind <= 1) ? 4 : 5;
+    if (h || always) arrs.push_back({h, d, stride, esz, h ? kind : -1});
+    return d;
+  };
+#define DIN(x, str)   (const double*)dev(x, str, 8, 0)
+#define DLATE(x, str) (const double*)dev(x, str, 8, 1)
+#define DOUTE(x, str) (double*)dev(x, str, 8, 2)
+#define DOUTF(x, str) (double*)dev(x, str, 8, 3)
+  const int* d_ncol = (const int*)dev(ncol, 1, 4, 0);
+  const double *d_t = DIN(t, s2), *d_q = DIN(q, s2), *d_pmid = DIN(pmid, s2), *d_pint = DIN(pint, s2p),
+               *d_pdel = DIN(pdel, s2), *d_zm = DIN(zm, s2), *d_zi = DIN(zi, s2p), *d_phis = DIN(phis, s1),
+               *d_pblh = DIN(pblh, s1), *d_tpert = DIN(tpert, s1), *d_lf = DIN(landfrac, s1);
+  const double *d_u = DLATE(u, s2), *d_v = DLATE(v, s2), *d_cld = DLATE(cld, s2);
+  double *d_mu = DOUTE(mu, s2), *d_md = DOUTE(md, s2), *d_du = DOUTE(du, s2), *d_eu = DOUTE(eu, s2),
+         *d_ed = DOUTE(ed, s2), *d_dp = DOUTE(dp, s2), *d_dsub = DOUTE(dsubcld, s1);
+  int *d_jt = (int*)dev(jt, s1, 4, 2), *d_maxg = (int*)dev(maxg, s1, 4, 2), *d_ideep = (int*)dev(ideep, s1, 4, 2),
+      *d_len = (int*)dev(lengath, 1, 4, 2);
   tls_mirror = PbufMirror{nchunks, d_mu, d_md, d_du, d_eu, d_ed, d_dp, d_dsub, d_jt, d_maxg, d_ideep, d_len};
-  int rc = conv_tend_impl(
-      nchunks, d_ncol, d_t, d_q, d_u, d_v, d_pmid, d_pint, d_pdel, d_zm, d_zi, d_phis, d_pblh, d_tpert, d_lf,
-      d_cld, ztodt, S.out(ptend_s, n2), S.out(ptend_q, n2), S.out(ptend_u, n2), S.out(ptend_v, n2),
-      S.out(mcon, n2p), S.out(cme, n2, E), S.out(pflx, n2p, E), S.out(zdu, n2, E), S.out(rliq, nc, E),
-      S.out(rice, nc, E), S.out(jctop, nc, E), S.out(jcbot, nc, E), S.out(prec, nc), S.out(snow, nc),
-      S.out(ql, n2, E), S.out(rprd, n2, E), S.out(evapcdp, n2), S.out(flxprec, n2p), S.out(flxsnow, n2p),
-      S.out(dlf, n2, E), d_mu, d_md, d_du, d_eu, d_ed, d_dp, d_dsub, d_jt, d_maxg, d_ideep, d_len,
-      S.out(cape, nc, E), (void*)st.stream, &hooks);
-  if (rc) return rc;
-  CK(cudaStreamWaitEvent(cp, hooks.convr_done, 0));
-  S.flush_early(cp);
-  if (S.flush()) return -100;
-  CK(cudaStreamSynchronize(cp));
-  return read_failures(tls_work, st.stream);
+  double *d_ps = DOUTF(ptend_s, s2), *d_pq = DOUTF(ptend_q, s2), *d_pu = DOUTF(ptend_u, s2), *d_pv = DOUTF(ptend_v, s2),
+         *d_mcon = DOUTF(mcon, s2p), *d_cme = DOUTE(cme, s2), *d_pflx = DOUTE(pflx, s2p), *d_zdu = DOUTE(zdu, s2),
+         *d_rliq = DOUTE(rliq, s1), *d_rice = DOUTE(rice, s1), *d_jctop = DOUTE(jctop, s1), *d_jcbot = DOUTE(jcbot, s1),
+         *d_prec = DOUTF(prec, s1), *d_snow = DOUTF(snow, s1), *d_ql = DOUTE(ql, s2), *d_rprd = DOUTE(rprd, s2),
+         *d_evap = DOUTF(evapcdp, s2), *d_fp = DOUTF(flxprec, s2p), *d_fs = DOUTF(flxsnow, s2p), *d_dlf = DOUTE(dlf, s2),
+         *d_cape = DOUTE(cape, s1);
+#undef DIN
+#undef DLATE
+#undef DOUTE
+#undef DOUTF
+  int rc = 0;
+  auto copy_kind = [&](int kind, int c0, int nb, cudaStream_t on) {
+    for (auto& a : arrs) {
+      if (a.kind != kind) continue;
+      const size_t off = (size_t)c0 * a.stride * a.esz, bytes = (size_t)nb * a.stride * a.esz;
+      cudaError_t e = (kind <= 1 || kind == 4) ? cudaMemcpyAsync((char*)a.d + off, (const char*)a.h + off, bytes, cudaMemcpyHostToDevice, on)
+                                  : cudaMemcpyAsync((char*)a.h + off, (char*)a.d + off, bytes, cudaMemcpyDeviceToHost, on);
+      if (e != cudaSuccess) rc = -100;
+    }
+  };
+  // Enqueue order on the host thread: inputs of sub-batch b+1 go out right after the kernels of sub-batch b
+  // were launched, so neither the copy engine nor the SMs wait for the host to finish enqueueing.
+  auto send_inputs = [&](int b) -> int {
+    const int c0 = tp.first(b, nchunks, NB), nb = tp.first(b + 1, nchunks, NB) - c0;
+    copy_kind(0, c0, nb, tp.h2d);
+    CK(cudaEventRecord(tp.in_ready[b], tp.h2d));
+    copy_kind(1, c0, nb, tp.h2d);
+    CK(cudaEventRecord(tp.late_ready[b], tp.h2d));
+    return 0;
+  };
+  CK(cudaEventRecord(tp.t0, tp.h2d));
+  copy_kind(4, 0, nchunks, tp.h2d);
+  if (send_inputs(0)) return -100;
+  for (int b = 0; b < NB && rc == 0; ++b) {
+    const int c0 = tp.first(b, nchunks, NB), nb = tp.first(b + 1, nchunks, NB) - c0;
+    Workspace& ws = tp.work[b];
+    ws.chunk0 = c0;
+    if (!ws.stream && ws.ensure(0)) return -100;
+    CK(cudaStreamWaitEvent(ws.stream, tp.in_ready[b], 0));
+    TendHooks hooks{tp.late_ready[b], tp.convr_done[b]};
+#define O2(x)  ((x) + (size_t)c0 * s2)
+#define O2P(x) ((x) + (size_t)c0 * s2p)
+#define O1(x)  ((x) + (size_t)c0 * s1)
+    rc = conv_tend_impl(ws, nb, d_ncol + c0, O2(d_t), O2(d_q), O2(d_u), O2(d_v), O2(d_pmid), O2P(d_pint), O2(d_pdel),
+                        O2(d_zm), O2P(d_zi), O1(d_phis), O1(d_pblh), O1(d_tpert), O1(d_lf), O2(d_cld), ztodt,
+                        O2(d_ps), O2(d_pq), O2(d_pu), O2(d_pv), O2P(d_mcon), O2(d_cme), O2P(d_pflx), O2(d_zdu),
+                        O1(d_rliq), O1(d_rice), O1(d_jctop), O1(d_jcbot), O1(d_prec), O1(d_snow), O2(d_ql),
+                        O2(d_rprd), O2(d_evap), O2P(d_fp), O2P(d_fs), O2(d_dlf), O2(d_mu), O2(d_md), O2(d_du),
+                        O2(d_eu), O2(d_ed), O2(d_dp), O1(d_dsub), O1(d_jt), O1(d_maxg), O1(d_ideep), d_len + c0,
+                        O1(d_cape), (void*)ws.stream, &hooks);
+#undef O2
+#undef O2P
+#undef O1
+    if (rc) break;
+    CK(cudaEventRecord(tp.done[b], ws.stream));
+    if (b + 1 < NB && send_inputs(b + 1)) return -100;
+    // device->host: zm_convr's outputs as soon as they are final, the rest when the sub-batch ends
+    // one return stream, in the order results become final: by the time sub-batch b's zm_convr outputs are
+    // across, its evap/momtran kernels have finished too
+    CK(cudaStreamWaitEvent(tp.d2h_early, tp.convr_done[b], 0));
+    copy_kind(2, c0, nb, tp.d2h_early);
+    CK(cudaEventRecord(tp.early_back[b], tp.d2h_early));
+    CK(cudaStreamWaitEvent(tp.d2h_early, tp.done[b], 0));
+    copy_kind(3, c0, nb, tp.d2h_early);
+    CK(cudaEventRecord(tp.final_back[b], tp.d2h_early));
+  }
+  if (rc == 0) copy_kind(5, 0, nchunks, tp.d2h_early);
+  cudaError_t e1 = cudaStreamSynchronize(tp.d2h_early), e2 = cudaStreamSynchronize(tp.d2h_final),
+              e3 = cudaStreamSynchronize(tp.h2d);
+  for (int b = 0; b < NB; ++b)
+    if (tp.work[b].stream && cudaStreamSynchronize(tp.work[b].stream) != cudaSuccess) rc = -100;
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) rc = -100;
+  if (rc) {
+    if (rc == -100 && tls_err.empty()) tls_err = std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError());
+    return rc;
+  }
+  int fails = 0;
+  for (int b = NB - 1; b >= 0; --b) {        // first failing sub-batch's message wins
+    const int f = read_failures(tp.work[b], tp.work[b].stream);
+    if (f < 0) return f;
+    fails += f;
+  }
+  return fails;
+}
+
+// Timeline of this thread's last zm_conv_tend_batch call: for each sub-batch 6 times in ms since the first
+// host->device copy was enqueued: inputs on device, late inputs on device, zm_convr done, sub-batch done,
+// zm_convr outputs on host, remaining outputs on host.  Returns the number of sub-batches.
+int zm_tend_trace(double* ms, int cap) {
+  TendPipe& tp = tls_pipe;
+  for (int b = 0; b < tp.last_nb && 6 * (b + 1) <= cap; ++b) {
+    cudaEvent_t ev[6] = {tp.in_ready[b], tp.late_ready[b], tp.convr_done[b], tp.done[b], tp.early_back[b], tp.final_back[b]};
+    for (int j = 0; j < 6; ++j) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, tp.t0, ev[j]) != cudaSuccess) { cudaGetLastError(); t = -1.f; }
+      ms[6 * b + j] = t;
+    }
+  }
+  return tp.last_nb;
 }
 
 // Per-rank budget terms for the global conservation check (device pointers; out6 on device):

@@ -71,7 +71,7 @@ EXPORTS = [
     "zm_convr_batch_dev", "zm_conv_evap_batch", "zm_conv_evap_batch_dev", "zm_momtran_batch",
     "zm_momtran_batch_dev", "zm_convtran_batch", "zm_convtran_batch_dev", "zm_sync_check",
     "zm_conv_tend_batch", "zm_conv_tend_batch_dev", "zm_microbench", "zm_conservation_dev",
-    "zm_conv_tend_2_batch", "zm_geopotential_t_batch", "zm_geopotential_t_batch_dev", "zm_convect_diagnostics_batch",
+    "zm_conv_tend_2_batch", "zm_tend_trace", "zm_geopotential_t_batch", "zm_geopotential_t_batch_dev", "zm_convect_diagnostics_batch",
     "zm_convect_diagnostics_batch_dev",
     "zm_math_eval_dev", "zm_math_eval_host", "zm_thermo_eval_dev", "zm_fp64_peak_flops",
     "zm_set_profiling", "zm_get_kernel_times", "zm_launch_count",
@@ -342,6 +342,14 @@ def thermo_eval(fid: int, a, b, c=None, d=None, e=None):
                                   _dp(o0), _dp(o1))
     _check(rc, "thermo_eval")
     return o0, o1
+
+
+def tend_trace():
+    """Timeline (ms) of the last zm_conv_tend call on this thread: rows = sub-batches, columns = inputs on device,
+    late inputs on device, zm_convr done, kernels done, zm_convr outputs on host, all outputs on host."""
+    buf = (C.c_double * 48)()
+    nb = lib().zm_tend_trace(buf, C.c_int(48))
+    return np.array(buf[:6 * nb]).reshape(nb, 6)
 
 
 def fp64_peak_flops(iters: int = 20000) -> float:

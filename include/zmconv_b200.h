@@ -193,6 +193,11 @@ int zm_convect_diagnostics_batch_dev(int nchunks, const int* ncol, double* cmfmc
 int zm_conv_tend_2_batch(int nchunks, const int* doconvtran, const double* q, int pcnst, const double* pdeldry,
                          const double* fracis, double* ptend_q, double ztodt, const int* cnst_is_dry);
 
+/* Pipeline timeline of the calling thread's last zm_conv_tend_batch (diagnostics): per sub-batch six times in
+ * ms (inputs on device, late inputs on device, zm_convr done, all kernels done, zm_convr outputs on host,
+ * remaining outputs on host).  Returns the number of sub-batches; fills at most cap doubles. */
+int zm_tend_trace(double* ms, int cap);
+
 /* Synchronises `stream` (NULL = the CUDA default stream) and returns the number of
  * Brent non-convergence events of this thread's last zm_convr_batch_dev call (0 = clean). */
 int zm_sync_check(void* stream);
