@@ -87,7 +87,7 @@ struct TendPipe {
   cudaStream_t h2d = nullptr, d2h_early = nullptr, d2h_final = nullptr;
   cudaEvent_t in_ready[MAXB] = {}, late_ready[MAXB] = {}, convr_done[MAXB] = {}, done[MAXB] = {};
   cudaEvent_t early_back[MAXB] = {}, final_back[MAXB] = {}, t0 = nullptr;   // timeline of the last call (zm_tend_trace)
-  int ninit = 0, last_nb = 0;
+  int ninit = 0, last_nb = 0, dev_nb = 0;
   // ZM_TEND_SUBBATCHES (1..8, default 8); a sub-batch is never smaller than 128 chunks
   int subbatches(int nchunks) const {
     int nb = 8;
@@ -574,9 +574,19 @@ int zm_get_kernel_times(int* n, const char** names, float* ms) {
 
 // sync the thread's stream and return the Brent failure count of the last zm_convr_batch_dev
 int zm_sync_check(void* stream) {
-  Workspace& ws = tls_work;
   cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
-  return read_failures(ws, s);
+  TendPipe& tp = tls_pipe;
+  if (tp.dev_nb > 1) {                        // last device call ran as sub-batches on the library's own streams
+    CK(cudaStreamSynchronize(s));
+    int fails = 0;
+    for (int b = tp.dev_nb - 1; b >= 0; --b) {
+      const int f = read_failures(tp.work[b], tp.work[b].stream);
+      if (f < 0) return f;
+      fails += f;
+    }
+    return fails;
+  }
+  return read_failures(tls_work, s);
 }
 
 int zm_convr_batch_dev(int nchunks, const int* ncol, const double* t, const double* qh, double* prec,
@@ -593,6 +603,7 @@ int zm_convr_batch_dev(int nchunks, const int* ncol, const double* t, const doub
   if (nchunks <= 0) return 0;
   Workspace& ws = tls_work;
   if (ws.ensure(0)) return -100;
+  tls_pipe.dev_nb = 0;
   cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
   ConvrIn in{nchunks, ncol, t, qh, pap, paph, dpp, zm, zi, geos, pblh, tpert, landfrac, delt};
   ConvrOut o{prec, jctop, jcbot, qtnd, heat, mcon, cme, cape, eurt, dlf, pflx, zdu, rprd,
@@ -871,10 +882,49 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
                            double* evapcdp, double* flxprec, double* flxsnow, double* dlf, double* mu,
                            double* md, double* du, double* eu, double* ed, double* dp, double* dsubcld,
                            int* jt, int* maxg, int* ideep, int* lengath, double* cape, void* stream) {
-  return conv_tend_impl(tls_work, nchunks, ncol, t, q, u, v, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac, cld,
-                        ztodt, ptend_s, ptend_q, ptend_u, ptend_v, mcon, cme, pflx, zdu, rliq, rice, jctop, jcbot,
-                        prec, snow, ql, rprd, evapcdp, flxprec, flxsnow, dlf, mu, md, du, eu, ed, dp, dsubcld, jt,
-                        maxg, ideep, lengath, cape, stream, nullptr);
+  NEED_INIT();
+  if (nchunks <= 0) return 0;
+  // Optionally cut the batch into sub-batches of whole chunks that run on their own (prioritised) streams:
+  // every kernel of the path is latency-bound at low occupancy, so the passes of different sub-batches
+  // fill each other's idle issue slots.  ZM_DEV_SUBBATCHES = 1 keeps everything on `stream`.
+  TendPipe& tp = tls_pipe;
+  int NB = 1;
+  if (const char* e = getenv("ZM_DEV_SUBBATCHES")) NB = atoi(e);
+  NB = NB < 1 ? 1 : (NB > TendPipe::MAXB ? TendPipe::MAXB : NB);
+  while (NB > 1 && nchunks / NB < 128) --NB;
+  tp.dev_nb = 0;
+  if (NB == 1 || g_profile)
+    return conv_tend_impl(tls_work, nchunks, ncol, t, q, u, v, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac,
+                          cld, ztodt, ptend_s, ptend_q, ptend_u, ptend_v, mcon, cme, pflx, zdu, rliq, rice, jctop,
+                          jcbot, prec, snow, ql, rprd, evapcdp, flxprec, flxsnow, dlf, mu, md, du, eu, ed, dp, dsubcld,
+                          jt, maxg, ideep, lengath, cape, stream, nullptr);
+  if (tp.init(NB)) return -100;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t pc = g_params.pcols, L = g_params.pver, s2 = pc * L, s2p = pc * (L + 1), s1 = pc;
+  CK(cudaEventRecord(tp.in_ready[0], s));
+  for (int b = 0; b < NB; ++b) {
+    const int c0 = tp.first(b, nchunks, NB), nb = tp.first(b + 1, nchunks, NB) - c0;
+    Workspace& ws = tp.work[b];
+    ws.chunk0 = c0;
+    CK(cudaStreamWaitEvent(ws.stream, tp.in_ready[0], 0));
+#define O2(x)  ((x) + (size_t)c0 * s2)
+#define O2P(x) ((x) + (size_t)c0 * s2p)
+#define O1(x)  ((x) + (size_t)c0 * s1)
+    int rc = conv_tend_impl(ws, nb, ncol + c0, O2(t), O2(q), O2(u), O2(v), O2(pmid), O2P(pint), O2(pdel), O2(zm),
+                            O2P(zi), O1(phis), O1(pblh), O1(tpert), O1(landfrac), O2(cld), ztodt, O2(ptend_s),
+                            O2(ptend_q), O2(ptend_u), O2(ptend_v), O2P(mcon), O2(cme), O2P(pflx), O2(zdu), O1(rliq),
+                            O1(rice), O1(jctop), O1(jcbot), O1(prec), O1(snow), O2(ql), O2(rprd), O2(evapcdp),
+                            O2P(flxprec), O2P(flxsnow), O2(dlf), O2(mu), O2(md), O2(du), O2(eu), O2(ed), O2(dp),
+                            O1(dsubcld), O1(jt), O1(maxg), O1(ideep), lengath + c0, O1(cape), (void*)ws.stream, nullptr);
+#undef O2
+#undef O2P
+#undef O1
+    if (rc) return rc;
+    CK(cudaEventRecord(tp.done[b], ws.stream));
+    CK(cudaStreamWaitEvent(s, tp.done[b], 0));
+  }
+  tp.dev_nb = NB;
+  return 0;
 }
 
 int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
