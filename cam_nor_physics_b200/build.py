@@ -38,7 +38,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
+    extra = os.environ.get("ZM_NVCC_EXTRA", "").split()       # experiments only, e.g. -DPL_WARPS=8
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
     env = dict(os.environ)
     env.pop("CXX", None)
     env.pop("CC", None)     # the image exports a gcc wrapper that nvcc should not pick up

@@ -24,7 +24,9 @@ enum PlumeArr {
   A_COUNT
 };
 
+#ifndef PL_WARPS
 #define PL_WARPS 4      // warps (columns) per block
+#endif
 
 struct PlumeSh {
   double* base; int ld;

@@ -126,164 +126,176 @@ __global__ void k_momtran_init(MomArgs a) {
   for (size_t e = tid; e < n2; e += nth) a.seten[e] = 0.0;
 }
 
-// Thread per gathered (convective) column, registers only: sweep 1 runs bottom-up (pressure-gradient
-// term + in-cloud updraft wind, zm_conv.F90:2497-2575) and parks conu in the icwu output; sweep 2 runs
-// top-down (downdraft wind 2579-2589) and finishes level k-1 (tendency 2596-2627, momentum flux and
-// end-of-step wind 2646-2666, KE-dissipation heating 2675-2712) as soon as level k is known.  Both
-// wind components advance together.  No per-level arrays: every input is read twice from L2/HBM,
-// nothing is staged in local memory (an array-based version spent its time in local-memory misses).
-__global__ void __launch_bounds__(64)
+// Warp per gathered (convective) column, lane = level.  Everything that is independent from level to level
+// (pressure-gradient terms 2497-2530, the mass-flux weighted differences, tendencies 2596-2627, momentum
+// flux and end-of-step wind 2646-2666, KE-dissipation heating 2675-2712) runs with one level per lane out of
+// shared memory; only the two first-order recurrences -- in-cloud updraft wind bottom-up (zm_conv.F90:2536-2575)
+// and downdraft wind top-down (2579-2589) -- are sequential, and those run for both wind components and both
+// directions in ONE loop (four independent dependency chains) with their level-local terms precomputed.
+// Expression order is the reference's everywhere, so results are bit-identical to the serial code.
+// (Earlier versions ran one thread per column: 0.26 ms of dependent divisions for 19k columns.)
+#define MOM_WARPS 4
+enum MomArr { M_MU = 0, M_MD, M_DU, M_EU, M_ED, M_DP, M_C, M_CHAT = M_C + 2, M_PGU = M_CHAT + 2, M_PGD = M_PGU + 2,
+              M_CONU = M_PGD + 2, M_COND = M_CONU + 2, M_MF = M_COND + 2, M_WF = M_MF + 2, M_T23 = M_WF + 2,
+              M_U2 = M_T23 + 2, M_U3 = M_U2 + 2, M_MUP = M_U3 + 2, M_RMUP, M_RMD, M_NARR };
+__host__ __device__ inline size_t momtran_smem_bytes(int pver) {
+  return (size_t)MOM_WARPS * M_NARR * (pver + 2) * sizeof(double);
+}
+__global__ void __launch_bounds__(32 * MOM_WARPS)
 k_momtran_t(MomArgs a) {
+  extern __shared__ double sm_mom[];
   const int pcols = P.pcols, pver = P.pver;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= *a.count) return;
-  const int slot = a.slots[tid];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wid = blockIdx.x * MOM_WARPS + wib;
+  if (wid >= *a.count) return;
+  const int slot = a.slots[wid];
   const int c = slot / pcols, gi = slot - c * pcols;
   const int ii = a.ideep[slot] - 1;
   const int mx = a.mx[slot];
   const int ktm = a.ktm[c], kbm = a.kbm[c];
   const double mbsth = 1.e-15, dt = a.dt;
-  const bool act[2] = {a.domom[0] != 0, a.domom[1] != 0};
-#define GA(arr, k) a.arr[cidx(c, (k) - 1, gi, pver)]
+  const int ld = pver + 2;                                    // levels 1..pver+1 addressed directly
+  double* S = sm_mom + (size_t)wib * M_NARR * ld;
+#define SA(arr, k) S[(arr) * ld + (k)]
 #define QI(m, k) ((((size_t)c * 2 + (m)) * pver + (k) - 1) * pcols + ii)
-
-  // ---------------- sweep 1: k = pver .. 1 ----------------
-  {
-    double c_k[2], c_km1[2], c_kp1[2], conu_kp1[2];
-    double mu_k = GA(mu, pver), mu_kp1 = 0.0;
-    double dp_k = GA(dp, pver), dp_km1 = GA(dp, max(1, pver - 1));
+#define PAR for (int k = lane + 1; k <= pver; k += 32)
+  // ---- stage the column ----
+  PAR {
+    const size_t g = cidx(c, k - 1, gi, pver);
+    SA(M_MU, k) = a.mu[g]; SA(M_MD, k) = a.md[g]; SA(M_DU, k) = a.du[g];
+    SA(M_EU, k) = a.eu[g]; SA(M_ED, k) = a.ed[g]; SA(M_DP, k) = a.dp[g];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) SA(M_C + m, k) = a.domom[m] ? a.q[QI(m, k)] : 0.0;
+  }
+  if (lane == 0) { SA(M_MF, pver + 1) = 0.0; SA(M_MF + 1, pver + 1) = 0.0; }
+  __syncwarp();
+  // ---- level-local terms ----
+  PAR {
+    const int km1 = max(1, k - 1), kp1 = min(pver, k + 1);
+    const double mu_k = SA(M_MU, k), md_k = SA(M_MD, k), dp_k = SA(M_DP, k), dp_km1 = SA(M_DP, km1);
+    const double mu_kp1 = SA(M_MU, kp1), md_kp1 = SA(M_MD, kp1);
+    const double mup_k = mu_k + SA(M_DU, k) * dp_k;
+    SA(M_MUP, k) = mup_k;
+    // refined reciprocals of the two divisors of the recurrences: q = x*r; q += r*(x - b*q) in the sequential
+    // loop is then the IEEE quotient x/b (the compiler's own fast-path division with the reciprocal hoisted
+    // out of the dependent chain); only used where |b| > mbsth
+    SA(M_RMUP, k) = rcp_hot(mup_k);
+    SA(M_RMD, k) = rcp_hot(md_k);
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-      c_k[m] = act[m] ? a.q[QI(m, pver)] : 0.0;
-      c_km1[m] = act[m] ? a.q[QI(m, max(1, pver - 1))] : 0.0;
-      c_kp1[m] = c_k[m]; conu_kp1[m] = 0.0;
-    }
-    for (int k = pver; k >= 1; --k) {
-      const double du_k = GA(du, k), eu_k = GA(eu, k);
-      const double mupdudp = mu_k + du_k * dp_k;
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        if (!act[m]) continue;
-        double pgu;
-        if (k == 1) {
-          pgu = 0.0;
-        } else if (k == pver) {
-          const double mududp = mu_k * (c_k[m] - c_km1[m]) / dp_km1;
-          pgu = -P.momcu * mududp;
-        } else {
-          const double mududp = (mu_k * (c_k[m] - c_km1[m]) / dp_km1 + mu_kp1 * (c_kp1[m] - c_k[m]) / dp_k);
-          pgu = -P.momcu * 0.5 * mududp;
-        }
-        const double chat = 0.5 * (c_k[m] + c_km1[m]);
-        double conu = chat;
-        if (mupdudp > mbsth) {
-          if (k == pver) conu = (+eu_k * c_k[m] * dp_k + pgu * dp_k) / mupdudp;
-          else           conu = (mu_kp1 * conu_kp1[m] + eu_k * c_k[m] * dp_k + pgu * dp_k) / mupdudp;
-        }
-        a.icwu[QI(m, k)] = conu;
-        a.pguall[QI(m, k)] = -pgu;
-        conu_kp1[m] = conu;
-        c_kp1[m] = c_k[m]; c_k[m] = c_km1[m];
-        if (k - 2 >= 1) c_km1[m] = a.q[QI(m, k - 2)];       // next level's km1 = max(1, (k-1)-1)
+      const double c_k = SA(M_C + m, k), c_km1 = SA(M_C + m, km1), c_kp1 = SA(M_C + m, kp1);
+      double pgu, pgd;
+      if (k == 1) {
+        pgu = 0.0; pgd = 0.0;
+      } else if (k == pver) {
+        pgu = -P.momcu * (mu_k * (c_k - c_km1) / dp_km1);
+        pgd = -P.momcd * (md_k * (c_k - c_km1) / dp_km1);
+      } else {
+        pgu = -P.momcu * 0.5 * (mu_k * (c_k - c_km1) / dp_km1 + mu_kp1 * (c_kp1 - c_k) / dp_k);
+        pgd = -P.momcd * 0.5 * (md_k * (c_k - c_km1) / dp_km1 + md_kp1 * (c_kp1 - c_k) / dp_k);
       }
-      mu_kp1 = mu_k; dp_k = dp_km1;
-      if (k - 1 >= 1) { mu_k = GA(mu, k - 1); dp_km1 = GA(dp, max(1, k - 2)); }
+      const double chat = 0.5 * (c_k + c_km1);
+      SA(M_CHAT + m, k) = chat; SA(M_CONU + m, k) = chat; SA(M_COND + m, k) = chat;
+      SA(M_PGU + m, k) = pgu; SA(M_PGD + m, k) = pgd;
+      SA(M_T23 + m, k) = SA(M_EU, k) * c_k * dp_k;            // eu*cnst*dp of level k (updraft recurrence)
     }
   }
-  // ---------------- sweep 2: k = 1 .. pver, finishing level k-1 one step late ----------------
-  {
-    double c_k[2], c_km1[2], c_j[2] = {0, 0}, c_jm1[2] = {0, 0};   // j = k-1 (level being finished)
-    double cond_km1[2] = {0, 0}, pgd_km1[2] = {0, 0};
-    double X_j[2] = {0, 0}, Y_j[2] = {0, 0}, mf_j[2] = {0, 0};
-    double md_km1 = 0.0, ed_km1 = 0.0, dp_km1 = 0.0, dp_j = 0.0;
-    double mu_k = GA(mu, 1), md_k = GA(md, 1), dp_k = GA(dp, 1);
+  __syncwarp();
+  PAR {          // terms of the downdraft recurrence at level k use level k-1 (needs pgd of all levels)
+    const int km1 = max(1, k - 1);
 #pragma unroll
-    for (int m = 0; m < 2; ++m) { c_k[m] = act[m] ? a.q[QI(m, 1)] : 0.0; c_km1[m] = c_k[m]; }
-    for (int k = 1; k <= pver + 1; ++k) {
-      double X_k[2] = {0, 0}, Y_k[2] = {0, 0}, mf_k[2] = {0, 0}, c_kp1[2] = {0, 0};
-      double mu_kp1 = 0.0, md_kp1 = 0.0, dp_kp1 = 0.0, ed_k = 0.0;
-      if (k <= pver) {
-        ed_k = GA(ed, k);
-        if (k < pver) { mu_kp1 = GA(mu, k + 1); md_kp1 = GA(md, k + 1); dp_kp1 = GA(dp, k + 1); }
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          if (!act[m]) continue;
-          c_kp1[m] = (k < pver) ? a.q[QI(m, k + 1)] : c_k[m];
-          double pgd;
-          if (k == 1) {
-            pgd = 0.0;
-          } else if (k == pver) {
-            const double mddudp = md_k * (c_k[m] - c_km1[m]) / dp_km1;
-            pgd = -P.momcd * mddudp;
-          } else {
-            const double mddudp = (md_k * (c_k[m] - c_km1[m]) / dp_km1 + md_kp1 * (c_kp1[m] - c_k[m]) / dp_k);
-            pgd = -P.momcd * 0.5 * mddudp;
-          }
-          const double chat = 0.5 * (c_k[m] + c_km1[m]);
-          double cond = chat;
-          if (k == 2) {
-            // operator precedence exactly as written in the reference (zm_conv.F90:2554)
-            if (md_k < -mbsth) cond = (-ed_km1 * c_km1[m] * dp_km1) - pgd_km1[m] * dp_km1 / md_k;
-          } else if (k >= 3) {
-            if (md_k < -mbsth)
-              cond = (md_km1 * cond_km1[m] - ed_km1 * c_km1[m] * dp_km1 - pgd_km1[m] * dp_km1) / md_k;
-          }
-          a.icwd[QI(m, k)] = cond;
-          a.pgdall[QI(m, k)] = -pgd;
-          const double conu = a.icwu[QI(m, k)];
-          X_k[m] = mu_k * (conu - chat);
-          Y_k[m] = md_k * (cond - chat);
-          mf_k[m] = (k >= ktm) ? (-X_k[m] - Y_k[m]) : 0.0;
-          cond_km1[m] = cond; pgd_km1[m] = pgd;
-        }
-      }
-      // ---- finish level j = k-1 ----
-      if (k >= 2) {
-        const int j = k - 1;
-        double wf[2] = {0, 0};
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          if (!act[m]) continue;
-          // kp1 = min(pver, j+1): at j = pver the "k" quantities are those of level pver again
-          const double Xp = (j < pver) ? X_k[m] : X_j[m], Yp = (j < pver) ? Y_k[m] : Y_j[m];
-          double dc = 0.0;
-          if (j >= ktm) dc = +(Xp - X_j[m] + Yp - Y_j[m]) / dp_j;
-          if (j >= kbm && j == mx) dc = (1.0 / dp_j) * (-X_j[m] - Y_j[m]);
-          a.dqdt[QI(m, j)] = dc;
-          if (j >= ktm) wf[m] = c_j[m] - (mf_k[m] - mf_j[m]) * dt / dp_j;     // mf_k = 0 at j = pver
-        }
-        double gset2 = 0.0;
-        if (j >= ktm) {
-          // wind0(kp1) with kp1 = min(pver, j+1); c_k is level j+1 (or level pver again at j = pver)
-          const double u_p = (j < pver) ? c_k[0] : c_j[0], v_p = (j < pver) ? c_k[1] : c_j[1];
-          const double utop = (c_j[0] + c_jm1[0]) / 2.0;
-          const double vtop = (c_j[1] + c_jm1[1]) / 2.0;
-          const double ubot = (u_p + c_j[0]) / 2.0;
-          const double vbot = (v_p + c_j[1]) / 2.0;
-          const double fket = utop * mf_j[0] + vtop * mf_j[1];
-          const double fkeb = ubot * mf_k[0] + vbot * mf_k[1];
-          const double ketend_cons = (fket - fkeb) / dp_j;
-          const double ketend = ((wf[0] * wf[0] + wf[1] * wf[1]) - (c_j[0] * c_j[0] + c_j[1] * c_j[1])) * 0.5 / dt;
-          gset2 = ketend_cons - ketend;
-        }
-        a.seten[cidx(c, j - 1, ii, pver)] = gset2;
-      }
-      // ---- shift k -> k+1 ----
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        c_jm1[m] = c_j[m];                       // wind0(max(1, j-1)) for the next j
-        if (k == 1) c_jm1[m] = c_k[m];           // j = 1: km1 = 1
-        c_j[m] = c_k[m];
-        X_j[m] = X_k[m]; Y_j[m] = Y_k[m]; mf_j[m] = mf_k[m];
-        c_km1[m] = c_k[m]; c_k[m] = c_kp1[m];
-      }
-      dp_j = dp_k;
-      md_km1 = md_k; ed_km1 = ed_k; dp_km1 = dp_k;
-      mu_k = mu_kp1; md_k = md_kp1; dp_k = dp_kp1;
+    for (int m = 0; m < 2; ++m) {
+      SA(M_U2 + m, k) = SA(M_ED, km1) * SA(M_C + m, km1) * SA(M_DP, km1);
+      SA(M_U3 + m, k) = SA(M_PGD + m, km1) * SA(M_DP, km1);
     }
   }
-#undef GA
+  __syncwarp();
+  // ---- the two recurrences, both components, one loop (all lanes redundantly: same instruction count as one) ----
+  if (a.domom[0] || a.domom[1]) {
+    double conu_n[2] = {0.0, 0.0}, cond_p[2] = {SA(M_COND, 1), SA(M_COND + 1, 1)};
+    for (int n = 0; n < pver; ++n) {
+      const int kk = pver - n;                                 // updraft level, bottom-up
+      const int k = n + 2;                                     // downdraft level, top-down (2..pver)
+      const double mup = SA(M_MUP, kk), rmup = SA(M_RMUP, kk), mu_kkp1 = SA(M_MU, min(pver, kk + 1));
+      const double md_k = (k <= pver) ? SA(M_MD, k) : 0.0, md_km1 = (k <= pver) ? SA(M_MD, k - 1) : 0.0;
+      const double rmd = (k <= pver) ? SA(M_RMD, k) : 0.0;
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        // zm_conv.F90:2536-2575
+        double conu = SA(M_CONU + m, kk);
+        if (mup > mbsth) {
+          const double pgudp = SA(M_PGU + m, kk) * SA(M_DP, kk);
+          if (kk == pver) conu = zmm::div_rcp(+SA(M_T23 + m, kk) + pgudp, mup, rmup);
+          else            conu = zmm::div_rcp(mu_kkp1 * conu_n[m] + SA(M_T23 + m, kk) + pgudp, mup, rmup);
+        }
+        conu_n[m] = conu;
+        if (lane == 0) SA(M_CONU + m, kk) = conu;
+        // zm_conv.F90:2554 (operator precedence as written) and 2579-2589
+        if (k <= pver) {
+          double cond = SA(M_COND + m, k);
+          if (md_k < -mbsth) {
+            if (k == 2) cond = (-SA(M_U2 + m, k)) - zmm::div_rcp(SA(M_U3 + m, k), md_k, rmd);
+            else        cond = zmm::div_rcp(md_km1 * cond_p[m] - SA(M_U2 + m, k) - SA(M_U3 + m, k), md_k, rmd);
+          }
+          cond_p[m] = cond;
+          if (lane == 0) SA(M_COND + m, k) = cond;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // ---- fluxes, tendencies, end-of-step wind (level-local) ----
+  PAR {
+    const int kp1 = min(pver, k + 1);
+    const double dp_k = SA(M_DP, k);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      if (!a.domom[m]) { SA(M_MF + m, k) = 0.0; SA(M_WF + m, k) = 0.0; continue; }
+      const double X_k = SA(M_MU, k) * (SA(M_CONU + m, k) - SA(M_CHAT + m, k));
+      const double Y_k = SA(M_MD, k) * (SA(M_COND + m, k) - SA(M_CHAT + m, k));
+      const double X_p = SA(M_MU, kp1) * (SA(M_CONU + m, kp1) - SA(M_CHAT + m, kp1));
+      const double Y_p = SA(M_MD, kp1) * (SA(M_COND + m, kp1) - SA(M_CHAT + m, kp1));
+      double dc = 0.0;
+      if (k >= ktm) dc = +(X_p - X_k + Y_p - Y_k) / dp_k;
+      if (k >= kbm && k == mx) dc = (1.0 / dp_k) * (-X_k - Y_k);
+      a.dqdt[QI(m, k)] = dc;
+      a.pguall[QI(m, k)] = -SA(M_PGU + m, k);
+      a.pgdall[QI(m, k)] = -SA(M_PGD + m, k);
+      a.icwu[QI(m, k)] = SA(M_CONU + m, k);
+      a.icwd[QI(m, k)] = SA(M_COND + m, k);
+      SA(M_MF + m, k) = (k >= ktm) ? (-X_k - Y_k) : 0.0;
+    }
+  }
+  __syncwarp();
+  PAR {
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+      if (a.domom[m])
+        SA(M_WF + m, k) = (k >= ktm) ? SA(M_C + m, k) - (SA(M_MF + m, k + 1) - SA(M_MF + m, k)) * dt / SA(M_DP, k) : 0.0;
+  }
+  __syncwarp();
+  // ---- KE dissipation heating (zm_conv.F90:2675-2712) ----
+  PAR {
+    double gset2 = 0.0;
+    if (k >= ktm) {
+      const int km1 = max(1, k - 1), kp1 = min(pver, k + 1);
+      const double u0 = SA(M_C, k), v0 = SA(M_C + 1, k);
+      const double utop = (u0 + SA(M_C, km1)) / 2.0;
+      const double vtop = (v0 + SA(M_C + 1, km1)) / 2.0;
+      const double ubot = (SA(M_C, kp1) + u0) / 2.0;
+      const double vbot = (SA(M_C + 1, kp1) + v0) / 2.0;
+      const double fket = utop * SA(M_MF, k) + vtop * SA(M_MF + 1, k);
+      const double fkeb = ubot * SA(M_MF, k + 1) + vbot * SA(M_MF + 1, k + 1);
+      const double ketend_cons = (fket - fkeb) / SA(M_DP, k);
+      const double uf = SA(M_WF, k), vf = SA(M_WF + 1, k);
+      const double ketend = ((uf * uf + vf * vf) - (u0 * u0 + v0 * v0)) * 0.5 / dt;
+      gset2 = ketend_cons - ketend;
+    }
+    a.seten[cidx(c, k - 1, ii, pver)] = gset2;
+  }
+#undef SA
 #undef QI
+#undef PAR
 }
 
 // ---- convtran --------------------------------------------------------------------------------------

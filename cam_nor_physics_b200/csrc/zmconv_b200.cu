@@ -269,7 +269,10 @@ int momtran_launch(Workspace& ws, cudaStream_t s, MomArgs a, bool own_arena = tr
   k_chunk_bounds<<<(a.nchunks * 32 + 127) / 128, 128, 0, s>>>(a.nchunks, a.jt, a.mx, a.lengath, ktm, kbm, slots, count);
   ++tls_launches;
   k_momtran_init<<<592, 256, 0, s>>>(a); ++tls_launches;
-  k_momtran_t<<<(ncolpad + 63) / 64, 64, 0, s>>>(a);
+  const size_t smem_mom = momtran_smem_bytes(pver);
+  if (smem_mom > 48 * 1024)
+    CK(cudaFuncSetAttribute(k_momtran_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mom));
+  k_momtran_t<<<(ncolpad + MOM_WARPS - 1) / MOM_WARPS, 32 * MOM_WARPS, smem_mom, s>>>(a);   // warp per convective column
   ++tls_launches;
   CK(cudaGetLastError());
   return 0;
