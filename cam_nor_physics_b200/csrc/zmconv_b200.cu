@@ -60,6 +60,16 @@ struct Workspace {
     dtop = 0;
     return 0;
   }
+  void release() {                      // frees this arena's device memory, streams and events
+    for (auto e : tev) cudaEventDestroy(e);
+    tev.clear(); tnames.clear();
+    if (dbuf) { cudaFree(dbuf); dbuf = nullptr; dcap = 0; dtop = 0; }
+    if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
+    if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
+    if (side) { cudaStreamDestroy(side); side = nullptr; }
+    if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    last_count = nullptr; last_err = nullptr;
+  }
   template <class T> T* take(size_t n) {
     size_t b = (n * sizeof(T) + 255) & ~(size_t)255;
     T* p = (T*)(dbuf + dtop);
@@ -97,6 +107,16 @@ struct TendPipe {
     return nb;
   }
   static int first(int b, int nchunks, int nb) { return (int)((long long)nchunks * b / nb); }
+  void release() {
+    for (int b = 0; b < MAXB; ++b) work[b].release();
+    for (int b = 0; b < ninit; ++b) {
+      cudaEventDestroy(in_ready[b]); cudaEventDestroy(late_ready[b]); cudaEventDestroy(convr_done[b]);
+      cudaEventDestroy(done[b]); cudaEventDestroy(early_back[b]); cudaEventDestroy(final_back[b]);
+    }
+    ninit = 0; last_nb = 0; dev_nb = 0;
+    if (t0) { cudaEventDestroy(t0); t0 = nullptr; }
+    if (h2d) { cudaStreamDestroy(h2d); cudaStreamDestroy(d2h_early); cudaStreamDestroy(d2h_final); h2d = d2h_early = d2h_final = nullptr; }
+  }
   int init(int nb) {
     if (!h2d) {
       CK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
@@ -547,9 +567,15 @@ int zm_init(const zm_params_t* p) {
   return 0;
 }
 
+// Marks the library uninitialised and releases the CALLING thread's device arenas, streams and events
+// (other threads' per-thread resources live until those threads call zm_finalize themselves or the
+// process ends).
 int zm_finalize(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_inited = false;
+  cudaDeviceSynchronize();
+  tls_work.release(); tls_stage.release(); tls_stage2.release(); tls_pipe.release();
+  tls_mirror = PbufMirror{};
   return 0;
 }
 
