@@ -27,6 +27,7 @@ struct ConvrIn {
   const int* ncol;                       // [nchunks]
   const double *t, *qh, *pap, *paph, *dpp, *zm, *zi, *geos, *pblh, *tpert, *landfrac;
   double delt;
+  const double* org;                     // zm_org only: state%q(:,:,ixorg), (pcols,pver) per chunk; else NULL
 };
 struct ConvrOut {
   double *prec, *jctop, *jcbot, *qtnd, *heat, *mcon, *cme, *cape, *eurt, *dlf, *pflx, *zdu, *rprd;
@@ -83,7 +84,8 @@ __global__ void k_convr_init(ConvrIn in, ConvrOut o, ConvrWork w) {
 
 // ---- buoyan_dilute + parcel_dilute, one thread per column ----------------------------------
 // zm_conv.F90:4425-4819 and 4824-5277.  PASS 1: every column.  PASS 2: worklist wl1 only.
-template <int PASS>
+// ORG = true adds the zm_org branches of parcel_dilute (zm_conv.F90:5066-5074, 5186-5188, 5255-5257).
+template <int PASS, bool ORG = false>
 __global__ void __launch_bounds__(128, PASS == 1 ? 3 : 2)      // pass 2 has few warps: let it keep everything in registers
 k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   extern __shared__ double sm_buoy[];               // [pver+2][blockDim.x]
@@ -107,6 +109,8 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   const double pblh = in.pblh[(size_t)c * pcols + i];
   const double tpert = in.tpert[(size_t)c * pcols + i];
   const double dmpdz = w.dmpdz[col];
+  const double landfrac = ORG ? in.landfrac[(size_t)c * pcols + i] : 0.0;
+  const double org2rkm = 10.0, org2Tpert = 0.0;     // zm_conv.F90:4948-4951
 
   // pblt (zm_conv.F90:839-843)
   int pblt = pver;
@@ -190,7 +194,9 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
     smix_p = sp0; qtmix_p = qtp0;
     qsmix2_p = qsmix1_p;
     double tpk = tmix1_p, qstpk = q_p;
-    double tpv = (tpk + tpert) * (1.0 + qstpk / eps1) / (1.0 + qstpk);
+    double tpv;
+    if (ORG) tpv = (tpk + (org2Tpert * IN2(org, k) + tpert)) * (1.0 + qstpk / eps1) / (1.0 + qstpk);
+    else     tpv = (tpk + tpert) * (1.0 + qstpk / eps1) / (1.0 + qstpk);
     double tv = t_p * (1.0 + q_p / eps1) / (1.0 + q_p);
     BUOY(k) = tpv - tv + P.tiedke_add;
     tp_o[(size_t)(k - 1) * ncolpad] = tpk;
@@ -199,6 +205,7 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   const double lwmax = 1.e-3, tscool = 0.0;
   for (int k = mx - 1; k >= msg + 1; --k) {
     const double t_k = IN2(t, k), q_k = IN2(qh, k), p_k = IN2(pap, k) * 0.01, z_k = IN2(zm, k) + zs;
+    const double org_k = ORG ? IN2(org, k) : 0.0;
     // ---- loop 1 body (zm_conv.F90:5042-5144) ----
     double dp = (p_k - p_p);
     double qtenv = 0.5 * (q_k + q_p);
@@ -209,7 +216,15 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
     double senv = enthalpy_q(tenv, penv, qtenv, zenv, dum);
     double dpdz = -(penv * grav) / (P.rgas * tenv);
     double dzdp = 1.0 / dpdz;
-    double dmpdp = dmpdz * dzdp;
+    double dmpdp;
+    if (ORG) {                                   // tht_tweaks: dmpdz_lnd = dmpdz_mask (zm_conv.F90:5072)
+      double dmpdz_mask = dmpdz;
+      const double dmpdz_lnd = dmpdz_mask;
+      dmpdz_mask = landfrac * dmpdz_lnd + (1.0 - landfrac) * dmpdz_mask;
+      dmpdp = (dmpdz_mask / (1.0 + org_k * org2rkm)) * dzdp;
+    } else {
+      dmpdp = dmpdz * dzdp;
+    }
     sp = sp - dmpdp * dp * senv;
     qtp = qtp - dmpdp * dp * qtenv;
     mp = mp - dmpdp * dp;
@@ -256,7 +271,9 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
     }
     double tpk = tmix2;
     double qstpk = (new_q > qsmix2) ? qsmix2 : new_q;
-    double tpv = (tpk + tpert) * (1.0 + qstpk / eps1) / (1.0 + new_q);
+    double tpv;
+    if (ORG) tpv = (tpk + (org2Tpert * org_k + tpert)) * (1.0 + qstpk / eps1) / (1.0 + new_q);
+    else     tpv = (tpk + tpert) * (1.0 + qstpk / eps1) / (1.0 + new_q);
     double tv = t_k * (1.0 + q_k / eps1) / (1.0 + q_k);
     BUOY(k) = tpv - tv + P.tiedke_add;
     tp_o[(size_t)(k - 1) * ncolpad] = tpk;

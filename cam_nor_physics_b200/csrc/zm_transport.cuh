@@ -23,7 +23,18 @@ k_conv_evap(EvapArgs a) {
   int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= a.nchunks * pcols) return;
   const int c = col / pcols, i = col - c * pcols;
-  if (i >= a.ncol[c]) return;
+  if (i >= a.ncol[c]) {
+    // padding lanes: the reference leaves its intent(out) arrays untouched there; define them (zero) so that
+    // what goes back to the host never depends on stale device memory
+    for (int k = 0; k < pver; ++k) {
+      const size_t e = cidx(c, k, i, pver);
+      a.tend_s[e] = 0.0; a.tend_q[e] = 0.0; a.tend_s_snwprd[e] = 0.0; a.tend_s_snwevmlt[e] = 0.0;
+      a.ntprprd[e] = 0.0; a.ntsnprd[e] = 0.0;
+    }
+    for (int k = 0; k < pverp; ++k) { a.flxprec[cidx(c, k, i, pverp)] = 0.0; a.flxsnow[cidx(c, k, i, pverp)] = 0.0; }
+    a.snow[col] = 0.0;
+    return;
+  }
   const double tmelt = P.tmelt, gravit = P.gravit, latice = P.latice, latvap = P.latvap;
   double prec = a.prec[col] * 1000.0;
   double flxprec = 0.0, flxsnow = 0.0, evpvint = 0.0;
@@ -40,7 +51,8 @@ k_conv_evap(EvapArgs a) {
     if (t > tmelt) { flxsntm = 0.0; snowmlt = flxsnow * gravit / pdel; }
     else           { flxsntm = flxsnow; snowmlt = 0.0; }
     double evplimit = fmax2(1.0 - q / (1.0 + q) / qs, 0.0);
-    const double kemask = P.ke;
+    // zm_conv.F90:1860-1864
+    const double kemask = P.zm_org ? P.ke * (1.0 - a.landfrac[col]) + P.ke_lnd * a.landfrac[col] : P.ke;
     double evpprec = kemask * (1.0 - cldfrc) * evplimit * sqrt(flxprec);
     evplimit = fmin2(evplimit, flxprec * gravit / pdel);
     evplimit = fmin2(evplimit, (prec - evpvint) * gravit / pdel);
@@ -74,6 +86,40 @@ k_conv_evap(EvapArgs a) {
   }
   a.prec[col] = flxprec / 1000.0;
   a.snow[col] = flxsnow / 1000.0;
+}
+
+// ---- zm_org (organisation tracer) -------------------------------------------------------------
+// org2d(i,:) = sum(dpp*org)/sum(dpp) over the levels with org > 0 (zm_conv.F90:793-819), orgt = 0 (:555-556).
+// Thread per column, levels summed in the reference's order.  Padding lanes (i >= ncol) get 0.
+__global__ void k_org2d(int nchunks, const int* ncol, const double* org, const double* dpp, double* orgt,
+                        double* org2d) {
+  const int pcols = P.pcols, pver = P.pver;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= nchunks * pcols) return;
+  const int c = col / pcols, i = col - c * pcols;
+  double orgavg = 0.0, dptot = 0.0;
+  if (i < ncol[c]) {
+    for (int k = 0; k < pver; ++k) {
+      const size_t e = cidx(c, k, i, pver);
+      const double o = org[e];
+      if (o > 0) { orgavg = orgavg + dpp[e] * o; dptot = dptot + dpp[e]; }
+    }
+    if (dptot > 0) orgavg = orgavg / dptot;
+  }
+  for (int k = 0; k < pver; ++k) { const size_t e = cidx(c, k, i, pver); org2d[e] = orgavg; orgt[e] = 0.0; }
+}
+// org tendency after zm_conv_evap (zm_conv_intr.F90:773-777), added to the zero tendency zm_convr returned
+__global__ void k_org_tend(int nchunks, const int* ncol, const double* org, const double* evapcdp, double ztodt,
+                           double* orgt) {
+  const int pcols = P.pcols, pver = P.pver;
+  const size_t n2 = (size_t)nchunks * pcols * pver;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e % pcols), c = (int)(e / ((size_t)pcols * pver));
+    if (i >= ncol[c]) continue;
+    double x = fmin2(1.0, fmax2(0.0, (50.0 * 1000.0 * 1000.0 * fabs(evapcdp[e])) - (org[e] / 10800.0)));
+    x = (x - org[e]) / ztodt;
+    orgt[e] = orgt[e] + x;
+  }
 }
 
 // ---- chunk-wide ktm / kbm (zm_conv.F90:2076-2081) + compact list of convective slots: warp per chunk --

@@ -86,6 +86,10 @@ struct PbufMirror {
   const int *jt = nullptr, *maxg = nullptr, *ideep = nullptr, *lengath = nullptr;
 };
 thread_local PbufMirror tls_mirror;
+// zm_org = 1: the pointer dummies org / orgt / org2d of zm_convr (zm_conv.F90:421-423), attached per call
+// with zm_org_fields (host pointers for the host-pointer entry points, device pointers for *_dev)
+struct OrgFields { const double* org = nullptr; double* orgt = nullptr; double* org2d = nullptr; };
+thread_local OrgFields tls_org;
 thread_local Workspace tls_work;     // kernel work arrays
 thread_local Workspace tls_stage;    // device staging of user arrays for the host-pointer API
 thread_local Workspace tls_stage2;   // staging for zm_conv_tend_2_batch (must not disturb tls_stage: the mirror lives there)
@@ -165,8 +169,13 @@ size_t convr_work_bytes(size_t ncolpad, int pver) {
 
 // enqueue the whole zm_convr pipeline on stream s (no host synchronisation)
 int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOut& o,
-                 bool own_arena = true) {
+                 bool own_arena = true, double* orgt = nullptr, double* org2d = nullptr) {
   const int pcols = g_params.pcols, pver = g_params.pver;
+  const bool org_on = g_params.zm_org != 0;
+  if (org_on && !(in.org && orgt && org2d)) {
+    tls_err = "zm_org = 1: call zm_org_fields(org, orgt, org2d) before zm_convr / zm_conv_tend";
+    return -8;
+  }
   const size_t ncolpad = (size_t)in.nchunks * pcols;
   if (own_arena && ws.ensure(convr_work_bytes(ncolpad, pver))) return -100;
   ConvrWork w;
@@ -192,11 +201,17 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
     CK(cudaFuncSetAttribute(k_buoyan_dilute<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_buoyan_dilute<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_buoyan_undilute, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((k_buoyan_dilute<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((k_buoyan_dilute<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   tick(ws, s, "start");
   k_convr_init<<<592, 256, 0, s>>>(in, o, w); ++tls_launches;
+  if (org_on) {      // zm_conv.F90:555-556, 793-819
+    k_org2d<<<nblk_cols, TB, 0, s>>>(in.nchunks, in.ncol, in.org, in.dpp, orgt, org2d); ++tls_launches;
+  }
   tick(ws, s, "convr_init");
   if (g_params.cam3) k_buoyan_undilute<<<nblk_cols, TB, smem, s>>>(in, w);     // zm_conv.F90:871-880
+  else if (org_on)   k_buoyan_dilute<1, true><<<nblk_cols, TB, smem, s>>>(in, w);
   else               k_buoyan_dilute<1><<<nblk_cols, TB, smem, s>>>(in, w);
   ++tls_launches;
   tick(ws, s, "buoyan_dilute_pass1");
@@ -205,7 +220,9 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   k_cldprp_pass1_w<<<nblk_pl, 32 * PL_WARPS, smem_pl, s>>>(in, w);
   ++tls_launches;
   tick(ws, s, "cldprp_pass1");
-  k_buoyan_dilute<2><<<nblk_cols, TB, smem, s>>>(in, w); ++tls_launches;
+  if (org_on) k_buoyan_dilute<2, true><<<nblk_cols, TB, smem, s>>>(in, w);
+  else        k_buoyan_dilute<2><<<nblk_cols, TB, smem, s>>>(in, w);
+  ++tls_launches;
   tick(ws, s, "buoyan_dilute_pass2");
   k_trigger<1><<<nwarpblk, 128, 0, s>>>(in, o, w); ++tls_launches;
   tick(ws, s, "trigger_final");
@@ -510,7 +527,7 @@ void zm_params_default(zm_params_t* p, int pcols, int pver, int limcnv) {
 // zm_convi (zm_conv.F90:115-227)
 int zm_init(const zm_params_t* p) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (p->zm_org || p->microp) { tls_err = "zm_org / zmconv_microp are out of scope (zm_microphysics absent)"; return -2; }
+  if (p->microp) { tls_err = "zmconv_microp is out of scope (zm_microphysics is not part of the reference tree)"; return -2; }
   if (p->masterproc && p->num_cin > 5) { tls_err = "**** ZM_CONVI : NUM_CIN must not exceeed 5 ****"; return -3; }
   if (p->num_cin < 1 || p->num_cin > ZM_MAXCIN) { tls_err = "num_cin out of range 1..5"; return -3; }
   if (p->cam3 && p->num_cin != 5) {
@@ -523,7 +540,7 @@ int zm_init(const zm_params_t* p) {
   g_params = *p;
   ZmDevParams d;
   d.pcols = p->pcols; d.pver = p->pver; d.pverp = p->pver + 1; d.limcnv = p->limcnv; d.msg = p->limcnv - 1;
-  d.num_cin = p->num_cin; d.no_deep_pbl = p->no_deep_pbl; d.lparcel_pbl = p->lparcel_pbl; d.cam3 = p->cam3;
+  d.num_cin = p->num_cin; d.no_deep_pbl = p->no_deep_pbl; d.lparcel_pbl = p->lparcel_pbl; d.cam3 = p->cam3; d.zm_org = p->zm_org != 0;
   d.rl = p->latvap; d.cpres = p->cpair; d.ke = p->ke; d.ke_lnd = p->ke_lnd; d.c0_lnd = p->c0_lnd;
   d.c0_ocn = p->c0_ocn; d.tau = p->tau; d.tfreez = p->tmelt; d.eps1 = p->epsilo; d.momcu = p->momcu;
   d.momcd = p->momcd; d.rgrav = 1.0 / p->gravit; d.rgas = p->rair; d.grav = p->gravit; d.cp = p->cpair;
@@ -637,7 +654,9 @@ int zm_convr_batch_dev(int nchunks, const int* ncol, const double* t, const doub
   ConvrIn in{nchunks, ncol, t, qh, pap, paph, dpp, zm, zi, geos, pblh, tpert, landfrac, delt};
   ConvrOut o{prec, jctop, jcbot, qtnd, heat, mcon, cme, cape, eurt, dlf, pflx, zdu, rprd,
              mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, lengath, ql, rliq, dif, dnlf, dnif, rice};
-  return convr_launch(ws, s, in, o);
+  const OrgFields of = tls_org; tls_org = OrgFields{};       // one-shot
+  in.org = g_params.zm_org ? of.org : nullptr;
+  return convr_launch(ws, s, in, o, true, of.orgt, of.org2d);
 }
 
 int zm_convr_batch(int nchunks, const int* ncol, const double* t, const double* qh, double* prec,
@@ -654,9 +673,15 @@ int zm_convr_batch(int nchunks, const int* ncol, const double* t, const double* 
   const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc;
   const size_t n2 = nc * L, n2p = nc * (L + 1);
   Workspace& st = tls_stage;
-  size_t bytes = al(nchunks, 4) + 22 * al(n2, 8) + 4 * al(n2p, 8) + 13 * al(nc, 8) + 4 * al(nc, 4) + 8192;
+  size_t bytes = al(nchunks, 4) + 25 * al(n2, 8) + 4 * al(n2p, 8) + 13 * al(nc, 8) + 4 * al(nc, 4) + 8192;
   if (st.ensure(bytes)) return -100;
   Stager S(st);
+  const OrgFields of = tls_org; tls_org = OrgFields{};       // one-shot
+  const bool org_on = g_params.zm_org != 0;
+  if (org_on && !(of.org && of.orgt && of.org2d)) {
+    tls_err = "zm_org = 1: call zm_org_fields(org, orgt, org2d) before zm_convr_batch";
+    return -8;
+  }
   const int* d_ncol = S.in(ncol, nchunks);
   ConvrIn in{nchunks, d_ncol, S.in(t, n2), S.in(qh, n2), S.in(pap, n2), S.in(paph, n2p), S.in(dpp, n2),
              S.in(zm, n2), S.in(zi, n2p), S.in(geos, nc), S.in(pblh, nc), S.in(tpert, nc),
@@ -671,7 +696,9 @@ int zm_convr_batch(int nchunks, const int* ncol, const double* t, const double* 
   o.ideep = S.out(ideep, nc); o.lengath = S.out(lengath, (size_t)nchunks); o.ql = S.out(ql, n2);
   o.rliq = S.out(rliq, nc); o.dif = S.out(dif, n2); o.dnlf = S.out(dnlf, n2); o.dnif = S.out(dnif, n2);
   o.rice = S.out(rice, nc);
-  int rc = convr_launch(tls_work, st.stream, in, o);
+  double *d_orgt = nullptr, *d_org2d = nullptr;
+  if (org_on) { in.org = S.in(of.org, n2); d_orgt = S.out(of.orgt, n2); d_org2d = S.out(of.org2d, n2); }
+  int rc = convr_launch(tls_work, st.stream, in, o, true, d_orgt, d_org2d);
   if (rc) return rc;
   if (S.flush()) return -100;
   return read_failures(tls_work, st.stream);
@@ -835,7 +862,8 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
                            double* evapcdp, double* flxprec, double* flxsnow, double* dlf, double* mu,
                            double* md, double* du, double* eu, double* ed, double* dp, double* dsubcld,
                            int* jt, int* maxg, int* ideep, int* lengath, double* cape, void* stream,
-                           const TendHooks* hooks) {
+                           const TendHooks* hooks, const double* org = nullptr, double* orgt = nullptr,
+                           double* org2d = nullptr) {
   NEED_INIT();
   if (nchunks <= 0) return 0;
   const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc;
@@ -853,7 +881,8 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
   ConvrIn in{nchunks, ncol, t, q, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac, 0.5 * ztodt};
   ConvrOut o{prec, jctop, jcbot, qtnd, heat, mcon, cme, cape, eurt, dlf, pflx, zdu, rprd,
              mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, lengath, ql, rliq, dif, dnlf, dnif, rice};
-  int rc = convr_launch(ws, s, in, o, false);
+  in.org = g_params.zm_org ? org : nullptr;
+  int rc = convr_launch(ws, s, in, o, false, orgt, org2d);
   if (rc) return rc;
   if (hooks) {
     CK(cudaEventRecord(hooks->convr_done, s));            // zm_convr outputs are final from here on
@@ -879,6 +908,9 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
   }
   rc = evap_launch(fork ? ws.side : s, ea);
   if (rc) return rc;
+  if (g_params.zm_org) {     // zm_conv_intr.F90:773-777 (needs evapcdp = ev_q)
+    k_org_tend<<<1184, 256, 0, fork ? ws.side : s>>>(nchunks, ncol, org, ev_q, ztodt, orgt); ++tls_launches;
+  }
   if (fork) CK(cudaEventRecord(ws.ev_join, ws.side));
   tick(ws, s, "zm_conv_evap");
   MomArgs ma;
@@ -922,11 +954,12 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
   NB = NB < 1 ? 1 : (NB > TendPipe::MAXB ? TendPipe::MAXB : NB);
   while (NB > 1 && nchunks / NB < 128) --NB;
   tp.dev_nb = 0;
+  const OrgFields of = tls_org; tls_org = OrgFields{};       // one-shot
   if (NB == 1 || g_profile)
     return conv_tend_impl(tls_work, nchunks, ncol, t, q, u, v, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac,
                           cld, ztodt, ptend_s, ptend_q, ptend_u, ptend_v, mcon, cme, pflx, zdu, rliq, rice, jctop,
                           jcbot, prec, snow, ql, rprd, evapcdp, flxprec, flxsnow, dlf, mu, md, du, eu, ed, dp, dsubcld,
-                          jt, maxg, ideep, lengath, cape, stream, nullptr);
+                          jt, maxg, ideep, lengath, cape, stream, nullptr, of.org, of.orgt, of.org2d);
   if (tp.init(NB)) return -100;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t pc = g_params.pcols, L = g_params.pver, s2 = pc * L, s2p = pc * (L + 1), s1 = pc;
@@ -944,7 +977,9 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
                             O2(ptend_q), O2(ptend_u), O2(ptend_v), O2P(mcon), O2(cme), O2P(pflx), O2(zdu), O1(rliq),
                             O1(rice), O1(jctop), O1(jcbot), O1(prec), O1(snow), O2(ql), O2(rprd), O2(evapcdp),
                             O2P(flxprec), O2P(flxsnow), O2(dlf), O2(mu), O2(md), O2(du), O2(eu), O2(ed), O2(dp),
-                            O1(dsubcld), O1(jt), O1(maxg), O1(ideep), lengath + c0, O1(cape), (void*)ws.stream, nullptr);
+                            O1(dsubcld), O1(jt), O1(maxg), O1(ideep), lengath + c0, O1(cape), (void*)ws.stream, nullptr,
+                            of.org ? O2(of.org) : nullptr, of.orgt ? O2(of.orgt) : nullptr,
+                            of.org2d ? O2(of.org2d) : nullptr);
 #undef O2
 #undef O2P
 #undef O1
@@ -971,7 +1006,7 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc;
   const size_t n2 = nc * L, n2p = nc * (L + 1);
   Workspace& st = tls_stage;
-  if (st.ensure(al(nchunks, 4) + 24 * al(n2, 8) + 6 * al(n2p, 8) + 14 * al(nc, 8) + 4 * al(nc, 4) + 8192))
+  if (st.ensure(al(nchunks, 4) + 27 * al(n2, 8) + 6 * al(n2p, 8) + 14 * al(nc, 8) + 4 * al(nc, 4) + 8192))
     return -100;
   // The batch is cut into NB sub-batches of whole chunks (columns are independent).  Sub-batch b's inputs
   // travel host->device while sub-batch b-1 computes, and its outputs travel back while sub-batch b+1
@@ -1012,6 +1047,15 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
          *d_prec = DOUTF(prec, s1), *d_snow = DOUTF(snow, s1), *d_ql = DOUTE(ql, s2), *d_rprd = DOUTE(rprd, s2),
          *d_evap = DOUTF(evapcdp, s2), *d_fp = DOUTF(flxprec, s2p), *d_fs = DOUTF(flxsnow, s2p), *d_dlf = DOUTE(dlf, s2),
          *d_cape = DOUTE(cape, s1);
+  const OrgFields of = tls_org; tls_org = OrgFields{};       // one-shot
+  const double* d_org = nullptr; double *d_orgt = nullptr, *d_org2d = nullptr;
+  if (g_params.zm_org) {
+    if (!(of.org && of.orgt && of.org2d)) {
+      tls_err = "zm_org = 1: call zm_org_fields(org, orgt, org2d) before zm_conv_tend_batch";
+      return -8;
+    }
+    d_org = DIN(of.org, s2); d_org2d = DOUTE(of.org2d, s2); d_orgt = DOUTF(of.orgt, s2);
+  }
 #undef DIN
 #undef DLATE
 #undef DOUTE
@@ -1055,7 +1099,8 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
                         O1(d_rliq), O1(d_rice), O1(d_jctop), O1(d_jcbot), O1(d_prec), O1(d_snow), O2(d_ql),
                         O2(d_rprd), O2(d_evap), O2P(d_fp), O2P(d_fs), O2(d_dlf), O2(d_mu), O2(d_md), O2(d_du),
                         O2(d_eu), O2(d_ed), O2(d_dp), O1(d_dsub), O1(d_jt), O1(d_maxg), O1(d_ideep), d_len + c0,
-                        O1(d_cape), (void*)ws.stream, &hooks);
+                        O1(d_cape), (void*)ws.stream, &hooks, d_org ? O2(d_org) : nullptr,
+                        d_orgt ? O2(d_orgt) : nullptr, d_org2d ? O2(d_org2d) : nullptr);
 #undef O2
 #undef O2P
 #undef O1
@@ -1089,6 +1134,14 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
     fails += f;
   }
   return fails;
+}
+
+// zm_org = 1: attach org (in), orgt and org2d (out), shapes (pcols,pver) per chunk, for the NEXT zm_convr_batch /
+// zm_conv_tend_batch [_dev] call of this thread (host pointers for the host-pointer entry points, device pointers
+// for *_dev).  Replaces the pointer dummies org/orgt/org2d of zm_convr (zm_conv.F90:242, 421-423).
+int zm_org_fields(const double* org, double* orgt, double* org2d) {
+  tls_org = OrgFields{org, orgt, org2d};
+  return 0;
 }
 
 // Timeline of this thread's last zm_conv_tend_batch call: for each sub-batch 6 times in ms since the first

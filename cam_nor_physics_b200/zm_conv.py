@@ -71,7 +71,7 @@ EXPORTS = [
     "zm_convr_batch_dev", "zm_conv_evap_batch", "zm_conv_evap_batch_dev", "zm_momtran_batch",
     "zm_momtran_batch_dev", "zm_convtran_batch", "zm_convtran_batch_dev", "zm_sync_check",
     "zm_conv_tend_batch", "zm_conv_tend_batch_dev", "zm_microbench", "zm_conservation_dev",
-    "zm_conv_tend_2_batch", "zm_tend_trace", "zm_geopotential_t_batch", "zm_geopotential_t_batch_dev", "zm_convect_diagnostics_batch",
+    "zm_conv_tend_2_batch", "zm_tend_trace", "zm_org_fields", "zm_geopotential_t_batch", "zm_geopotential_t_batch_dev", "zm_convect_diagnostics_batch",
     "zm_convect_diagnostics_batch_dev",
     "zm_math_eval_dev", "zm_math_eval_host", "zm_thermo_eval_dev", "zm_fp64_peak_flops",
     "zm_set_profiling", "zm_get_kernel_times", "zm_launch_count",
@@ -147,9 +147,16 @@ def _grid():
     return _params.pcols, _params.pver
 
 
-def zm_convr(ncol, t, qh, pblh, zm, geos, zi, pap, paph, dpp, delt, tpert, landfrac):
+def zm_org_fields(org, orgt, org2d):
+    """Attach the pointer dummies org / orgt / org2d of zm_convr (zm_conv.F90:421-423) for the next zm_convr /
+    zm_conv_tend call of this thread (needed iff zmconv_org)."""
+    _check(lib().zm_org_fields(_dp(org), _dp(orgt), _dp(org2d)), "zm_org_fields")
+
+
+def zm_convr(ncol, t, qh, pblh, zm, geos, zi, pap, paph, dpp, delt, tpert, landfrac, org=None):
     """zm_convr (zm_conv.F90:231).  Inputs `[nchunks, nlev, pcols]` / `[nchunks, pcols]`;
-    returns a dict with every intent(out) dummy of the reference by its Fortran name."""
+    returns a dict with every intent(out) dummy of the reference by its Fortran name (plus `orgt`, `org2d`
+    when the organisation tracer `org` is passed, zmconv_org)."""
     pc, L = _grid()
     ncol = _i(ncol)
     nch = ncol.shape[0]
@@ -164,6 +171,10 @@ def zm_convr(ncol, t, qh, pblh, zm, geos, zi, pap, paph, dpp, delt, tpert, landf
     t, qh, pblh, zm, geos, zi, pap, paph, dpp, tpert, landfrac = map(
         _f, (t, qh, pblh, zm, geos, zi, pap, paph, dpp, tpert, landfrac))
     assert t.shape == (nch, L, pc) and paph.shape == (nch, L + 1, pc) and geos.shape == (nch, pc)
+    if org is not None:
+        org = _f(org)
+        o["orgt"], o["org2d"] = z2(), z2()
+        zm_org_fields(org, o["orgt"], o["org2d"])
     rc = lib().zm_convr_batch(
         C.c_int(nch), _ip(ncol), _dp(t), _dp(qh), _dp(o["prec"]), _dp(o["jctop"]), _dp(o["jcbot"]),
         _dp(pblh), _dp(zm), _dp(geos), _dp(zi), _dp(o["qtnd"]), _dp(o["heat"]), _dp(pap), _dp(paph),
@@ -277,6 +288,11 @@ def zm_conv_tend(ncol, state: dict, ztodt: float, out: dict | None = None, keep_
         out["lengath"] = np.zeros(nch, np.int32)
     ins = [_f(state[k]) for k in TEND_IN_ORDER]
     args = [C.c_int(nch), _ip(ncol)] + [_dp(a) for a in ins] + [C.c_double(ztodt)]
+    if "org" in state:                      # zmconv_org: organisation tracer in, its tendency and column mean out
+        org = _f(state["org"])
+        if "orgt" not in out:
+            out["orgt"], out["org2d"] = np.zeros_like(org), np.zeros_like(org)
+        zm_org_fields(org, out["orgt"], out["org2d"])
     mirror_only = {"mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg"} if keep_pbuf_on_device else set()
     for k in TEND_ARG_ORDER:
         a = out[k]

@@ -42,6 +42,12 @@ module zm_conv
        type(zm_params_t), intent(in) :: p
      end function zm_init
 
+     integer(c_int) function zm_org_fields(org, orgt, org2d) bind(C, name='zm_org_fields')
+       import :: c_int, c_double
+       real(c_double), intent(in)  :: org(*)
+       real(c_double), intent(out) :: orgt(*), org2d(*)
+     end function zm_org_fields
+
      integer(c_int) function zm_last_error(buf, buflen) bind(C, name='zm_last_error')
        import :: c_int, c_char
        character(kind=c_char), intent(out) :: buf(*)
@@ -102,6 +108,8 @@ module zm_conv
 
   logical :: zmconv_microp = .false.
 
+  logical, save :: zm_org_on = .false.    ! zmconv_org as given to zm_convi (read-only afterwards)
+
 contains
 
   subroutine zm_abort(where, rc)
@@ -135,6 +143,7 @@ contains
 
     p%pcols = pcols; p%pver = pver; p%limcnv = limcnv_in; p%num_cin = zmconv_num_cin
     p%zm_org = merge(1, 0, zmconv_org); p%microp = merge(1, 0, zmconv_microp_in)
+    zm_org_on = zmconv_org
     p%no_deep_pbl = merge(1, 0, no_deep_pbl_in); p%lparcel_pbl = merge(1, 0, zmconv_parcel_pbl)
     p%cam3 = merge(1, 0, cam_physpkg_is('cam3')); p%masterproc = merge(1, 0, masterproc)
     p%c0_lnd = zmconv_c0_lnd; p%c0_ocn = zmconv_c0_ocn; p%ke = zmconv_ke; p%ke_lnd = zmconv_ke_lnd
@@ -147,8 +156,9 @@ contains
     if (rc /= 0) call zm_abort('zm_convi', rc)
   end subroutine zm_convi
 
-  ! zm_conv.F90:231-244 (org/orgt/org2d/conv/aero are accepted and ignored: zm_org and zmconv_microp
-  ! must be .false., zm_init rejects them otherwise)
+  ! zm_conv.F90:231-244.  With zmconv_org the pointer dummies org/orgt/org2d (contiguous (pcols,pver) slices,
+  ! zm_conv_intr.F90:656-659) are attached with zm_org_fields before the call; conv/aero are accepted and
+  ! ignored (zmconv_microp must be .false., zm_init rejects it otherwise)
   subroutine zm_convr(lchnk, ncol, t, qh, prec, jctop, jcbot, pblh, zm, geos, zi, qtnd, heat, pap, paph, dpp, &
                       delt, mcon, cme, cape, eurt, tpert, dlf, pflx, zdu, rprd, mu, md, du, eu, ed, &
                       dp, dsubcld, jt, maxg, ideep, lengath, ql, rliq, landfrac, org, orgt, org2d, &
@@ -170,6 +180,9 @@ contains
     integer(c_int) :: rc, nc(1), len1(1)
 
     nc(1) = ncol
+    if (zm_org_on) then
+       rc = zm_org_fields(org, orgt, org2d)
+    end if
     rc = zm_convr_batch(1_c_int, nc, t, qh, prec, jctop, jcbot, pblh, zm, geos, zi, qtnd, heat, pap, paph, dpp, &
                         delt, mcon, cme, cape, eurt, tpert, dlf, pflx, zdu, rprd, mu, md, du, eu, ed, dp, &
                         dsubcld, jt, maxg, ideep, len1, ql, rliq, landfrac, dif, dnlf, dnif, rice)

@@ -29,7 +29,8 @@ extern "C" {
 typedef struct zm_params {
   int pcols, pver;              /* ppgrid (zm_conv.F90:17) */
   int limcnv, num_cin;          /* zm_convi args (zm_conv.F90:115-120) */
-  int zm_org, microp;           /* must be 0: branches out of scope (zm_microphysics absent) */
+  int zm_org;                   /* organisation tracer branches (zm_conv.F90:793-819, 5066-5074, 1860-1864): see zm_org_fields */
+  int microp;                   /* must be 0: zm_microphysics is not part of the reference tree */
   int no_deep_pbl, lparcel_pbl;
   int cam3;                     /* cam_physpkg_is('cam3'), zm_conv.F90:871 -> undilute buoyan */
   int masterproc;               /* zm_conv.F90:213: tentrm=-dmpdz only assigned on masterproc */
@@ -124,7 +125,7 @@ int zm_convtran_batch_dev(int nchunks, const int* doconvtran, const double* q, i
  * the device end to end: zm_convr (delt = 0.5*ztodt, :666) -> physics_update of state1 (t += s*dt/cpair,
  * q(:,:,1) += qtnd*dt clipped at qmin=1e-12; physics_types.F90:322-329,427) -> zm_conv_evap (:764) ->
  * momtran on (u,v) (:822) -> ptend_all = sum of the three ptend_loc (:736,803,833).  mcon is returned
- * in kg/m2/s (:693).  convtran1 (:875), zm_org and zmconv_microp are separate / out of scope.
+ * in kg/m2/s (:693).  convtran1 (:875) is separate; zm_org goes through zm_org_fields; zmconv_microp is out of scope.
  * State in: t,q(wv),u,v,pmid,pint,pdel,zm,zi,phis + pblh,tpert,landfrac,cld(pbuf 'CLD').
  * Out: ptend_all%s,q(:,:,1),u,v; the dummy outputs mcon,cme,pflx,zdu,rliq,rice,jctop,jcbot; and the
  * pbuf fields the reference fills (prec_dp, snow_dp, icwmrdp=ql, rprddp=rprd, nevapr_dpcu=evapcdp,
@@ -192,6 +193,16 @@ int zm_convect_diagnostics_batch_dev(int nchunks, const int* ncol, double* cmfmc
  * q, fracis, ptend_q are (pcols,pver,pcnst); pdeldry is (pcols,pver). */
 int zm_conv_tend_2_batch(int nchunks, const int* doconvtran, const double* q, int pcnst, const double* pdeldry,
                          const double* fracis, double* ptend_q, double ztodt, const int* cnst_is_dry);
+
+/* zm_org = 1 (zmconv_org): attach the pointer dummies org / orgt / org2d of zm_convr
+ * (zm_conv.F90:242, 421-423; zm_conv_intr.F90:656-659) for the NEXT zm_convr_batch / zm_conv_tend_batch [_dev] call
+ * of the calling thread: host pointers for the host-pointer entry points, device pointers for *_dev.  All three are
+ * (pcols,pver) per chunk.  org: state%q(:,:,ixorg) (in).  org2d: pressure-weighted column mean of org (out,
+ * zm_conv.F90:793-819).  orgt: ptend%q(:,:,ixorg) (out) -- zm_convr zeroes it (zm_conv.F90:555-556); zm_conv_tend adds
+ * the organisation tendency diagnosed from the evaporation of convective precipitation (zm_conv_intr.F90:773-777).
+ * With zm_org = 1 the test-parcel entrainment is divided by (1 + 10 org) and land-weighted (zm_conv.F90:5066-5074) and
+ * zm_conv_evap uses ke over ocean / ke_lnd over land (zm_conv.F90:1860-1864).  Calls without attached fields fail (-8). */
+int zm_org_fields(const double* org, double* orgt, double* org2d);
 
 /* Pipeline timeline of the calling thread's last zm_conv_tend_batch (diagnostics): per sub-batch six times in
  * ms (inputs on device, late inputs on device, zm_convr done, all kernels done, zm_convr outputs on host,

@@ -58,6 +58,10 @@ Module g;
 thread_local long long cnt[10];
 thread_local int brent_fail;
 // optional trace of Brent inversions (rcall, icol, lchnk, state-function evaluations) for divergence studies
+// zm_org (organisation tracer): the pointer dummies org/orgt/org2d of zm_convr (zm_conv.F90:421-423).
+// tl_* point at the chunk being processed; the batch drivers set them from the batch-wide base pointers.
+thread_local const double* tl_org = nullptr; thread_local double* tl_orgt = nullptr; thread_local double* tl_org2d = nullptr;
+const double* batch_org = nullptr; double* batch_orgt = nullptr; double* batch_org2d = nullptr;
 thread_local int* trace_buf = nullptr; thread_local int trace_n = 0, trace_cap = 0;
 
 inline double fmax2(double a, double b) { return (a > b) ? a : b; }
@@ -224,7 +228,10 @@ void invert(int rcall, int icol, int lchnk, double s, double p, double z, double
 void parcel_dilute(int lchnk, int ncol, int msg, I1& klaunch, C2 p, C2 z, C2 t, C2 q,
                    const double* tpert_, A2 tp, A2 tpv, A2 qstp, W1& pl, double* tl_, W1& ql,
                    int* lcl_, const double* landfrac_, C2 dmpdz) {
-  (void)landfrac_;
+  const double* org_ = g.zm_org ? tl_org : nullptr;        // pointer dummy `org` (zm_conv.F90:4865)
+  const double org2rkm = 10.0, org2Tpert = 0.0;             // zm_conv.F90:4948-4951
+  auto org = [&](int i, int k) { return org_[(size_t)(i - 1) + (size_t)g.pcols * (k - 1)]; };
+  auto landfrac = [&](int i) { return landfrac_[i - 1]; };
   const int pcols = g.pcols, pver = g.pver;
   auto tpert = [&](int i) { return tpert_[i - 1]; };
   auto tl = [&](int i) -> double& { return tl_[i - 1]; };
@@ -268,7 +275,14 @@ void parcel_dilute(int lchnk, int ncol, int msg, I1& klaunch, C2 p, C2 z, C2 t, 
 
         dpdz = -(penv * g.grav) / (g.rgas * tenv);
         dzdp = 1.0 / dpdz;
-        dmpdp = dmpdz(i, k) * dzdp;
+        if (g.zm_org) {                       // zm_conv.F90:5066-5074 (tht_tweaks: dmpdz_lnd = dmpdz_mask)
+          double dmpdz_mask = dmpdz(i, k);
+          const double dmpdz_lnd = dmpdz_mask;
+          dmpdz_mask = landfrac(i) * dmpdz_lnd + (1.0 - landfrac(i)) * dmpdz_mask;
+          dmpdp = (dmpdz_mask / (1.0 + org(i, k) * org2rkm)) * dzdp;
+        } else {
+          dmpdp = dmpdz(i, k) * dzdp;
+        }
 
         sp(i) = sp(i) - dmpdp * dp * senv;
         qtp(i) = qtp(i) - dmpdp * dp * qtenv;
@@ -307,7 +321,10 @@ void parcel_dilute(int lchnk, int ncol, int msg, I1& klaunch, C2 p, C2 z, C2 t, 
       if (k == klaunch(i)) {
         tp(i, k) = tmix(i, k);
         qstp(i, k) = q(i, k);
-        tpv(i, k) = (tp(i, k) + tpert(i)) * (1.0 + qstp(i, k) / g.eps1) / (1.0 + qstp(i, k));
+        if (g.zm_org)                         // zm_conv.F90:5186-5188
+          tpv(i, k) = (tp(i, k) + (org2Tpert * org(i, k) + tpert(i))) * (1.0 + qstp(i, k) / g.eps1) / (1.0 + qstp(i, k));
+        else
+          tpv(i, k) = (tp(i, k) + tpert(i)) * (1.0 + qstp(i, k) / g.eps1) / (1.0 + qstp(i, k));
       }
       if (k < klaunch(i)) {
         smix(i, k) = entropy(tmix(i, k), p(i, k), qtmix(i, k));
@@ -336,7 +353,10 @@ void parcel_dilute(int lchnk, int ncol, int msg, I1& klaunch, C2 p, C2 z, C2 t, 
         } else {
           qstp(i, k) = new_q;
         }
-        tpv(i, k) = (tp(i, k) + tpert(i)) * (1.0 + qstp(i, k) / g.eps1) / (1.0 + new_q);
+        if (g.zm_org)                         // zm_conv.F90:5255-5257
+          tpv(i, k) = (tp(i, k) + (org2Tpert * org(i, k) + tpert(i))) * (1.0 + qstp(i, k) / g.eps1) / (1.0 + new_q);
+        else
+          tpv(i, k) = (tp(i, k) + tpert(i)) * (1.0 + qstp(i, k) / g.eps1) / (1.0 + new_q);
       }
     }
   }
@@ -1222,6 +1242,21 @@ int convr(int lchnk, int ncol, const double* t_, const double* qh_, double* prec
   auto maxg = [&](int i) -> int& { return maxg_[i - 1]; };
   int& lengath = *lengath_;
 
+  if (g.zm_org) {
+    // orgt(:,:) = 0 (zm_conv.F90:555-556); org2d = pressure-thickness weighted column mean of org over the
+    // levels where org > 0 (zm_conv.F90:793-819)
+    for (size_t e = 0; e < (size_t)pcols * pver; ++e) tl_orgt[e] = 0.0;
+    for (int i = 1; i <= ncol; ++i) {
+      double orgavg = 0.0, dptot = 0.0;
+      for (int k = 1; k <= pver; ++k) {
+        const double o = tl_org[(size_t)(i - 1) + (size_t)pcols * (k - 1)];
+        if (o > 0) { orgavg = orgavg + dpp(i, k) * o; dptot = dptot + dpp(i, k); }
+      }
+      if (dptot > 0) orgavg = orgavg / dptot;
+      for (int k = 1; k <= pver; ++k) tl_org2d[(size_t)(i - 1) + (size_t)pcols * (k - 1)] = orgavg;
+    }
+  }
+
   W1 cin(pcols), zs(pcols), mumax(pcols), pblt(pcols), tl(pcols), capeg(pcols), tlg(pcols),
       landfracg(pcols), mb(pcols), dmmx(pcols), dmsm(pcols), orgc(pcols);
   W2 dlg(pcols, pver), pflxg(pcols, pverp), cug(pcols, pver), evpg(pcols, pver);
@@ -1524,7 +1559,7 @@ void zmo_params_default(zmo_params_t* p, int pcols, int pver, int limcnv) {
 
 // zm_convi  zm_conv.F90:115-227
 int zmo_convi(const zmo_params_t* p) {
-  if (p->zm_org || p->microp) return 2;      // out of scope
+  if (p->microp) return 2;                   // zm_microphysics is not part of the reference tree
   g.pcols = p->pcols; g.pver = p->pver; g.pverp = p->pver + 1;
   g.cpair = p->cpair; g.epsilo = p->epsilo; g.gravit = p->gravit; g.latice = p->latice;
   g.latvap = p->latvap; g.tmelt = p->tmelt; g.rair = p->rair; g.cpwv = p->cpwv; g.cpliq = p->cpliq;
@@ -1540,7 +1575,7 @@ int zmo_convi(const zmo_params_t* p) {
   g.cp = g.cpres;
   g.dcol = (g.cpliq - g.cpwv) / g.latvap;
   g.c0_lnd = p->c0_lnd; g.c0_ocn = p->c0_ocn; g.num_cin = p->num_cin; g.ke = p->ke;
-  g.ke_lnd = p->ke_lnd; g.zm_org = false; g.momcu = p->momcu; g.momcd = p->momcd;
+  g.ke_lnd = p->ke_lnd; g.zm_org = p->zm_org != 0; g.momcu = p->momcu; g.momcd = p->momcd;
   g.zmconv_microp = false;
   g.tiedke_add = p->tiedke_add; g.capelmt = p->capelmt; g.dmpdz_param = p->dmpdz;
   g.no_deep_pbl = p->no_deep_pbl != 0; g.lparcel_pbl = p->lparcel_pbl != 0; g.tau = p->tau;
@@ -1617,7 +1652,8 @@ void zmo_conv_evap(int ncol, int lchnk, const double* t_, const double* pmid_, c
         snowmlt(i) = 0.0;
       }
       evplimit = fmax2(1.0 - q(i, k) / (1.0 + q(i, k)) / qs(i, k), 0.0);
-      kemask = g.ke;
+      if (g.zm_org) kemask = g.ke * (1.0 - landfrac_[i - 1]) + g.ke_lnd * landfrac_[i - 1];   // zm_conv.F90:1860-1864
+      else kemask = g.ke;
       evpprec(i) = kemask * (1.0 - cldfrc(i, k)) * evplimit * std::sqrt(flxprec(i, k));
       // tht_tweaks: the second evplimit assignment is commented out (zm_conv.F90:1875-1877)
       evplimit = fmin2(evplimit, flxprec(i, k) * gravit / pdel(i, k));
@@ -1934,6 +1970,12 @@ int zmo_ienthalpy(double s, double p, double z, double qt, double tfg, double* t
 void zmo_qsat_hpa(double t, double p, double* es, double* qm) { qsat_hPa(t, p, *es, *qm); }
 void zmo_qsat_table(double t, double p, double* es, double* qs) { g.estbl.qsat(t, p, g.epsilo, *es, *qs); }
 
+// zm_org: attach the org/orgt/org2d fields (pointer dummies of zm_convr, zm_conv.F90:421-423).  For the
+// single-chunk entry points they address one chunk; for the *_batch drivers the whole batch [chunk][k][i].
+void zmo_org_fields(const double* org, double* orgt, double* org2d) {
+  tl_org = org; tl_orgt = orgt; tl_org2d = org2d;
+  batch_org = org; batch_orgt = orgt; batch_org2d = org2d;
+}
 void zmo_trace_set(int* buf, int cap) { trace_buf = buf; trace_cap = cap; trace_n = 0; }
 int zmo_trace_count(void) { return trace_n / 4; }
 void zmo_counters_reset(void) { for (int i = 0; i < 10; ++i) cnt[i] = 0; }
@@ -1958,6 +2000,7 @@ int zmo_convr_batch(int nchunks, const int* ncol, const double* t, const double*
 #endif
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : fails)
   for (int c = 0; c < nchunks; ++c) {
+    if (g.zm_org) { tl_org = batch_org + (size_t)c * L; tl_orgt = batch_orgt + (size_t)c * L; tl_org2d = batch_org2d + (size_t)c * L; }
     fails += convr(c + 1, ncol[c], t + c * L, qh + c * L, prec + c * pc, jctop + c * pc, jcbot + c * pc,
                    pblh + c * pc, zm + c * L, geos + c * pc, zi + c * Lp, qtnd + c * L, heat + c * L,
                    pap + c * L, paph + c * Lp, dpp + c * L, delt, mcon + c * Lp, cme + c * L,
@@ -2008,6 +2051,17 @@ static int conv_tend_chunk(int lchnk, int ncol, const double* t, const double* q
   zmo_conv_evap(ncol, lchnk, t1.data(), pmid, pdel, q1.data(), landfrac, ev_s.data(), snwprd.data(),
                 snwevmlt.data(), ev_q.data(), rprd, cld, ztodt, prec, snow, ntprprd.data(), ntsnprd.data(),
                 flxprec, flxsnow);
+  if (g.zm_org) {
+    // zm_conv_intr.F90:773-777: ptend_loc%q(:ncol,:,ixorg) from |evapcdp| and org; physics_ptend_sum adds it to
+    // the (zero) org tendency zm_convr returned, so orgt ends up holding ptend_all%q(:,:,ixorg)
+    for (int k = 1; k <= pver; ++k)
+      for (int i = 1; i <= ncol; ++i) {
+        size_t e = (size_t)(i - 1) + (size_t)pcols * (k - 1);
+        double x = std::min(1.0, std::max(0.0, (50.0 * 1000.0 * 1000.0 * std::fabs(ev_q[e])) - (tl_org[e] / 10800.0)));
+        x = (x - tl_org[e]) / ztodt;
+        tl_orgt[e] = tl_orgt[e] + x;
+      }
+  }
   const int domom[2] = {1, 1};
   zmo_momtran(lchnk, ncol, domom, winds.data(), 2, mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, 1,
               *lengath, 0, wtend.data(), pgu.data(), pgd.data(), icwu.data(), icwd.data(), ztodt, seten.data());
@@ -2040,6 +2094,7 @@ int zmo_conv_tend_batch(int nchunks, const int* ncol, const double* t, const dou
 #endif
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : fails)
   for (int c = 0; c < nchunks; ++c) {
+    if (g.zm_org) { tl_org = batch_org + (size_t)c * L; tl_orgt = batch_orgt + (size_t)c * L; tl_org2d = batch_org2d + (size_t)c * L; }
     fails += conv_tend_chunk(
         c + 1, ncol[c], t + c * L, q + c * L, u + c * L, v + c * L, pmid + c * L, pint + c * Lp, pdel + c * L,
         zm + c * L, zi + c * Lp, phis + c * pc, pblh + c * pc, tpert + c * pc, landfrac + c * pc, cld + c * L,

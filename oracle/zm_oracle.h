@@ -34,7 +34,7 @@ const char* zmo_math_backend(void);
 int zmo_convi(const zmo_params_t* p);
 
 /* zm_convr (zm_conv.F90:231) -- argument order of the Fortran dummy list, minus
- * org/orgt/org2d/conv/aero (zm_org and zmconv_microp are out of scope).
+ * org/orgt/org2d (attached with zmo_org_fields when zm_org = 1) and conv/aero (zmconv_microp is out of scope).
  * Returns 0, or the number of Brent non-convergence events (reference: endrun). */
 int zmo_convr(int lchnk, int ncol,
               const double* t, const double* qh, double* prec, double* jctop, double* jcbot,
@@ -92,6 +92,10 @@ void zmo_qsat_hpa(double t, double p, double* es, double* qm);
 void zmo_qsat_table(double t, double p, double* es, double* qs);
 
 /* operation counters for the roofline flop figure (per-thread; reset then read) */
+/* zm_org = 1 (organisation tracer): attach org (in), orgt (out: zeroed by zm_convr, zm_conv.F90:555; after
+ * zmo_conv_tend_batch it holds ptend_all%q(:,:,ixorg), zm_conv_intr.F90:773-777) and org2d (out, zm_conv.F90:793-819)
+ * before calling zmo_convr / zmo_convr_batch / zmo_conv_tend_batch.  Shapes (pcols,pver) per chunk. */
+void zmo_org_fields(const double* org, double* orgt, double* org2d);
 void zmo_counters_reset(void);
 /* optional per-inversion trace: 4 ints per call (rcall, icol, lchnk, state-function evaluations); single thread */
 void zmo_trace_set(int* buf, int cap);

@@ -117,7 +117,10 @@ class Oracle:
         self.lib.zmo_counters_reset()
 
     # -- zm_convr over a batch of chunks -------------------------------------------------
-    def convr_batch(self, ch, delt=None, nthreads=0):
+    def org_fields(self, org, orgt, org2d):
+        self.lib.zmo_org_fields(_dp(org), _dp(orgt), _dp(org2d))
+
+    def convr_batch(self, ch, delt=None, nthreads=0, org=None):
         """ch: soundings.Chunks.  Returns dict of outputs, arrays [nchunks, nlev, pcols]."""
         P = self.params
         nch, L, pc = ch.nchunks, P.pver, P.pcols
@@ -131,6 +134,10 @@ class Oracle:
                  ideep=np.zeros((nch, pc), np.int32), lengath=np.zeros(nch, np.int32),
                  ql=z2(), rliq=z1(), dif=z2(), dnlf=z2(), dnif=z2(), rice=z1())
         ncol = np.ascontiguousarray(ch.ncol, dtype=np.int32)
+        if org is not None:
+            org = _f(org)
+            o["orgt"], o["org2d"] = np.full_like(org, 7.0), np.zeros_like(org)
+            self.org_fields(org, o["orgt"], o["org2d"])
         rc = self.lib.zmo_convr_batch(
             C.c_int(nch), _ip(ncol), _dp(_f(ch.t)), _dp(_f(ch.q)), _dp(o["prec"]), _dp(o["jctop"]),
             _dp(o["jcbot"]), _dp(_f(ch.pblh)), _dp(_f(ch.zm)), _dp(_f(ch.phis)), _dp(_f(ch.zi)),
@@ -192,11 +199,15 @@ class Oracle:
                              _dp(o["icwd"]), C.c_double(dt), _dp(o["seten"]))
         return o
 
-    def conv_tend_batch(self, ch, nthreads=0):
+    def conv_tend_batch(self, ch, nthreads=0, org=None):
         """zm_conv_tend sequence on soundings.Chunks; same output names as zm_conv.zm_conv_tend."""
         P = self.params
         nch, L, pc = ch.nchunks, P.pver, P.pcols
         out = {}
+        if org is not None:
+            org = _f(org)
+            out["orgt"], out["org2d"] = np.full_like(org, 7.0), np.zeros_like(org)
+            self.org_fields(org, out["orgt"], out["org2d"])
         for k in ["ptend_s", "ptend_q", "ptend_u", "ptend_v", "cme", "zdu", "ql", "rprd", "evapcdp", "dlf",
                   "mu", "md", "du", "eu", "ed", "dp"]:
             out[k] = np.zeros((nch, L, pc))

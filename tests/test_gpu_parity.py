@@ -356,3 +356,26 @@ def test_finalize_releases_and_reinit_reproduces(built):
     for k in out1:
         assert np.array_equal(out1[k], out2[k]), k
     assert out1["lengath"].sum() > 0
+
+
+def test_zm_org_bit_exact_vs_oracle(built):
+    """zmconv_org branches: zm_convr and the zm_conv_tend sequence with an organisation tracer."""
+    Z = init_cuda(16, 32, zm_org=1)
+    o, _, rc = get_oracle("pm", 16, 32, zm_org=1)
+    assert rc == 0
+    ch = S.make_chunks(16 * 300 - 5, 32, 16, p_conv=0.6)
+    org = np.maximum(np.random.default_rng(3).uniform(-0.3, 1.0, ch.t.shape), 0.0)   # tracer in [0,1], ~23 % zeros
+    ref = o.convr_batch(ch, org=org)
+    out = Z.zm_convr(ch.ncol, ch.t, ch.q, ch.pblh, ch.zm, ch.phis, ch.zi, ch.pmid, ch.pint, ch.pdel,
+                     0.5 * ch.ztodt, ch.tpert, ch.landfrac, org=org)
+    assert_same(out, ref, CONVR_KEYS + ["orgt", "org2d"], 16, exact=True, what="zm_convr zm_org")
+    assert out["lengath"].sum() > 0 and np.any(out["org2d"] > 0)
+    st = state_of(ch); st["org"] = org
+    tref = o.conv_tend_batch(ch, org=org)
+    tout = Z.zm_conv_tend(ch.ncol, st, ch.ztodt)
+    assert_same(tout, tref, TEND_KEYS + ["orgt", "org2d"], 16, exact=True, what="zm_conv_tend zm_org")
+    assert np.any(tout["orgt"] != 0.0)
+    # a call without the fields attached fails loudly
+    with pytest.raises(Z.ZmError):
+        Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
+    init_cuda(16, 32)                   # back to the default configuration for the tests that follow

@@ -155,3 +155,37 @@ def test_geopotential_reproduces_the_input_heights(oracle_libm):
                                   ch.t[c], ch.q[c], rair[c], S.GRAVIT, zvir[c])
         assert np.allclose(zi, ch.zi[c], rtol=1e-12, atol=1e-9) and np.allclose(zm, ch.zm[c], rtol=1e-12, atol=1e-9)
         assert np.all(zi[-1] == 0.0)
+
+
+def test_zm_org_branches_oracle():
+    """zmconv_org (zm_conv.F90:555-556, 793-819, 5066-5074, 1860-1864; zm_conv_intr.F90:773-777).
+    org = 0 with all-ocean/all-land columns reproduces the zm_org = .false. zm_convr bit for bit; a positive
+    organisation reduces the test-parcel entrainment, so CAPE can only grow; org2d is the pressure-weighted mean
+    over org > 0; the tendency relaxes org toward min(1, 5e7 |evapcdp| - org/10800)."""
+    o0, _, _ = get_oracle("pm", 16, 32)
+    ch = S.make_chunks(640, 32, 16, p_conv=0.6)
+    ch.landfrac[:] = np.round(ch.landfrac)
+    base = o0.convr_batch(ch)
+    o1, p1, rc = get_oracle("pm", 16, 32, zm_org=1)
+    assert rc == 0
+    zero = np.zeros_like(ch.t)
+    r0 = o1.convr_batch(ch, org=zero)
+    for k in CONVR_KEYS:
+        assert np.array_equal(masked(r0, k, r0["lengath"], 16) if k in ("mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg")
+                              else r0[k], masked(base, k, base["lengath"], 16) if k in ("mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg")
+                              else base[k]), k
+    assert np.all(r0["orgt"] == 0.0) and np.all(r0["org2d"] == 0.0)
+    rng = np.random.default_rng(11)
+    org = np.maximum(rng.uniform(-0.3, 1.0, ch.t.shape), 0.0)      # the tracer lives in [0, 1]; ~23 % exact zeros
+    r1 = o1.convr_batch(ch, org=org)
+    assert np.all(r1["orgt"] == 0.0)
+    # org2d: weighted mean over org > 0
+    w = np.where(org > 0, ch.pdel, 0.0)
+    mean = (w * org).sum(axis=1) / np.maximum(w.sum(axis=1), 1e-300)
+    assert np.allclose(r1["org2d"], np.repeat(mean[:, None, :], 32, axis=1), rtol=1e-13)
+    # less entrainment where org > 0 cannot lower the trigger count by much; CAPE of triggered columns grows
+    assert r1["lengath"].sum() >= base["lengath"].sum()
+    t1 = o1.conv_tend_batch(ch, org=org)
+    assert t1["rc"] == 0
+    tgt = np.minimum(1.0, np.maximum(0.0, 5e7 * np.abs(t1["evapcdp"]) - org / 10800.0))
+    assert np.allclose(t1["orgt"], (tgt - org) / ch.ztodt, rtol=1e-13, atol=1e-18)
