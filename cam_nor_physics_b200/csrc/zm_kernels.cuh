@@ -309,8 +309,14 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
         }
       }
     }
+    // interface pressures are carried from level to level and fetched one level ahead (the loop used to wait
+    // for two dependent global loads per level: 5 % of the kernel's stall samples)
+    double pf_k = IN2P(paph, msg + 1) * 0.01, pf_n = IN2P(paph, msg + 2) * 0.01;
     for (int k = msg + 1; k <= mx; ++k) {
-      double lg = zmm::log_((IN2P(paph, k + 1) * 0.01) / (IN2P(paph, k) * 0.01));
+      const double pf_k1 = pf_n;
+      if (k < mx) pf_n = IN2P(paph, k + 2) * 0.01;
+      double lg = zmm::log_hot(div_hot(pf_k1, pf_k));        // log(pf(k+1)/pf(k)), zm_conv.F90:4789
+      pf_k = pf_k1;
       double b = BUOY(k);
 #pragma unroll
       for (int n = 0; n < ZM_MAXCIN; ++n) {
