@@ -28,15 +28,19 @@ enum PlumeArr {
 #define PL_WARPS 4      // warps (columns) per block
 #endif
 
-struct PlumeSh {
-  double* base; int ld;
-  __device__ __forceinline__ double& operator()(int a, int k) const { return base[a * ld + k]; }
+// Per-warp shared-memory work arrays [array][level]; the leading dimension is a compile-time constant
+// (32/64/128-level builds) so that S(A_X, k) is base + immediate + k instead of a multiply per access.
+template <int LD>
+struct PlumeShT {
+  double* base;
+  __device__ __forceinline__ double& operator()(int a, int k) const { return base[a * LD + k]; }
 };
 
 #define PAR(k, lo, hi) for (int k = (lo) + lane; k <= (hi); k += 32)
 #define WSYNC() __syncwarp()
 
 // gather one column into shared arrays (zm_conv.F90:926-940, 980-1027 / 1114-1195); returns dsubcld
+template <class PlumeSh>
 __device__ __forceinline__ double gather_column_w(const PlumeSh& S, const ConvrIn& in, int c, int i, int maxg,
                                                   int lane) {
   const int pver = P.pver, pcols = P.pcols, msg = P.msg;
@@ -80,7 +84,7 @@ __device__ __forceinline__ double gather_column_w(const PlumeSh& S, const ConvrI
 struct PlumeIdx { int jt, jlcl, j0, jd; };
 
 // cldprp for one column.  FULL=false stops after the cloud-top reset (zm_conv.F90:3646).
-template <bool FULL>
+template <bool FULL, class PlumeSh>
 __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int lel, double landfrac, int lane) {
   const int pver = P.pver, pverp = P.pverp, msg = P.msg, limcnv = P.limcnv;
   const double eps1 = P.eps1, zvir = P.zvir, cpvir = P.cpvir, dcol = P.dcol, tmelt = P.tmelt;
@@ -553,9 +557,12 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
   return R;
 }
 
-inline size_t plume_smem_bytes(int pver) { return (size_t)PL_WARPS * A_COUNT * (pver + 2) * sizeof(double); }
+// leading dimension of the per-warp arrays for a given level count (levels 0..pver+1 are addressed)
+inline int plume_ld(int pver) { return pver <= 32 ? 34 : (pver <= 64 ? 66 : 130); }
+inline size_t plume_smem_bytes(int pver) { return (size_t)PL_WARPS * A_COUNT * plume_ld(pver) * sizeof(double); }
 
 // ---- pass-1 plume: diagnose the pass-2 test-parcel entrainment rate (zm_conv.F90:1047-1078) ---
+template <int LD>
 __global__ void __launch_bounds__(32 * PL_WARPS)
 k_cldprp_pass1_w(ConvrIn in, ConvrWork w) {
   extern __shared__ double sm_pl[];
@@ -565,7 +572,7 @@ k_cldprp_pass1_w(ConvrIn in, ConvrWork w) {
   const int col = w.wl1[gw];
   const int pcols = P.pcols, pver = P.pver, msg = P.msg;
   const int c = col / pcols, i = col - c * pcols;
-  PlumeSh S{sm_pl + (size_t)wib * A_COUNT * (pver + 2), pver + 2};
+  const PlumeShT<LD> S{sm_pl + (size_t)wib * A_COUNT * LD};
   const int maxg = w.mx[col];
   gather_column_w(S, in, c, i, maxg, lane);
   cldprp_warp<false>(S, maxg, w.lel[col], in.landfrac[(size_t)c * pcols + i], lane);
@@ -588,6 +595,7 @@ k_cldprp_pass1_w(ConvrIn in, ConvrWork w) {
 }
 
 // ---- final plume: cldprp #2 + closure + limiter + q1q2 + scatter + prec -----------------------
+template <int LD>
 __global__ void __launch_bounds__(32 * PL_WARPS)
 k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
   extern __shared__ double sm_pl[];
@@ -601,7 +609,7 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
   const int gi = slot - c * pcols;                     // gathered position (0-based)
   const double eps1 = P.eps1, rl = P.rl, rd = P.rgas, grav = P.grav, cp = P.cpres;
   const double delt = in.delt;
-  PlumeSh S{sm_pl + (size_t)wib * A_COUNT * (pver + 2), pver + 2};
+  const PlumeShT<LD> S{sm_pl + (size_t)wib * A_COUNT * LD};
   const int maxg = w.mx[col], lel = w.lel[col], lcl = w.lcl[col];
   const double capeg = w.cape[col], tlg = w.tl[col];
   const double landfrac = in.landfrac[(size_t)c * pcols + i];

@@ -195,8 +195,12 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   const int nwarpblk = (int)(((size_t)in.nchunks * 32 + 127) / 128);
   const int nblk_pl = (int)((ncolpad + PL_WARPS - 1) / PL_WARPS);     // one warp per convective column
   const size_t smem_pl = plume_smem_bytes(pver);
-  CK(cudaFuncSetAttribute(k_cldprp_pass1_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
-  CK(cudaFuncSetAttribute(k_plume_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
+  // plume kernels are built for 32/64/128-level leading dimensions (compile-time shared-memory strides)
+  const int pl_ld = plume_ld(pver);
+  auto k_cld1 = pl_ld == 34 ? k_cldprp_pass1_w<34> : (pl_ld == 66 ? k_cldprp_pass1_w<66> : k_cldprp_pass1_w<130>);
+  auto k_plm = pl_ld == 34 ? k_plume_w<34> : (pl_ld == 66 ? k_plume_w<66> : k_plume_w<130>);
+  CK(cudaFuncSetAttribute(k_cld1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
+  CK(cudaFuncSetAttribute(k_plm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
   if (smem > 48 * 1024) {
     CK(cudaFuncSetAttribute(k_buoyan_dilute<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_buoyan_dilute<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -217,7 +221,7 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   tick(ws, s, "buoyan_dilute_pass1");
   k_trigger<0><<<nwarpblk, 128, 0, s>>>(in, o, w); ++tls_launches;
   tick(ws, s, "trigger_pass1");
-  k_cldprp_pass1_w<<<nblk_pl, 32 * PL_WARPS, smem_pl, s>>>(in, w);
+  k_cld1<<<nblk_pl, 32 * PL_WARPS, smem_pl, s>>>(in, w);
   ++tls_launches;
   tick(ws, s, "cldprp_pass1");
   if (org_on) k_buoyan_dilute<2, true><<<nblk_cols, TB, smem, s>>>(in, w);
@@ -226,7 +230,7 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   tick(ws, s, "buoyan_dilute_pass2");
   k_trigger<1><<<nwarpblk, 128, 0, s>>>(in, o, w); ++tls_launches;
   tick(ws, s, "trigger_final");
-  k_plume_w<<<nblk_pl, 32 * PL_WARPS, smem_pl, s>>>(in, o, w);
+  k_plm<<<nblk_pl, 32 * PL_WARPS, smem_pl, s>>>(in, o, w);
   ++tls_launches;
   tick(ws, s, "plume_closure_q1q2");
   CK(cudaGetLastError());
