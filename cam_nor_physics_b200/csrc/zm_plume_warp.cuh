@@ -16,12 +16,12 @@
 #include "zm_kernels.cuh"
 
 enum PlumeArr {
-  A_Q, A_T, A_P, A_Z, A_S, A_ZF, A_DZ, A_DP, A_SHAT, A_QHAT, A_TP, A_QSTP,
+  A_Q, A_T, A_P, A_Z, A_S, A_ZF, A_DZ, A_DP, A_SHAT, A_QHAT,
   A_MU, A_EU, A_DU, A_MD, A_ED, A_SD, A_QD, A_MC, A_QU, A_SU, A_QST, A_HMN, A_HSAT, A_QL, A_CMEG,
   A_PFLX, A_EVP, A_CU, A_RPRD, A_QCDE,
   A_GAMMA, A_HU, A_HD, A_EPS, A_F, A_K1, A_I2, A_I3, A_I4, A_QSTHAT, A_HSTHAT, A_GAMHAT, A_QDS,
-  A_MCP, A_MRL, A_TU, A_TD, A_W1, A_W2, A_W3, A_W4, A_W5, A_DPP,
-  A_COUNT
+  A_TU, A_TD, A_W1, A_W2, A_W3, A_W4, A_W5,
+  A_COUNT      // 50 arrays: 4 warps x 50 x 34 doubles = 54.4 KB per block, four blocks per SM at L32
 };
 
 #ifndef PL_WARPS
@@ -49,7 +49,6 @@ __device__ __forceinline__ double gather_column_w(const PlumeSh& S, const ConvrI
     size_t e = cidx(c, k - 1, i, pver);
     double qk = in.qh[e], tk = in.t[e];
     const double dppk = in.dpp[e];
-    S(A_DPP, k) = dppk;
     S(A_DP, k) = 0.01 * dppk;
     S(A_Q, k) = qk;
     S(A_T, k) = tk;
@@ -109,7 +108,6 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
       const double mrd = (1.0 + zvir * qk) * rd;
       const double mcp = (1.0 + cpvir * qk) * cp;
       const double mrl = (1.0 - dcol * (tk - tmelt)) * rl;
-      S(A_MCP, k) = mcp; S(A_MRL, k) = mrl;
       S(A_GAMMA, k) = qs * (1.0 + qs / eps1) * eps1 * mrl / (mrd * (tk * tk)) * mrl / mcp;
       const double hmn = mcp * tk + grav * zk + mrl * qk;
       S(A_HMN, k) = hmn;
@@ -129,7 +127,10 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
       const double q1 = S(A_QST, k - 1), q0 = S(A_QST, k), g1 = S(A_GAMMA, k - 1), g0 = S(A_GAMMA, k);
       const double qsthat = (fabs(q1 - q0) > 1.E-6) ? zmm::log_(q1 / q0) * q1 * q0 / (q1 - q0) : q0;
       S(A_QSTHAT, k) = qsthat;
-      S(A_HSTHAT, k) = S(A_MCP, k) * S(A_SHAT, k) + S(A_MRL, k) * qsthat;
+      // mcp, mrl of level k recomputed (same expressions as above) instead of kept in two more arrays
+      const double mcp = (1.0 + cpvir * S(A_Q, k)) * cp;
+      const double mrl = (1.0 - dcol * (S(A_T, k) - tmelt)) * rl;
+      S(A_HSTHAT, k) = mcp * S(A_SHAT, k) + mrl * qsthat;
       S(A_GAMHAT, k) = (fabs(g1 - g0) > 1.E-6) ? zmm::log_(g1 / g0) * g1 * g0 / (g1 - g0) : g0;
     }
   }
@@ -614,10 +615,6 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
   const double capeg = w.cape[col], tlg = w.tl[col];
   const double landfrac = in.landfrac[(size_t)c * pcols + i];
   const double dsubcld = gather_column_w(S, in, c, i, maxg, lane);
-  PAR(k, 1, pver) {
-    S(A_TP, k) = w.tp[(size_t)(k - 1) * ncolpad + col];
-    S(A_QSTP, k) = w.qstp[(size_t)(k - 1) * ncolpad + col];
-  }
   const PlumeIdx R = cldprp_warp<true>(S, maxg, lel, landfrac, lane);
   const int jt = R.jt, mx = maxg;
   const double dmpdz = w.dmpdz[col];
@@ -669,7 +666,9 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
         }
       }
       double dboydt = 0.0;
-      const double tpk = S(A_TP, k), qstpk = S(A_QSTP, k), tk = S(A_T, k), qk = S(A_Q, k);
+      // parcel temperature / humidity of the final CAPE pass, straight from the scratch arrays
+      const double tpk = w.tp[(size_t)(k - 1) * ncolpad + col], qstpk = w.qstp[(size_t)(k - 1) * ncolpad + col];
+      const double tk = S(A_T, k), qk = S(A_Q, k);
       if (k >= lel && k <= lcl) {
         const double pw = zmm::pow_(1000.0 / S(A_P, k), rd / cp);
         const double thetavp = tpk * pw * (1.0 + 1.608 * qstpk - q_mx);
@@ -764,7 +763,7 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
   double prec = 0.0, rliq = 0.0;
   WSYNC();
   PAR(k, 1, pver) {
-    const double dppk = S(A_DPP, k), qhk = S(A_Q, k);
+    const double dppk = in.dpp[cidx(c, k - 1, i, pver)], qhk = S(A_Q, k);
     const double dlfk = (k >= msg + 1) ? S(A_W3, k) : 0.0;
     const double qnew = qhk + 2.0 * delt * ((k >= msg + 1) ? S(A_W2, k) : 0.0);
     S(A_W4, k) = dppk * (qnew - qhk);
