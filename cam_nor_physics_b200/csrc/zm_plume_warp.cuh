@@ -18,10 +18,21 @@
 enum PlumeArr {
   A_Q, A_T, A_P, A_Z, A_S, A_ZF, A_DZ, A_DP, A_SHAT, A_QHAT,
   A_MU, A_EU, A_DU, A_MD, A_ED, A_SD, A_QD, A_MC, A_QU, A_SU, A_QST, A_HMN, A_HSAT, A_QL, A_CMEG,
-  A_PFLX, A_EVP, A_CU, A_RPRD, A_QCDE,
-  A_GAMMA, A_HU, A_HD, A_EPS, A_F, A_K1, A_I2, A_I3, A_I4, A_QSTHAT, A_HSTHAT, A_GAMHAT, A_QDS,
-  A_TU, A_TD, A_W1, A_W2, A_W3, A_W4, A_W5,
-  A_COUNT      // 50 arrays: 4 warps x 50 x 34 doubles = 54.4 KB per block, four blocks per SM at L32
+  A_PFLX, A_EVP, A_CU, A_RPRD,
+  A_GAMMA, A_HU, A_EPS, A_F, A_K1, A_I2, A_I3, A_I4, A_QSTHAT, A_HSTHAT, A_GAMHAT,
+  A_W1,
+  A_COUNT,     // 41 arrays: 4 warps x 41 x 34 doubles = 44.6 KB per block, FIVE blocks (20 warps) per SM at L32
+  // Arrays with disjoint lifetimes share storage (occupancy of these kernels is bounded by shared memory).
+  // Host array -> last use; guest -> first use, in the (straight-line) order of cldprp_warp / k_plume_w:
+  A_W4 = A_K1,       // k1: entrainment Taylor series (ends with the f(z) evaluation); W4 from the hu recurrence on
+  A_QCDE = A_I2,     // i2: as k1; qcde zero-filled with the tu initialisation, written by the rain-out section
+  A_TU = A_I3,       // i3: as k1; tu from the updraft temperature section on
+  A_W2 = A_I4,       // i4: as k1; W2 from the hu recurrence on
+  A_W3 = A_GAMMA,    // gamma only feeds gamhat (interface values, right after the saturation section)
+  A_W5 = A_QST,      // qst last read by the statement that first writes W5 (same level, same lane)
+  A_HD = A_F,        // f: ends with eps; hd/td/qds are (re)initialised at the start of the downdraft section
+  A_TD = A_EPS,      // eps: ends with the updraft mass flux
+  A_QDS = A_HSAT     // hsat: last read by the hu recurrence coefficients
 };
 
 #ifndef PL_WARPS
@@ -99,7 +110,7 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
     if (k <= pver) {
       const double qk = S(A_Q, k), tk = S(A_T, k), pk = S(A_P, k), zk = S(A_Z, k), sk = S(A_S, k);
       S(A_EU, k) = 0.0; S(A_DU, k) = 0.0; S(A_CU, k) = 0.0; S(A_EVP, k) = 0.0; S(A_CMEG, k) = 0.0;
-      S(A_QDS, k) = qk; S(A_MD, k) = 0.0; S(A_ED, k) = 0.0; S(A_SD, k) = sk; S(A_QD, k) = qk;
+      S(A_MD, k) = 0.0; S(A_ED, k) = 0.0; S(A_SD, k) = sk; S(A_QD, k) = qk;
       S(A_MC, k) = 0.0; S(A_QU, k) = qk; S(A_SU, k) = sk;
       double est, qs;
       qsat_hPa(tk, pk, est, qs);
@@ -112,10 +123,8 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
       const double hmn = mcp * tk + grav * zk + mrl * qk;
       S(A_HMN, k) = hmn;
       S(A_HSAT, k) = mcp * tk + grav * zk + mrl * qs;
-      S(A_HU, k) = hmn; S(A_HD, k) = hmn;
-      S(A_RPRD, k) = 0.0; S(A_QCDE, k) = 0.0;
-      S(A_TD, k) = (hmn - grav * S(A_ZF, k) - (1.0 + dcol * tmelt) * rl * qk) /
-                   (cp * (1.0 + (cpvir - dcol * (rl / cp)) * qk));
+      S(A_HU, k) = hmn;
+      S(A_RPRD, k) = 0.0;
     }
   }
   if (lane == 0) S(A_PFLX, 1) = 0.0;
@@ -305,6 +314,7 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
   PlumeIdx R{jt, jlcl, j0, jd};
   if (!FULL) return R;
 
+  PAR(k, 1, pver) S(A_QCDE, k) = 0.0;        // zm_conv.F90:3309 (its storage held i2 until now)
   // tu initialisation (zm_conv.F90:3649-3654)
   PAR(k, msg + 2, pver) {
     const double qu = S(A_QU, k);
@@ -424,7 +434,16 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
     }
   }
   WSYNC();
-  // downdraft (zm_conv.F90:3880-3975)
+  // downdraft (zm_conv.F90:3880-3975).  hd, qds, td start from their environment values (zm_conv.F90:3283-3312);
+  // set here because their storage held f / hsat / eps until now.
+  PAR(k, 1, pver) {
+    const double qk = S(A_Q, k), hmn = S(A_HMN, k);
+    S(A_HD, k) = hmn;
+    S(A_QDS, k) = qk;
+    S(A_TD, k) = (hmn - grav * S(A_ZF, k) - (1.0 + dcol * tmelt) * rl * qk) /
+                 (cp * (1.0 + (cpvir - dcol * (rl / cp)) * qk));
+  }
+  WSYNC();
   const double alfa = P.alfadet;
   double epsm = 0.0;
   jt = min(jt, jb - 1);
