@@ -129,11 +129,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = f"f09 FV grid shard: {args.ncols} columns x L{args.pver} per GPU, pcols=16, zm_conv_tend = " \
-               "zm_convr+physics_update+zm_conv_evap+momtran (BASELINE config 3)"
+    if args.ncols == NCOLS_F09 and args.pver == 32:
+        grid = f"f09 FV grid shard: {args.ncols} columns x L32 per GPU (BASELINE config 3)"
+    else:
+        grid = f"{args.ncols} columns x L{args.pver} per GPU (non-default size; BASELINE config 5 uses 131072 x L58 per GPU)"
+    workload = grid + ", pcols=16, zm_conv_tend = zm_convr+physics_update+zm_conv_evap+momtran"
+    step_gb = args.ncols * ((26 * args.pver + 15) * 8 + 12 + (14 * args.pver + 6) * 8 + 19 * args.pver * 8 + 12) / 1e9
     config = {"workload": workload, "columns_per_gpu": args.ncols, "pver": args.pver, "pcols": 16,
               "convective_fraction_target": args.pconv, "parcel_pbl": bool(args.parcel_pbl), "seed": 20261018, "parallelism": f"columns x{world}",
-              "l2": "per-step inputs+outputs (~0.85 GB) exceed the 126 MB L2; no explicit flush"}
+              "l2": f"per-step algorithmic inputs+outputs ({step_gb:.2f} GB) exceed the 126 MB L2; no explicit flush"}
 
     # ---------------- reference arm: CPU port of the reference on host cores ---------------------
     if args.impl == "reference":
@@ -249,16 +253,22 @@ def main():
     except Exception:
         fl, flops_per_col = {}, float("nan")
     fp64_peak = Z.fp64_peak_flops(20000)
+    # the committed flop count was captured on the default workload; it does not transfer to other level
+    # counts / launch parcels, so the FP64 fraction is only reported there
+    flops_valid = (args.ncols == int(fl.get("ncols", -1)) and L == 32 and not args.parcel_pbl
+                   and abs(args.pconv - 0.35) < 1e-12)
+    if not flops_valid:
+        flops_per_col = float("nan")
     achieved = flops_per_col * args.ncols / t_dom / 1e12
     alg_bytes = (6 * L + 2 + 2 * L + 6) * 8 + 12      # inputs t,q,pap,zm (L) + paph,zi (L+1) + 3; outputs tp,qstp + 6 scalars
     roofline = {"kernel": "k_buoyan_dilute<1> (dilute CAPE trigger, pass 1, all columns)",
-                "bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                "frac": achieved / (fp64_peak / 1e12),
+                "bound": "fp64", "achieved": achieved if flops_valid else None, "peak": fp64_peak / 1e12,
+                "unit": "TFLOP/s", "frac": achieved / (fp64_peak / 1e12) if flops_valid else None,
                 "peak_source": "FP64 FMA-chain microbenchmark run live in this process (MEASURED_PEAKS.json has no "
                                "FP64 entry; SURVEY.md section 6 asks the builder to measure it)",
-                "flops_per_column": flops_per_col, "flops_source": fl.get("source"),
+                "flops_per_column": flops_per_col if flops_valid else None, "flops_source": fl.get("source"),
                 "ms_per_launch": t_dom * 1e3,
-                "traffic": fl.get("dram_bytes_per_launch"),
+                "traffic": fl.get("dram_bytes_per_launch") if flops_valid else None,
                 "hbm": {"achieved_gbs": alg_bytes * args.ncols / t_dom / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                         "peak_kind": peak_kind, "alg_bytes_per_column": alg_bytes},
                 "kernel_ms": kavg}
