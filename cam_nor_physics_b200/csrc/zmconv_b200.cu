@@ -152,6 +152,18 @@ struct TendPipe {
 };
 thread_local TendPipe tls_pipe;
 
+// CUDA graph of one device-resident zm_conv_tend step (15 kernels, one memset, a fork/join with the side stream).
+// A step is launch-gap sensitive (several kernels run 10-50 us), and a model calls it every time step with the same
+// device arrays: the second call with an identical argument list is captured, later ones replay the graph.
+struct TendGraph {
+  std::vector<const void*> key;
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+  void clear() { if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; } key.clear(); launches = 0; }
+};
+thread_local TendGraph tls_graph;
+int g_epoch = 0;                       // bumped by zm_init: parameters are baked into captured kernels' constants
+
 inline size_t al(size_t n, size_t sz) { return (n * sz + 255) & ~(size_t)255; }
 
 void tick(Workspace& ws, cudaStream_t s, const char* name) {
@@ -542,6 +554,7 @@ int zm_init(const zm_params_t* p) {
     tls_err = "unsupported grid (need 1 <= pver <= 128, 2 <= limcnv <= pver)"; return -5;
   }
   g_params = *p;
+  ++g_epoch;
   ZmDevParams d;
   d.pcols = p->pcols; d.pver = p->pver; d.pverp = p->pver + 1; d.limcnv = p->limcnv; d.msg = p->limcnv - 1;
   d.num_cin = p->num_cin; d.no_deep_pbl = p->no_deep_pbl; d.lparcel_pbl = p->lparcel_pbl; d.cam3 = p->cam3; d.zm_org = p->zm_org != 0;
@@ -595,6 +608,7 @@ int zm_finalize(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_inited = false;
   cudaDeviceSynchronize();
+  tls_graph.clear();
   tls_work.release(); tls_stage.release(); tls_stage2.release(); tls_pipe.release();
   tls_mirror = PbufMirror{};
   return 0;
@@ -959,11 +973,52 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
   while (NB > 1 && nchunks / NB < 128) --NB;
   tp.dev_nb = 0;
   const OrgFields of = tls_org; tls_org = OrgFields{};       // one-shot
-  if (NB == 1 || g_profile)
-    return conv_tend_impl(tls_work, nchunks, ncol, t, q, u, v, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac,
-                          cld, ztodt, ptend_s, ptend_q, ptend_u, ptend_v, mcon, cme, pflx, zdu, rliq, rice, jctop,
-                          jcbot, prec, snow, ql, rprd, evapcdp, flxprec, flxsnow, dlf, mu, md, du, eu, ed, dp, dsubcld,
-                          jt, maxg, ideep, lengath, cape, stream, nullptr, of.org, of.orgt, of.org2d);
+  if (NB == 1 || g_profile) {
+    auto direct = [&](Workspace& ws, void* on) {
+      return conv_tend_impl(ws, nchunks, ncol, t, q, u, v, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac,
+                            cld, ztodt, ptend_s, ptend_q, ptend_u, ptend_v, mcon, cme, pflx, zdu, rliq, rice, jctop,
+                            jcbot, prec, snow, ql, rprd, evapcdp, flxprec, flxsnow, dlf, mu, md, du, eu, ed, dp,
+                            dsubcld, jt, maxg, ideep, lengath, cape, on, nullptr, of.org, of.orgt, of.org2d);
+    };
+    static const bool use_graph = !(getenv("ZM_DEV_GRAPH") && atoi(getenv("ZM_DEV_GRAPH")) == 0);
+    if (g_profile || !use_graph) { tls_graph.clear(); return direct(tls_work, stream); }
+    Workspace& ws = tls_work;
+    TendGraph& G = tls_graph;
+    double zt = ztodt; const void* ztbits; std::memcpy(&ztbits, &zt, sizeof ztbits);
+    std::vector<const void*> key = {ncol, t, q, u, v, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac, cld,
+        ptend_s, ptend_q, ptend_u, ptend_v, mcon, cme, pflx, zdu, rliq, rice, jctop, jcbot, prec, snow, ql, rprd,
+        evapcdp, flxprec, flxsnow, dlf, mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, lengath, cape,
+        of.org, of.orgt, of.org2d, ztbits, (const void*)(size_t)nchunks, (const void*)(size_t)g_epoch,
+        (const void*)ws.dbuf, (const void*)ws.dcap};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (key == G.key) {
+      if (!G.exec) {                                   // second identical call: capture on the library's own stream
+        cudaGraph_t graph = nullptr;
+        const long long l0 = tls_launches;
+        bool ok = ws.stream && cudaStreamBeginCapture(ws.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          const int rc = direct(ws, (void*)ws.stream);
+          const cudaError_t ee = cudaStreamEndCapture(ws.stream, &graph);
+          ok = rc == 0 && ee == cudaSuccess && graph && cudaGraphInstantiate(&G.exec, graph, 0) == cudaSuccess;
+          if (graph) cudaGraphDestroy(graph);
+        }
+        G.launches = tls_launches - l0;
+        tls_launches = l0;                             // captured launches did not run
+        if (!ok) { cudaGetLastError(); G.clear(); return direct(ws, stream); }
+      }
+      CK(cudaGraphLaunch(G.exec, s));
+      tls_launches += G.launches;
+      return 0;
+    }
+    G.clear();
+    const int rc = direct(ws, stream);                 // first call with these arguments: run, remember
+    if (rc == 0) {
+      G.key = key;
+      G.key[G.key.size() - 2] = (const void*)ws.dbuf;  // the arena may have been (re)allocated by this call
+      G.key[G.key.size() - 1] = (const void*)ws.dcap;
+    }
+    return rc;
+  }
   if (tp.init(NB)) return -100;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t pc = g_params.pcols, L = g_params.pver, s2 = pc * L, s2p = pc * (L + 1), s1 = pc;
