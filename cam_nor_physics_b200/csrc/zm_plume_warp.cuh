@@ -35,9 +35,7 @@ enum PlumeArr {
   A_QDS = A_HSAT     // hsat: last read by the hu recurrence coefficients
 };
 
-#ifndef PL_WARPS
-#define PL_WARPS 4      // warps (columns) per block
-#endif
+#define PL_WARPS 4      // most warps (columns) a block may hold; the launch picks 1..PL_WARPS, see plume_warps_per_block
 
 // Per-warp shared-memory work arrays [array][level]; the leading dimension is a compile-time constant
 // (32/64/128-level builds) so that S(A_X, k) is base + immediate + k instead of a multiply per access.
@@ -579,7 +577,22 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
 
 // leading dimension of the per-warp arrays for a given level count (levels 0..pver+1 are addressed)
 inline int plume_ld(int pver) { return pver <= 32 ? 34 : (pver <= 64 ? 66 : 130); }
-inline size_t plume_smem_bytes(int pver) { return (size_t)PL_WARPS * A_COUNT * plume_ld(pver) * sizeof(double); }
+// Warps per block: shared memory bounds the residency of these kernels, and what is left over after the last
+// whole block is wasted -- pick the block size that leaves the most warps resident per SM (227 KB, 1 KB reserved
+// per block).  L32: 4 warps x 5 blocks = 20 warps; L58/L64: 1 warp x 10 blocks (4-warp blocks would hold 8).
+inline int plume_warps_per_block(int pver) {
+  const size_t per_warp = (size_t)A_COUNT * plume_ld(pver) * sizeof(double), sm = 227 * 1024;
+  int best = 1; size_t best_res = 0;
+  for (int w = PL_WARPS; w >= 1; --w) {
+    const size_t blocks = sm / (w * per_warp + 1024);
+    const size_t res = (blocks > 32 ? 32 : blocks) * w;
+    if (res > best_res) { best_res = res; best = w; }
+  }
+  return best;
+}
+inline size_t plume_smem_bytes(int pver) {
+  return (size_t)plume_warps_per_block(pver) * A_COUNT * plume_ld(pver) * sizeof(double);
+}
 
 // ---- pass-1 plume: diagnose the pass-2 test-parcel entrainment rate (zm_conv.F90:1047-1078) ---
 template <int LD>
@@ -587,7 +600,7 @@ __global__ void __launch_bounds__(32 * PL_WARPS)
 k_cldprp_pass1_w(ConvrIn in, ConvrWork w) {
   extern __shared__ double sm_pl[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int gw = blockIdx.x * PL_WARPS + wib;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + wib;
   if (gw >= w.count[0]) return;
   const int col = w.wl1[gw];
   const int pcols = P.pcols, pver = P.pver, msg = P.msg;
@@ -620,7 +633,7 @@ __global__ void __launch_bounds__(32 * PL_WARPS)
 k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
   extern __shared__ double sm_pl[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int gw = blockIdx.x * PL_WARPS + wib;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + wib;
   if (gw >= w.count[1]) return;
   const int col = w.wl2[2 * gw], slot = w.wl2[2 * gw + 1];
   const int pcols = P.pcols, pver = P.pver, pverp = P.pverp, msg = P.msg;

@@ -205,7 +205,8 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   const int nblk_cols = (int)((ncolpad + TB - 1) / TB);
   const size_t smem = (size_t)(pver + 2) * TB * sizeof(double);
   const int nwarpblk = (int)(((size_t)in.nchunks * 32 + 127) / 128);
-  const int nblk_pl = (int)((ncolpad + PL_WARPS - 1) / PL_WARPS);     // one warp per convective column
+  const int pl_warps = plume_warps_per_block(pver);
+  const int nblk_pl = (int)((ncolpad + pl_warps - 1) / pl_warps);     // one warp per convective column
   const size_t smem_pl = plume_smem_bytes(pver);
   // plume kernels are built for 32/64/128-level leading dimensions (compile-time shared-memory strides)
   const int pl_ld = plume_ld(pver);
@@ -233,7 +234,7 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   tick(ws, s, "buoyan_dilute_pass1");
   k_trigger<0><<<nwarpblk, 128, 0, s>>>(in, o, w); ++tls_launches;
   tick(ws, s, "trigger_pass1");
-  k_cld1<<<nblk_pl, 32 * PL_WARPS, smem_pl, s>>>(in, w);
+  k_cld1<<<nblk_pl, 32 * pl_warps, smem_pl, s>>>(in, w);
   ++tls_launches;
   tick(ws, s, "cldprp_pass1");
   if (org_on) k_buoyan_dilute<2, true><<<nblk_cols, TB, smem, s>>>(in, w);
@@ -242,7 +243,7 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   tick(ws, s, "buoyan_dilute_pass2");
   k_trigger<1><<<nwarpblk, 128, 0, s>>>(in, o, w); ++tls_launches;
   tick(ws, s, "trigger_final");
-  k_plm<<<nblk_pl, 32 * PL_WARPS, smem_pl, s>>>(in, o, w);
+  k_plm<<<nblk_pl, 32 * pl_warps, smem_pl, s>>>(in, o, w);
   ++tls_launches;
   tick(ws, s, "plume_closure_q1q2");
   CK(cudaGetLastError());
