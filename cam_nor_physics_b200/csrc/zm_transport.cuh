@@ -181,9 +181,15 @@ __global__ void k_momtran_init(MomArgs a) {
 // Expression order is the reference's everywhere, so results are bit-identical to the serial code.
 // (Earlier versions ran one thread per column: 0.26 ms of dependent divisions for 19k columns.)
 #define MOM_WARPS 4
-enum MomArr { M_MU = 0, M_MD, M_DU, M_EU, M_ED, M_DP, M_C, M_CHAT = M_C + 2, M_PGU = M_CHAT + 2, M_PGD = M_PGU + 2,
-              M_CONU = M_PGD + 2, M_COND = M_CONU + 2, M_MF = M_COND + 2, M_WF = M_MF + 2, M_T23 = M_WF + 2,
-              M_U2 = M_T23 + 2, M_U3 = M_U2 + 2, M_MUP = M_U3 + 2, M_RMUP, M_RMD, M_NARR };
+// shared-memory arrays of one column.  Recurrence coefficients are stored per chain (0: updraft u, 1: updraft v,
+// 2: downdraft u, 3: downdraft v) or per direction (0: up, 1: down) so that one lane can run one chain with
+// the same instructions as its neighbours:  val = use ? ((A*prev + B1) + B2) / D : default
+enum MomArr { M_MU = 0, M_MD, M_ED, M_DP, M_C, M_CHAT = M_C + 2, M_PGU = M_CHAT + 2, M_PGD = M_PGU + 2,
+              M_CONU = M_PGD + 2, M_COND = M_CONU + 2,      // = "chain value" arrays M_CONU + chain
+              M_MF = M_COND + 2, M_WF = M_MF + 2,
+              M_B1 = M_WF + 2, M_B2 = M_B1 + 4,             // per chain
+              M_A = M_B2 + 4, M_D = M_A + 2, M_R = M_D + 2, M_USE = M_R + 2,   // per direction
+              M_NARR = M_USE + 2 };
 __host__ __device__ inline size_t momtran_smem_bytes(int pver) {
   return (size_t)MOM_WARPS * M_NARR * (pver + 2) * sizeof(double);
 }
@@ -208,8 +214,7 @@ k_momtran_t(MomArgs a) {
   // ---- stage the column ----
   PAR {
     const size_t g = cidx(c, k - 1, gi, pver);
-    SA(M_MU, k) = a.mu[g]; SA(M_MD, k) = a.md[g]; SA(M_DU, k) = a.du[g];
-    SA(M_EU, k) = a.eu[g]; SA(M_ED, k) = a.ed[g]; SA(M_DP, k) = a.dp[g];
+    SA(M_MU, k) = a.mu[g]; SA(M_MD, k) = a.md[g]; SA(M_ED, k) = a.ed[g]; SA(M_DP, k) = a.dp[g];
 #pragma unroll
     for (int m = 0; m < 2; ++m) SA(M_C + m, k) = a.domom[m] ? a.q[QI(m, k)] : 0.0;
   }
@@ -220,13 +225,16 @@ k_momtran_t(MomArgs a) {
     const int km1 = max(1, k - 1), kp1 = min(pver, k + 1);
     const double mu_k = SA(M_MU, k), md_k = SA(M_MD, k), dp_k = SA(M_DP, k), dp_km1 = SA(M_DP, km1);
     const double mu_kp1 = SA(M_MU, kp1), md_kp1 = SA(M_MD, kp1);
-    const double mup_k = mu_k + SA(M_DU, k) * dp_k;
-    SA(M_MUP, k) = mup_k;
-    // refined reciprocals of the two divisors of the recurrences: q = x*r; q += r*(x - b*q) in the sequential
-    // loop is then the IEEE quotient x/b (the compiler's own fast-path division with the reciprocal hoisted
-    // out of the dependent chain); only used where |b| > mbsth
-    SA(M_RMUP, k) = rcp_hot(mup_k);
-    SA(M_RMD, k) = rcp_hot(md_k);
+    const size_t g = cidx(c, k - 1, gi, pver);
+    const double eu_k = a.eu[g];
+    const double mup_k = mu_k + a.du[g] * dp_k;
+    // Divisors of the two recurrences with their refined reciprocals: q = x*r; q += r*(x - b*q) in the sequential
+    // loop is the IEEE quotient x/b (the compiler's own fast-path division with the reciprocal hoisted out of
+    // the dependent chain); only used where the reference divides (|b| > mbsth).
+    SA(M_D, k) = mup_k;      SA(M_R, k) = rcp_hot(mup_k);     SA(M_USE, k) = (mup_k > mbsth) ? 1.0 : 0.0;
+    SA(M_D + 1, k) = md_k;   SA(M_R + 1, k) = rcp_hot(md_k);  SA(M_USE + 1, k) = (md_k < -mbsth) ? 1.0 : 0.0;
+    SA(M_A, k) = mu_kp1;                                       // mu(kk+1) of the updraft step at level kk = k
+    SA(M_A + 1, k) = SA(M_MD, km1);                            // md(k-1) of the downdraft step at level k
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
       const double c_k = SA(M_C + m, k), c_km1 = SA(M_C + m, km1), c_kp1 = SA(M_C + m, kp1);
@@ -243,7 +251,8 @@ k_momtran_t(MomArgs a) {
       const double chat = 0.5 * (c_k + c_km1);
       SA(M_CHAT + m, k) = chat; SA(M_CONU + m, k) = chat; SA(M_COND + m, k) = chat;
       SA(M_PGU + m, k) = pgu; SA(M_PGD + m, k) = pgd;
-      SA(M_T23 + m, k) = SA(M_EU, k) * c_k * dp_k;            // eu*cnst*dp of level k (updraft recurrence)
+      SA(M_B1 + m, k) = eu_k * c_k * dp_k;                    // updraft: eu*cnst*dp ...
+      SA(M_B2 + m, k) = pgu * dp_k;                           // ... + pgu*dp (zm_conv.F90:2538, 2563)
     }
   }
   __syncwarp();
@@ -251,41 +260,33 @@ k_momtran_t(MomArgs a) {
     const int km1 = max(1, k - 1);
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-      SA(M_U2 + m, k) = SA(M_ED, km1) * SA(M_C + m, km1) * SA(M_DP, km1);
-      SA(M_U3 + m, k) = SA(M_PGD + m, km1) * SA(M_DP, km1);
+      // downdraft: - ed(k-1)*cnst(k-1)*dp(k-1) - pgd(k-1)*dp(k-1), stored negated (x - y == x + (-y))
+      SA(M_B1 + 2 + m, k) = -(SA(M_ED, km1) * SA(M_C + m, km1) * SA(M_DP, km1));
+      SA(M_B2 + 2 + m, k) = -(SA(M_PGD + m, km1) * SA(M_DP, km1));
     }
   }
   __syncwarp();
-  // ---- the two recurrences, both components, one loop (all lanes redundantly: same instruction count as one) ----
-  if (a.domom[0] || a.domom[1]) {
-    double conu_n[2] = {0.0, 0.0}, cond_p[2] = {SA(M_COND, 1), SA(M_COND + 1, 1)};
+  // ---- the recurrences: lane & 3 picks the chain (updraft u, updraft v, downdraft u, downdraft v), every chain
+  // runs the same instruction stream (other lanes repeat one of the four).  Updraft (zm_conv.F90:2536-2575):
+  // level kk = pver - n, conu = (mu(kk+1)*conu(kk+1) + eu*c*dp + pgu*dp)/mupdudp, without the first product at
+  // kk = pver.  Downdraft (2579-2589): level k = n + 2, cond = (md(k-1)*cond(k-1) - ed*c*dp - pgd*dp)/md(k); at
+  // k = 2 the reference's operator precedence (2554) makes it (-ed*c*dp) - (pgd*dp)/md(2).
+  {
+    const int chain = lane & 3, dir = chain >> 1, m = chain & 1;
+    const bool on = a.domom[m] != 0;
+    double prev = dir ? SA(M_COND + m, 1) : 0.0;
     for (int n = 0; n < pver; ++n) {
-      const int kk = pver - n;                                 // updraft level, bottom-up
-      const int k = n + 2;                                     // downdraft level, top-down (2..pver)
-      const double mup = SA(M_MUP, kk), rmup = SA(M_RMUP, kk), mu_kkp1 = SA(M_MU, min(pver, kk + 1));
-      const double md_k = (k <= pver) ? SA(M_MD, k) : 0.0, md_km1 = (k <= pver) ? SA(M_MD, k - 1) : 0.0;
-      const double rmd = (k <= pver) ? SA(M_RMD, k) : 0.0;
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        // zm_conv.F90:2536-2575
-        double conu = SA(M_CONU + m, kk);
-        if (mup > mbsth) {
-          const double pgudp = SA(M_PGU + m, kk) * SA(M_DP, kk);
-          if (kk == pver) conu = zmm::div_rcp(+SA(M_T23 + m, kk) + pgudp, mup, rmup);
-          else            conu = zmm::div_rcp(mu_kkp1 * conu_n[m] + SA(M_T23 + m, kk) + pgudp, mup, rmup);
-        }
-        conu_n[m] = conu;
-        if (lane == 0) SA(M_CONU + m, kk) = conu;
-        // zm_conv.F90:2554 (operator precedence as written) and 2579-2589
-        if (k <= pver) {
-          double cond = SA(M_COND + m, k);
-          if (md_k < -mbsth) {
-            if (k == 2) cond = (-SA(M_U2 + m, k)) - zmm::div_rcp(SA(M_U3 + m, k), md_k, rmd);
-            else        cond = zmm::div_rcp(md_km1 * cond_p[m] - SA(M_U2 + m, k) - SA(M_U3 + m, k), md_k, rmd);
-          }
-          cond_p[m] = cond;
-          if (lane == 0) SA(M_COND + m, k) = cond;
-        }
+      const int lev = dir ? n + 2 : pver - n;
+      if (lev <= pver && on) {
+        const double b1 = SA(M_B1 + chain, lev), b2 = SA(M_B2 + chain, lev);
+        const double dd = SA(M_D + dir, lev), rr = SA(M_R + dir, lev);
+        const bool first = (n == 0);                   // updraft at pver: no flux from below; downdraft at 2: :2554
+        const double num = first ? (dir ? b2 : b1 + b2) : (SA(M_A + dir, lev) * prev + b1) + b2;
+        const double q = zmm::div_rcp(num, dd, rr);
+        double val = (first && dir) ? b1 + q : q;
+        if (SA(M_USE + dir, lev) == 0.0) val = SA(M_CONU + chain, lev);     // keeps chat
+        prev = val;
+        if (lane < 4) SA(M_CONU + chain, lev) = val;
       }
     }
   }
