@@ -403,6 +403,7 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
       S(A_W2, k) = dz * S(A_DU, k);
       S(A_W3, k) = dz * S(A_CU, k);
       S(A_W4, k) = 1.0 + dz * c0mask;
+      S(A_W5, k) = rcp_hot(1.0 + dz * c0mask);          // divisor's refined reciprocal: off the serial chain
     }
   }
   WSYNC();
@@ -413,7 +414,7 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
         double ql = 0.0;
         if (S(A_MU, k) > 0.0) {
           const double ql1 = S(A_W1, k) * (S(A_MU, k + 1) * qlp - S(A_W2, k) * qlp + S(A_W3, k));
-          ql = ql1 / S(A_W4, k);
+          ql = zmm::div_rcp(ql1, S(A_W4, k), S(A_W5, k));    // == ql1 / (1 + dz*c0mask)
         }
         S(A_QL, k) = ql;
         totpcp = totpcp + S(A_DZ, k) * (S(A_CU, k) - S(A_DU, k) * qlp);
@@ -482,6 +483,7 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
       if (k >= jt) {
         S(A_W1, k) = S(A_DZ, k - 1) * S(A_ED, k - 1) * S(A_HMN, k - 1);
         S(A_W2, k) = fmin2(S(A_MD, k), -small);
+        S(A_W3, k) = rcp_hot(fmin2(S(A_MD, k), -small));
       }
     }
     WSYNC();
@@ -489,7 +491,7 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
       const int k0 = max(jt, msg + 1);
       double hdp = S(A_HD, k0 - 1);
       for (int k = k0; k <= pver; ++k) {
-        hdp = (S(A_MD, k - 1) * hdp - S(A_W1, k)) / S(A_W2, k);
+        hdp = zmm::div_rcp(S(A_MD, k - 1) * hdp - S(A_W1, k), S(A_W2, k), S(A_W3, k));
         S(A_HD, k) = hdp;
       }
     }
@@ -531,13 +533,14 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
         S(A_EVP, k) = ev;
         S(A_W1, k) = ((1.0 - dcol * (S(A_TD, k) - tmelt)) * rl / ((1.0 + cpvir * qd) * cp) * ev - ed * S(A_S, k)) * dz;
         S(A_W2, k) = fmin2(S(A_MD, k + 1), -small);
+        S(A_W4, k) = rcp_hot(fmin2(S(A_MD, k + 1), -small));
         S(A_W3, k) = dz * ed * S(A_Q, k);
       }
     }
     WSYNC();
     double sdp = S(A_SD, k0);
     for (int k = k0; k < jb; ++k) {
-      sdp = (S(A_W1, k) + S(A_MD, k) * sdp) / S(A_W2, k);
+      sdp = zmm::div_rcp(S(A_W1, k) + S(A_MD, k) * sdp, S(A_W2, k), S(A_W4, k));
       S(A_SD, k + 1) = sdp;
       totevp = totevp - S(A_W3, k);
     }
