@@ -67,6 +67,7 @@ def test_thermo_scalars_match_oracle(built):
     (1000, 0.6, 32, {}),                        # ragged: last chunk has 8 of 16 columns
     (320, 0.0, 32, {}),                         # no convection anywhere (lengath = 0 in every chunk)
     (2048, 0.6, 58, {"lparcel_pbl": 1}),        # L58 with the PBL-mixed launch parcel (BASELINE config 5 setup)
+    (512, 0.6, 72, {}),                         # > 64 levels: the 128-level instantiation of the plume kernels
     (1024, 0.7, 32, {"num_cin": 3}),            # several negative-buoyancy regions allowed
     (1024, 0.7, 32, {"no_deep_pbl": 1}),
     (1024, 0.7, 32, {"masterproc": 0, "dmpdz": -0.5e-3}),   # tentrm quirk (zm_conv.F90:213)
@@ -418,3 +419,19 @@ def test_device_resident_step_graph_replay(built):
     for k in ["lengath", "ideep", "ptend_s", "ptend_q", "ptend_u", "prec", "mcon"]:
         assert_same({k: dev.out[k].cpu().numpy(), "lengath": dev.out["lengath"].cpu().numpy()}, ref2, [k], 16,
                     exact=True, what="device step after input change")
+
+
+@pytest.mark.parametrize("pver,over", [(58, {"lparcel_pbl": 1}), (72, {}), (24, {})])
+def test_zm_conv_tend_other_level_counts(built, pver, over):
+    """The whole zm_conv_tend sequence (zm_convr + physics_update + zm_conv_evap + momtran) at level counts where
+    a lane owns more than one level (L58, L72) or fewer lanes than a warp are busy (L24)."""
+    Z = init_cuda(16, pver, **over)
+    o, _, rc = get_oracle("pm", 16, pver, **over)
+    assert rc == 0
+    ch = S.make_chunks(16 * 40 - 3, pver, 16, p_conv=0.6)
+    ref = o.conv_tend_batch(ch)
+    assert ref["rc"] == 0
+    out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
+    assert_same(out, ref, TEND_KEYS, 16, exact=True, what=f"zm_conv_tend L{pver}")
+    assert out["lengath"].sum() > 0
+    init_cuda(16, 32)
