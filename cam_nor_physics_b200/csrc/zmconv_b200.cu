@@ -354,8 +354,9 @@ int convtran_launch(Workspace& ws, cudaStream_t s, TranArgs a, const int* doconv
   k_chunk_bounds<<<(a.nchunks * 32 + 127) / 128, 128, 0, s>>>(a.nchunks, a.jt, a.mx, a.lengath, ktm, kbm, slots, count);
   ++tls_launches;
   k_convtran_zero<<<a.nchunks * a.nactive, 128, 0, s>>>(a); ++tls_launches;
-  dim3 blk(32, 4);
-  dim3 grd((ncolpad + 31) / 32, (a.nactive + 3) / 4);
+  const int cpb = convtran_cnst_per_block(pver);
+  dim3 blk(32, cpb);
+  dim3 grd((a.nactive + cpb - 1) / cpb, (ncolpad + 31) / 32);       // x: constituent groups, y: column groups
   k_convtran_t<<<grd, blk, 0, s>>>(a);
   ++tls_launches;
   CK(cudaGetLastError());
