@@ -129,7 +129,14 @@ int zm_convtran_batch_dev(int nchunks, const int* doconvtran, const double* q, i
  * State in: t,q(wv),u,v,pmid,pint,pdel,zm,zi,phis + pblh,tpert,landfrac,cld(pbuf 'CLD').
  * Out: ptend_all%s,q(:,:,1),u,v; the dummy outputs mcon,cme,pflx,zdu,rliq,rice,jctop,jcbot; and the
  * pbuf fields the reference fills (prec_dp, snow_dp, icwmrdp=ql, rprddp=rprd, nevapr_dpcu=evapcdp,
- * DP_FLXPRC/SNW, dlfzm, ZM_MU..ZM_IDEEP) + cape + lengath. */
+ * DP_FLXPRC/SNW, dlfzm, ZM_MU..ZM_IDEEP) + cape + lengath.
+ *
+ * Execution (environment variables, read per call):
+ *   host-pointer variant: the batch is pipelined over ZM_TEND_SUBBATCHES (1..8, default 8) sub-batches of whole
+ *     chunks so that host->device copies, kernels and device->host copies overlap; results do not depend on it.
+ *   _dev variant: from the third call with an identical argument list on, the step is replayed as a CUDA graph on
+ *     `stream` (ZM_DEV_GRAPH=0 disables); ZM_DEV_SUBBATCHES (default 1) optionally splits the step over the
+ *     library's own prioritised streams, joined back into `stream`. */
 int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
                        const double* v, const double* pmid, const double* pint, const double* pdel,
                        const double* zm, const double* zi, const double* phis, const double* pblh,
