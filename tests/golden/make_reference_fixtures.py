@@ -1,0 +1,261 @@
+"""Generates tests/golden/reftext_*.npz: outputs of the REFERENCE'S OWN SOURCE TEXT for seeded inputs.
+
+physics/zm_conv.F90 is read from /root/reference (this container only), every routine on the hot path is translated
+mechanically to Python by fortran_exec.py (statement by statement; nothing is re-derived by hand) and executed:
+zm_convi, zm_convr (-> buoyan_dilute, parcel_dilute, entropy, enthalpy, ientropy, ienthalpy, qsat_hPa, cldprp,
+closure, q1q2_pjr, buoyan for cam3), zm_conv_evap, momtran, convtran.  Inputs, namelist values and outputs are stored;
+tests/test_oracle.py::test_oracle_equals_reference_source_text compares the CPU oracle with them bit for bit (glibc
+libm flavour), tests/test_gpu_parity.py compares the CUDA library within the north-star tolerance.
+
+The externals that are NOT part of the reference tree (wv_saturation::qsat_water / qsat, cloud_fraction::cldfrc_fice,
+physconst values, constituents::cnst_get_type_byind) are supplied here in Python with the formulas SURVEY.md 8c
+lists -- those stay unpinned (there is no reference text for them).
+
+usage:  python tests/golden/make_reference_fixtures.py        (needs /root/reference; ~1 minute)
+"""
+import math
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import fortran_exec as F                      # noqa: E402
+from cam_nor_physics_b200 import soundings as S   # noqa: E402
+
+SRC = "/root/reference/physics/zm_conv.F90"
+ROUTINES = ["zm_convi", "qsat_hpa", "entropy", "enthalpy", "ientropy", "ienthalpy", "parcel_dilute", "buoyan_dilute",
+            "buoyan", "cldprp", "closure", "q1q2_pjr", "zm_convr", "zm_conv_evap", "momtran", "convtran"]
+
+
+# ---- externals (not in the reference tree) -----------------------------------------------------
+def physconst():
+    boltz, avogad = 1.38065e-23, 6.02214e26
+    rgas = avogad * boltz
+    mwdair, mwwv = 28.966, 18.016
+    c = dict(cpair=1.00464e3, epsilo=mwwv / mwdair, gravit=9.80616, latice=3.337e5, latvap=2.501e6, tmelt=273.15,
+             rair=rgas / mwdair, cpwv=1.810e3, cpliq=4.188e3, rh2o=rgas / mwwv)
+    c["cpvir"] = c["cpwv"] / c["cpair"] - 1.0
+    c["zvir"] = c["rh2o"] / c["rair"] - 1.0
+    return c
+
+
+def gg_water(t):
+    tb = 373.16
+    return 10.0 ** (-7.90298 * (tb / t - 1.0) + 5.02808 * math.log10(tb / t)
+                    - 1.3816e-7 * (10.0 ** (11.344 * (1.0 - t / tb)) - 1.0)
+                    + 8.1328e-3 * (10.0 ** (-3.49149 * (tb / t - 1.0)) - 1.0) + math.log10(1013.246)) * 100.0
+
+
+def gg_ice(t):
+    t3 = 273.16
+    return 10.0 ** (-9.09718 * (t3 / t - 1.0) - 3.56654 * math.log10(t3 / t) + 0.876793 * (1.0 - t / t3)
+                    + math.log10(6.1071)) * 100.0
+
+
+class Externals:
+    def __init__(self, c):
+        self.c = c
+        tmelt, ttrice = c["tmelt"], 20.0
+        tmin, tmax = 127.16, 375.16
+        n = int(tmax - tmin + 1) + 1
+        self.tmin, self.tmax = tmin, tmax
+        self.estbl = []
+        for i in range(n):
+            t = tmin + i
+            if t < tmelt - ttrice:
+                w = 1.0
+            elif t < tmelt:
+                w = (tmelt - t) / ttrice
+            else:
+                w = 0.0
+            if w >= 1.0:
+                es = gg_ice(t)
+            elif w <= 0.0:
+                es = gg_water(t)
+            else:
+                es = w * gg_ice(t) + (1.0 - w) * gg_water(t)
+            self.estbl.append(es)
+
+    def svp_to_qsat(self, es, p):
+        eps = self.c["epsilo"]
+        if (p - es) <= 0.0:
+            return 1.0
+        return eps * es / (p - (1.0 - eps) * es)
+
+    def qsat_water(self, t, p, es=None, qs=None):
+        e = gg_water(t)
+        q = self.svp_to_qsat(e, p)
+        return min(e, p), q
+
+    def qsat(self, t, p, es, qs, ncol):
+        """wv_saturation::qsat (table version) on (ncol) vectors: es, qs are filled in place.  The caller passes array
+        sections (t(1:ncol,k) ...), which arrive here as 0-based numpy views of the Fortran arrays."""
+        for i in range(ncol):
+            tt = max(min(t[i], self.tmax) - self.tmin, 0.0)
+            j = int(tt)
+            w = tt - math.trunc(tt)
+            e = (1.0 - w) * self.estbl[j] + w * self.estbl[j + 1]
+            qs[i] = self.svp_to_qsat(e, p[i])
+            es[i] = min(e, p[i])
+
+    def cldfrc_fice(self, ncol, t, fice, fsnow):
+        tmelt = self.c["tmelt"]
+        tmax_fice, tmin_fice = tmelt - 10.0, tmelt - 40.0
+        tmax_fsnow, tmin_fsnow = tmelt, tmelt - 5.0
+        for k in range(1, t.shape[1] + 1):
+            for i in range(1, ncol + 1):
+                tt = t[i, k]
+                if tt > tmax_fice:
+                    fice[i, k] = 0.0
+                elif tt < tmin_fice:
+                    fice[i, k] = 1.0
+                else:
+                    fice[i, k] = (tmax_fice - tt) / (tmax_fice - tmin_fice)
+                if tt > tmax_fsnow:
+                    fsnow[i, k] = 0.0
+                elif tt < tmin_fsnow:
+                    fsnow[i, k] = 1.0
+                else:
+                    fsnow[i, k] = (tmax_fsnow - tt) / (tmax_fsnow - tmin_fsnow)
+
+
+def build_module(pcols, pver, masterproc=True, cam3=False, dry_of=None):
+    c = physconst()
+    ext = Externals(c)
+    ns = dict(c)
+    ns.update(pcols=pcols, pver=pver, pverp=pver + 1, masterproc=masterproc, iulog=6,
+              qsat_water=ext.qsat_water, qsat=ext.qsat, cldfrc_fice=ext.cldfrc_fice,
+              _OUTS={"qsat_water": [2, 3]},
+              get_rlat_p=lambda *a: 0.0, get_rlon_p=lambda *a: 0.0,
+              cam_physpkg_is=lambda s: bool(cam3) and s == "cam3",
+              cnst_get_type_byind=(lambda m: "dry" if (dry_of and dry_of[m - 1]) else "wet"))
+    m = F.Module(SRC, ns)
+    m.module_parameters(40, 108)
+    m.load(*ROUTINES)
+    return m, c
+
+
+def FA(a, dtype=float):
+    """numpy [.., nlev, pcols] chunk array -> FArr view indexed (i, k[, m]) like the Fortran dummy."""
+    if a.ndim == 1:
+        return F.FArr(a.shape, dtype=dtype, data=a)
+    return F.FArr(a.T.shape, dtype=dtype, data=a.T)
+
+
+def run_case(name, ncols, pver, p_conv, nl, ncol_used=None, org=False, cam3=False, col0=0, ncnst=6):
+    """One chunk (pcols = 16).  nl: namelist overrides of zm_convi."""
+    pcols = 16
+    L = pver
+    # cam3: zm_convr tests `cin` (zm_conv.F90:909) although buoyan never defines it -- undefined behaviour in the
+    # reference.  Undefined local reals read as 0.0 for that case (what fresh stack memory usually holds, and what
+    # the oracle / CUDA library define); NaN everywhere else, so that no other result can
+    # silently depend on an undefined value.
+    F.FArr.UNDEFINED = 0.0 if cam3 else np.nan
+    ch = S.make_chunks(ncols, L, pcols, p_conv=p_conv, col0=col0)
+    ncol = int(ch.ncol[0]) if ncol_used is None else ncol_used
+    do = [0] + [1, 1, 0, 1, 1, 1, 1][:ncnst - 1]
+    dry = [0] + [0, 1, 0, 1, 0, 1, 0][:ncnst - 1]
+    m, c = build_module(pcols, L, masterproc=nl.get("masterproc", True), cam3=cam3, dry_of=dry)
+    p = dict(limcnv=S.limcnv_for(L), c0_lnd=0.0075, c0_ocn=0.03, ke=5.0e-6, ke_lnd=1.0e-5, momcu=0.7, momcd=0.7,
+             num_cin=1, zm_org=bool(org), microp=False, no_deep_pbl=False, tiedke_add=0.5, capelmt=70.0,
+             dmpdz=-1.0e-3, lparcel_pbl=False, tau=3600.0)
+    p.update({k: v for k, v in nl.items() if k != "masterproc"})
+    m.ns["zm_convi"](p["limcnv"], p["c0_lnd"], p["c0_ocn"], p["ke"], p["ke_lnd"], p["momcu"], p["momcd"], p["num_cin"],
+                     p["zm_org"], p["microp"], p["no_deep_pbl"], p["tiedke_add"], p["capelmt"], p["dmpdz"],
+                     p["lparcel_pbl"], p["tau"])
+    z2 = lambda n=L: np.zeros((n, pcols))      # noqa: E731
+    z1 = lambda: np.zeros(pcols)               # noqa: E731
+    o = dict(prec=z1(), jctop=z1(), jcbot=z1(), qtnd=z2(), heat=z2(), mcon=z2(L + 1), cme=z2(), cape=z1(), eurt=z2(),
+             dlf=z2(), pflx=z2(L + 1), zdu=z2(), rprd=z2(), mu=z2(), md=z2(), du=z2(), eu=z2(), ed=z2(), dp=z2(),
+             dsubcld=z1(), jt=np.zeros(pcols, np.int64), maxg=np.zeros(pcols, np.int64),
+             ideep=np.zeros(pcols, np.int64), ql=z2(), rliq=z1(), dif=z2(), dnlf=z2(), dnif=z2(), rice=z1())
+    inp = {k: np.ascontiguousarray(getattr(ch, k)[0]) for k in
+           ("t", "q", "u", "v", "pmid", "pint", "pdel", "zm", "zi", "phis", "pblh", "tpert", "landfrac", "cld")}
+    orgf = orgt = org2d = None
+    if org:
+        rng = np.random.default_rng(17)
+        orgf = np.maximum(rng.uniform(-0.3, 1.0, (L, pcols)), 0.0)
+        orgt, org2d = np.full((L, pcols), 7.0), np.zeros((L, pcols))
+    delt = 0.5 * float(ch.ztodt)
+    A = lambda k, dt=float: FA(o[k], dt)       # noqa: E731
+    lengath, = m.ns["zm_convr"](
+        1, ncol, FA(inp["t"]), FA(inp["q"]), A("prec"), A("jctop"), A("jcbot"), FA(inp["pblh"]), FA(inp["zm"]),
+        FA(inp["phis"]), FA(inp["zi"]), A("qtnd"), A("heat"), FA(inp["pmid"]), FA(inp["pint"]), FA(inp["pdel"]), delt,
+        A("mcon"), A("cme"), A("cape"), A("eurt"), FA(inp["tpert"]), A("dlf"), A("pflx"), A("zdu"), A("rprd"), A("mu"),
+        A("md"), A("du"), A("eu"), A("ed"), A("dp"), A("dsubcld"), A("jt", int), A("maxg", int), A("ideep", int), None,
+        A("ql"), A("rliq"), FA(inp["landfrac"]), FA(orgf) if org else None, FA(orgt) if org else None,
+        FA(org2d) if org else None, A("dif"), A("dnlf"), A("dnif"), F.FStruct(), F.FStruct(), A("rice"))
+    fx = {"nl_" + k: np.asarray(v) for k, v in p.items()}
+    fx.update(nl_masterproc=np.asarray(bool(nl.get("masterproc", True))), nl_cam3=np.asarray(bool(cam3)),
+              pcols=np.asarray(pcols), pver=np.asarray(L), ncol=np.asarray(ncol), ztodt=np.asarray(float(ch.ztodt)))
+    fx.update({"in_" + k: v for k, v in inp.items()})
+    fx.update({"convr_" + k: v for k, v in o.items()})
+    fx["convr_lengath"] = np.asarray(int(lengath))
+    if org:
+        fx.update(in_org=orgf, convr_orgt=orgt, convr_org2d=org2d)
+
+    # ---- zm_conv_evap on the state after physics_update (zm_conv_intr.F90:733-769; glue computed here) ----
+    t1 = inp["t"] + o["heat"] * float(ch.ztodt) / c["cpair"]
+    q1 = np.maximum(inp["q"] + o["qtnd"] * float(ch.ztodt), 1e-12)
+    ev = dict(tend_s=z2(), tend_s_snwprd=z2(), tend_s_snwevmlt=z2(), tend_q=z2(), prec=o["prec"].copy(), snow=z1(),
+              ntprprd=z2(), ntsnprd=z2(), flxprec=z2(L + 1), flxsnow=z2(L + 1))
+    E = lambda k: FA(ev[k])                    # noqa: E731
+    m.ns["zm_conv_evap"](ncol, 1, FA(t1), FA(inp["pmid"]), FA(inp["pdel"]), FA(q1), FA(inp["landfrac"]), E("tend_s"),
+                         E("tend_s_snwprd"), E("tend_s_snwevmlt"), E("tend_q"), FA(o["rprd"]), FA(inp["cld"]),
+                         float(ch.ztodt), E("prec"), E("snow"), E("ntprprd"), E("ntsnprd"), E("flxprec"), E("flxsnow"))
+    fx.update(evap_in_t=t1, evap_in_q=q1)
+    fx.update({"evap_" + k: v for k, v in ev.items()})
+
+    # ---- momtran (zm_conv_intr.F90:811-826) ----
+    winds = np.stack([inp["u"], inp["v"]], axis=0)                     # [2][L][pcols] == Fortran (pcols,pver,2)
+    mo = dict(dqdt=np.zeros((2, L, pcols)), pguall=np.zeros((2, L, pcols)), pgdall=np.zeros((2, L, pcols)),
+              icwu=np.zeros((2, L, pcols)), icwd=np.zeros((2, L, pcols)), seten=z2())
+    F3 = lambda a: F.FArr(a.T.shape, data=a.T)     # noqa: E731
+    domom = F.FArr((2,), dtype=int, data=np.array([1, 1]))
+    m.ns["momtran"](1, ncol, domom, F3(winds), 2, FA(o["mu"]), FA(o["md"]), FA(o["du"]), FA(o["eu"]), FA(o["ed"]),
+                    FA(o["dp"]), FA(o["dsubcld"]), FA(o["jt"], int), FA(o["maxg"], int), FA(o["ideep"], int), 1,
+                    int(lengath), 0, F3(mo["dqdt"]), F3(mo["pguall"]), F3(mo["pgdall"]), F3(mo["icwu"]), F3(mo["icwd"]),
+                    float(ch.ztodt), FA(mo["seten"]))
+    fx.update({"momtran_" + k: v for k, v in mo.items()})
+
+    # ---- convtran (zm_conv_intr.F90:1014-1024 dpdry gather; :875 / :1020 call) ----
+    qtr, fracis, pdeldry = S.make_tracers(ch, ncnst)
+    qtr, fracis, pdeldry = qtr[0], fracis[0], pdeldry[0]
+    dpdry = np.zeros((L, pcols))
+    n = int(lengath)
+    idx = o["ideep"][:n] - 1
+    dpdry[:, :n] = pdeldry[:, idx] / 100.0
+    dq = np.full((ncnst, L, pcols), 7.25)
+    m.ns["convtran"](1, F.FArr((ncnst,), dtype=int, data=np.array(do)), F3(qtr), ncnst, FA(o["mu"]), FA(o["md"]),
+                     FA(o["du"]), FA(o["eu"]), FA(o["ed"]), FA(o["dp"]), FA(o["dsubcld"]), FA(o["jt"], int),
+                     FA(o["maxg"], int), FA(o["ideep"], int), 1, int(lengath), 0, F3(fracis), F3(dq), FA(dpdry),
+                     float(ch.ztodt))
+    fx.update(convtran_in_q=qtr, convtran_in_fracis=fracis, convtran_in_dpdry=dpdry,
+              convtran_in_doconvtran=np.array(do, np.int32), convtran_in_is_dry=np.array(dry, np.int32),
+              convtran_dqdt=dq)
+    path = os.path.join(HERE, "reftext_%s.npz" % name)
+    np.savez_compressed(path, **fx)
+    print("%-22s ncol %2d  lengath %2d  prec mean %.3e  -> %s (%d KB)" %
+          (name, ncol, int(lengath), float(o["prec"].mean()), os.path.basename(path), os.path.getsize(path) // 1024))
+
+
+CASES = [
+    dict(name="config1_L32", ncols=16, pver=32, p_conv=1.0, nl={}),
+    dict(name="mixed_ragged_L32", ncols=11, pver=32, p_conv=0.5, nl={}, col0=4000),
+    dict(name="parcel_pbl_L58", ncols=16, pver=58, p_conv=0.7, nl={"lparcel_pbl": True}, col0=900),
+    dict(name="num_cin3_L32", ncols=16, pver=32, p_conv=0.7, nl={"num_cin": 3}, col0=1700),
+    dict(name="no_deep_pbl_L32", ncols=16, pver=32, p_conv=0.7, nl={"no_deep_pbl": True}, col0=2500),
+    dict(name="not_master_L32", ncols=16, pver=32, p_conv=0.7, nl={"masterproc": False, "dmpdz": -0.5e-3}, col0=3300),
+    dict(name="zm_org_L32", ncols=16, pver=32, p_conv=0.7, nl={}, org=True, col0=5100),
+    dict(name="cam3_L32", ncols=16, pver=32, p_conv=0.7, nl={"num_cin": 5}, cam3=True, col0=6000),
+]
+
+if __name__ == "__main__":
+    only = sys.argv[1:]
+    for cs in CASES:
+        if only and cs["name"] not in only:
+            continue
+        run_case(**cs)

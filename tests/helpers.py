@@ -86,3 +86,27 @@ def dpdry_gathered(ch, ref, pdeldry):
         idx = ref["ideep"][c][:n] - 1
         dpdry[c][:, :n] = pdeldry[c][:, idx] / 100.0
     return dpdry
+
+
+# ---- fixtures produced by executing the reference's own source text (tests/golden/make_reference_fixtures.py) ----
+REFTEXT_CASES = ["config1_L32", "mixed_ragged_L32", "parcel_pbl_L58", "num_cin3_L32", "no_deep_pbl_L32",
+                 "not_master_L32", "zm_org_L32", "cam3_L32"]
+REFTEXT_CONVR = ["prec", "jctop", "jcbot", "qtnd", "heat", "mcon", "cme", "cape", "eurt", "dlf", "pflx", "zdu", "rprd",
+                 "mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg", "ideep", "ql", "rliq", "dif", "dnlf",
+                 "dnif", "rice"]
+
+
+def reftext_overrides(g):
+    """zm_params overrides that reproduce the namelist of a reference-text fixture."""
+    ov = dict(num_cin=int(g["nl_num_cin"]), no_deep_pbl=int(bool(g["nl_no_deep_pbl"])),
+              lparcel_pbl=int(bool(g["nl_lparcel_pbl"])), masterproc=int(bool(g["nl_masterproc"])),
+              dmpdz=float(g["nl_dmpdz"]), zm_org=int(bool(g["nl_zm_org"])), cam3=int(bool(g["nl_cam3"])),
+              tiedke_add=float(g["nl_tiedke_add"]), capelmt=float(g["nl_capelmt"]), tau=float(g["nl_tau"]),
+              c0_lnd=float(g["nl_c0_lnd"]), c0_ocn=float(g["nl_c0_ocn"]), ke=float(g["nl_ke"]),
+              ke_lnd=float(g["nl_ke_lnd"]), momcu=float(g["nl_momcu"]), momcd=float(g["nl_momcd"]))
+    return ov
+
+
+def reftext_gather(a, n):
+    """Gathered outputs are defined for the first lengath entries only."""
+    return a[..., :n]

@@ -10,7 +10,7 @@ import pytest
 
 from cam_nor_physics_b200 import soundings as S
 from helpers import (get_oracle, init_cuda, state_of, assert_same, cuda_convr, dpdry_gathered, CONVR_KEYS,
-                     TEND_KEYS, near_threshold_columns)
+                     TEND_KEYS, near_threshold_columns, REFTEXT_CASES, REFTEXT_CONVR, reftext_overrides, RTOL, ATOL)
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -434,4 +434,61 @@ def test_zm_conv_tend_other_level_counts(built, pver, over):
     out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
     assert_same(out, ref, TEND_KEYS, 16, exact=True, what=f"zm_conv_tend L{pver}")
     assert out["lengath"].sum() > 0
+    init_cuda(16, 32)
+
+
+@pytest.mark.parametrize("case", REFTEXT_CASES)
+def test_cuda_vs_reference_source_text(built, case):
+    """CUDA library against the outputs of the reference's own Fortran text (tests/golden/reftext_*.npz, produced by
+    tests/golden/make_reference_fixtures.py): integer outputs exact, r8 outputs within the north-star tolerance
+    (the fixtures were computed with glibc log/exp/pow, the library uses its portable math)."""
+    g = np.load(os.path.join(GOLD, "reftext_%s.npz" % case))
+    pc, L, ncol = int(g["pcols"]), int(g["pver"]), int(g["ncol"])
+    Z = init_cuda(pc, L, **reftext_overrides(g))
+    ztodt = float(g["ztodt"])
+    ncols = np.array([ncol], np.int32)
+    I = lambda k: g["in_" + k][None]          # noqa: E731
+    org = g["in_org"][None] if "in_org" in g.files else None
+    r = Z.zm_convr(ncols, I("t"), I("q"), I("pblh"), I("zm"), I("phis"), I("zi"), I("pmid"), I("pint"), I("pdel"),
+                   0.5 * ztodt, I("tpert"), I("landfrac"), org=org)
+    n = int(g["convr_lengath"])
+    assert len(near_threshold_columns(g["convr_cape"])) == 0
+    assert int(r["lengath"][0]) == n
+    bad = []
+    for k in REFTEXT_CONVR:
+        a, b = r[k][0], g["convr_" + k]
+        if k in ("mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg"):
+            a, b = a[..., :n], b[..., :n]
+        if k in ("jctop", "jcbot"):
+            a, b = a[..., :ncol], b[..., :ncol]
+        if k in ("ideep", "jt", "maxg", "jctop", "jcbot"):
+            ok = np.array_equal(np.asarray(a, float), np.asarray(b, float))
+        else:
+            ok = np.allclose(a, b, rtol=RTOL, atol=ATOL)
+        if not ok:
+            bad.append(k)
+    assert not bad, "zm_convr vs reference text: %s" % bad
+    if org is not None:
+        assert np.all(r["orgt"] == 0.0)
+        assert np.allclose(r["org2d"][0][:, :ncol], g["convr_org2d"][:, :ncol], rtol=RTOL, atol=ATOL)
+    # downstream routines on the REFERENCE's zm_convr outputs
+    G = lambda k: g["convr_" + k][None]       # noqa: E731
+    ev = Z.zm_conv_evap(ncols, g["evap_in_t"][None], I("pmid"), I("pdel"), g["evap_in_q"][None], I("landfrac"),
+                        G("rprd"), I("cld"), ztodt, G("prec"))
+    for k in ("tend_s", "tend_s_snwprd", "tend_s_snwevmlt", "tend_q", "prec", "snow", "ntprprd", "ntsnprd", "flxprec",
+              "flxsnow"):
+        assert np.allclose(ev[k][0][..., :ncol], g["evap_" + k][..., :ncol], rtol=RTOL, atol=ATOL), ("evap", k)
+    winds = np.stack([g["in_u"], g["in_v"]], axis=0)[None]
+    ilen = np.array([n], np.int32)
+    mo = Z.momtran(ncols, [1, 1], winds, G("mu"), G("md"), G("du"), G("eu"), G("ed"), G("dp"), G("dsubcld"),
+                   G("jt").astype(np.int32), G("maxg").astype(np.int32), G("ideep").astype(np.int32), ilen, ztodt)
+    for k in ("dqdt", "pguall", "pgdall", "icwu", "icwd", "seten"):
+        assert np.allclose(mo[k][0][..., :ncol], g["momtran_" + k][..., :ncol], rtol=RTOL, atol=1e-13), ("momtran", k)
+    do, dry = g["convtran_in_doconvtran"], g["convtran_in_is_dry"]
+    dq = Z.convtran(do, g["convtran_in_q"][None], G("mu"), G("md"), G("du"), G("eu"), G("ed"), G("dp"), G("dsubcld"),
+                    G("jt").astype(np.int32), G("maxg").astype(np.int32), G("ideep").astype(np.int32), ilen,
+                    g["convtran_in_fracis"][None], g["convtran_in_dpdry"][None], ztodt, dry)
+    for mth in range(1, len(do)):
+        if do[mth]:
+            assert np.allclose(dq[0, mth], g["convtran_dqdt"][mth], rtol=RTOL, atol=1e-30), ("convtran", mth)
     init_cuda(16, 32)

@@ -6,7 +6,7 @@ import pytest
 
 from cam_nor_physics_b200 import soundings as S
 from helpers import (get_oracle, state_of, assert_same, TEND_KEYS, CONVR_KEYS, masked, dpdry_gathered,
-                     near_threshold_columns, RTOL, ATOL)
+                     near_threshold_columns, RTOL, ATOL, REFTEXT_CASES, REFTEXT_CONVR, reftext_overrides)
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -189,3 +189,62 @@ def test_zm_org_branches_oracle():
     assert t1["rc"] == 0
     tgt = np.minimum(1.0, np.maximum(0.0, 5e7 * np.abs(t1["evapcdp"]) - org / 10800.0))
     assert np.allclose(t1["orgt"], (tgt - org) / ch.ztodt, rtol=1e-13, atol=1e-18)
+
+
+@pytest.mark.parametrize("case", REFTEXT_CASES)
+def test_oracle_equals_reference_source_text(case):
+    """THE PIN: tests/golden/reftext_*.npz hold what the reference's own Fortran text computes (translated
+    statement by statement and executed by tests/golden/fortran_exec.py, see make_reference_fixtures.py) for
+    zm_convr (with buoyan_dilute / parcel_dilute / Brent inversions / cldprp / closure / q1q2_pjr inside),
+    zm_conv_evap, momtran and convtran.  The oracle built with glibc libm must reproduce every output BIT FOR BIT."""
+    g = np.load(os.path.join(GOLD, "reftext_%s.npz" % case))
+    pc, L, ncol = int(g["pcols"]), int(g["pver"]), int(g["ncol"])
+    o, p, rc = get_oracle("libm", pc, L, **reftext_overrides(g))
+    assert rc == 0 and int(g["nl_limcnv"]) == p.limcnv
+    ztodt = float(g["ztodt"])
+
+    class Ch:      # one chunk in the layout convr_batch expects
+        nchunks, ztodt = 1, float(g["ztodt"])
+    ch = Ch()
+    ch.ncol = np.array([ncol], np.int32)
+    for k in ("t", "q", "pmid", "pint", "pdel", "zm", "zi", "phis", "pblh", "tpert", "landfrac"):
+        setattr(ch, k, g["in_" + k][None])
+    org = g["in_org"][None] if "in_org" in g.files else None
+    r = o.convr_batch(ch, org=org)
+    assert r["rc"] == 0
+    n = int(g["convr_lengath"])
+    assert int(r["lengath"][0]) == n
+    bad = []
+    for k in REFTEXT_CONVR:
+        a, b = r[k][0], g["convr_" + k]
+        if k in ("mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg"):
+            a, b = a[..., :n], b[..., :n]
+        if k in ("jctop", "jcbot", "ideep", "jt", "maxg"):     # defined for i <= ncol / gathered entries
+            a, b = a[..., :ncol] if k in ("jctop", "jcbot") else a, b[..., :ncol] if k in ("jctop", "jcbot") else b
+        if not np.array_equal(np.asarray(a, float), np.asarray(b, float)):
+            bad.append(k)
+    if org is not None:
+        assert np.array_equal(r["orgt"][0], g["convr_orgt"]) and np.array_equal(r["org2d"][0][:, :ncol], g["convr_org2d"][:, :ncol])
+    assert not bad, "zm_convr outputs differ from the reference text: %s" % bad
+    # zm_conv_evap
+    ev = o.conv_evap(ncol, g["evap_in_t"], g["in_pmid"], g["in_pdel"], g["evap_in_q"], g["in_landfrac"],
+                     g["convr_rprd"], g["in_cld"], ztodt, g["convr_prec"])
+    for k in ("tend_s", "tend_s_snwprd", "tend_s_snwevmlt", "tend_q", "prec", "snow", "ntprprd", "ntsnprd", "flxprec",
+              "flxsnow"):
+        assert np.array_equal(ev[k][..., :ncol], g["evap_" + k][..., :ncol]), ("zm_conv_evap", k)
+    # momtran
+    winds = np.stack([g["in_u"], g["in_v"]], axis=0)
+    mo = o.momtran(ncol, [1, 1], winds, g["convr_mu"], g["convr_md"], g["convr_du"], g["convr_eu"], g["convr_ed"],
+                   g["convr_dp"], g["convr_dsubcld"], g["convr_jt"], g["convr_maxg"], g["convr_ideep"], n, ztodt)
+    for k in ("dqdt", "pguall", "pgdall", "icwu", "icwd", "seten"):
+        assert np.array_equal(mo[k][..., :ncol], g["momtran_" + k][..., :ncol]), ("momtran", k)
+    # convtran
+    do, dry = g["convtran_in_doconvtran"], g["convtran_in_is_dry"]
+    dq = o.convtran(do, g["convtran_in_q"], g["convr_mu"], g["convr_md"], g["convr_du"], g["convr_eu"], g["convr_ed"],
+                    g["convr_dp"], g["convr_dsubcld"], g["convr_jt"], g["convr_maxg"], g["convr_ideep"], n,
+                    g["convtran_in_fracis"], g["convtran_in_dpdry"], ztodt, dry)
+    for mth in range(1, len(do)):
+        if do[mth]:
+            assert np.array_equal(dq[mth], g["convtran_dqdt"][mth]), ("convtran", mth)
+        else:
+            assert np.all(g["convtran_dqdt"][mth] == 7.25)      # the reference leaves inactive constituents untouched
