@@ -138,8 +138,12 @@ INTRINSICS = {
     "abs": "abs", "min": "min", "max": "max", "log": "_log", "log10": "_log10", "exp": "math.exp",
     "sqrt": "math.sqrt", "sign": "_sign", "merge": "_merge", "nint": "_nint", "int": "int", "real": "_real",
     "mod": "math.fmod", "dble": "float", "minval": "_minval", "maxval": "_maxval", "present": "_present",
-    "sum": "_sum", "size": "_size", "allocated": "_present", "associated": "_present",
+    "sum": "_sum", "size": "_size", "allocated": "_present", "associated": "_present", "_arr": "_arr",
 }
+
+
+def _arr(*a):
+    return list(a)
 
 
 def _minval(a):
@@ -347,6 +351,7 @@ DOTOPS = {".and.": " and ", ".or.": " or ", ".not.": " not ", ".true.": " True "
 
 
 def tokenize(s):
+    s = s.replace("(/", " _arr( ").replace("/)", " ) ")      # array constructor
     pos, out = 0, []
     while pos < len(s):
         m = TOKEN.match(s, pos)
@@ -528,10 +533,11 @@ def parse_routine(llines):
 class Module:
     """Holds translated routines and the exec namespace."""
 
-    def __init__(self, src_path, namespace):
+    def __init__(self, src_path, namespace, lenient=False):
+        self.lenient = lenient
         self.lines = read_source(src_path)
         self.ns = dict(namespace)
-        self.ns.update(dict(math=math, np=np, FArr=FArr, FStruct=FStruct, _ipow=_ipow, _sign=_sign, _merge=_merge, _nint=_nint, _frange=_frange,
+        self.ns.update(dict(math=math, np=np, FArr=FArr, FStruct=FStruct, _ipow=_ipow, _arr=_arr, r8=8, _sign=_sign, _merge=_merge, _nint=_nint, _frange=_frange,
                             _log=_log, _log10=_log10, _real=_real, FortranStop=FortranStop, _minval=_minval,
                             _maxval=_maxval, _present=_present, _sum=_sum, _size=_size))
         self.routines = {}
@@ -609,7 +615,10 @@ class Module:
                 ind = self._stmt(text, tr, emit_ind=lambda s, i=None: out.append("    " * (ind if i is None else i) + s),
                                  ind=ind, loops=loops, ret=ret, routine=r)
             except Exception as e:       # noqa: BLE001
-                raise type(e)("%s (line %d of the reference: %s)" % (e, n, text)) from e
+                if not self.lenient or re.match(r"^(end\s*(if|do)|else|if\s*\(.*\)\s*then|do\s)", text):
+                    raise type(e)("%s (line %d of the reference: %s)" % (e, n, text)) from e
+                # lenient mode: a statement outside the supported subset is kept as a run-time stop, never skipped
+                out.append("    " * ind + "raise FortranStop(%r)" % ("untranslated statement (line %d): %s" % (n, text)))
         out.append("    " + ret)
         src = "\n".join(out)
         self.py[r.name] = src
@@ -715,7 +724,7 @@ class Module:
             if name == "endrun":
                 emit("raise FortranStop(%s)" % (fix_div(tr.expr(argtxt)) or "'endrun'"))
                 return ind
-            if name in SKIP_CALLS:
+            if name in SKIP_CALLS and name not in self.ns:       # history output etc.; a shim in the namespace captures it
                 emit("pass")
                 return ind
             args = [fix_div(tr.expr(a)) for a in _split_top(argtxt)]

@@ -242,6 +242,84 @@ def run_case(name, ncols, pver, p_conv, nl, ncol_used=None, org=False, cam3=Fals
           (name, ncol, int(lengath), float(o["prec"].mean()), os.path.basename(path), os.path.getsize(path) // 1024))
 
 
+def run_geopotential():
+    """geopotential_t (physics/geopotential.F90:153) for the FV ('LR') and the Eulerian branch."""
+    pcols, L = 16, 32
+    F.FArr.UNDEFINED = np.nan
+    ch = S.make_chunks(13, L, pcols, p_conv=0.5, col0=7000)
+    c = physconst()
+    fx = {}
+    for lr in (1, 0):
+        m = F.Module("/root/reference/physics/geopotential.F90",
+                     dict(pcols=pcols, pver=L, pverp=L + 1, dycore_is=(lambda s, lr=lr: s == "LR" if lr else s == "EUL")),
+                     lenient=True)       # the MPAS/SE branch uses module data that is not in scope: kept as run-time stops
+        m.load("geopotential_t")
+        pint, pmid, pdel, t, q = (np.ascontiguousarray(getattr(ch, k)[0]) for k in ("pint", "pmid", "pdel", "t", "q"))
+        piln, pmln, rpdel = np.log(pint), np.log(pmid), 1.0 / pdel
+        rair = np.full((L, pcols), c["rair"]); zvir = np.full((L, pcols), c["zvir"])
+        zi, zm = np.zeros((L + 1, pcols)), np.zeros((L, pcols))
+        q3 = q[None]                                            # (pcols,pver,1)
+        m.ns["geopotential_t"](FA(piln), FA(pmln), FA(pint), FA(pmid), FA(pdel), FA(rpdel), FA(t),
+                               F.FArr(q3.T.shape, data=q3.T), FA(rair), c["gravit"], FA(zvir), FA(zi), FA(zm), 13)
+        fx.update({"in_piln": piln, "in_pint": pint, "in_pmid": pmid, "in_pdel": pdel, "in_rpdel": rpdel, "in_t": t,
+                   "in_q": q, "in_rair": rair, "in_zvir": zvir, "gravit": np.asarray(c["gravit"]), "ncol": np.asarray(13),
+                   "zi_lr%d" % lr: zi, "zm_lr%d" % lr: zm})
+    path = os.path.join(HERE, "reftext_geopotential_t.npz")
+    np.savez_compressed(path, **fx)
+    print("geopotential_t -> %s (%d KB)" % (os.path.basename(path), os.path.getsize(path) // 1024))
+
+
+def run_convect_diagnostics():
+    """convect_diagnostics_calc (physics/convect_diagnostics.F90:115-249), shallow_scheme = 'CLUBB_SGS'.
+    The physics buffer is a dict of FArr; pbuf_get_field / pbuf_set_field are two-line shims."""
+    pcols, L, ncol = 16, 32, 14
+    F.FArr.UNDEFINED = np.nan
+    rng = np.random.default_rng(23)
+    ch = S.make_chunks(ncol, L, pcols, p_conv=0.5, col0=8000)
+    names = ["icwmrsh", "rprddp", "rprdsh", "nevapr_shcu", "cldtop", "cldbot", "prec_sh", "snow_sh", "cmfmc_sh", "rprdtot"]
+    idx = {n + "_idx": i for i, n in enumerate(names)}
+    arr2 = lambda n=L: rng.uniform(0.0, 1.0e-3, (n, pcols))      # noqa: E731
+    pb = {"icwmrsh": arr2(), "rprddp": arr2(), "rprdsh": arr2(), "nevapr_shcu": arr2(),
+          "cldtop": np.floor(rng.uniform(3, L - 4, pcols)), "cldbot": np.floor(rng.uniform(L - 6, L + 1, pcols)),
+          "prec_sh": rng.uniform(0, 1e-7, pcols), "snow_sh": rng.uniform(0, 1e-8, pcols), "cmfmc_sh": arr2(L + 1),
+          "rprdtot": np.zeros((L, pcols))}
+    pb["cldbot"][::5] = 1.0                                       # exercises `if (cnb == 1) cnb = cnt`
+    fx = {"pb_in_" + k: v.copy() for k, v in pb.items()}
+    pbuf = {idx[k + "_idx"]: FA(v) for k, v in pb.items()}
+
+    hist = {}
+
+    def pbuf_get_field(pbuf, i, ptr=None):
+        return (pbuf[i],)
+
+    def outfld(name, field, idim, lchnk):
+        hist[name] = np.array(field.a, copy=True)
+
+    def pbuf_set_field(pbuf, i, val, start=None, kount=None):
+        a = pbuf[i]
+        a.a[start[0] - 1:start[0] - 1 + kount[0], start[1] - 1:start[1] - 1 + kount[1]] = val
+
+    ns = dict(idx)
+    ns.update(pcols=pcols, pver=L, pverp=L + 1, shallow_scheme="CLUBB_SGS", pbuf_get_field=pbuf_get_field,
+              pbuf_set_field=pbuf_set_field, outfld=outfld, _OUTS={"pbuf_get_field": [2]})
+    m = F.Module("/root/reference/physics/convect_diagnostics.F90", ns, lenient=True)
+    m.load("convect_diagnostics_calc")
+    state = F.FStruct()
+    state.lchnk, state.ncol = 1, ncol
+    pmid = np.ascontiguousarray(ch.pmid[0])
+    state.pmid = FA(pmid)
+    cmfmc, qc, rliq = arr2(L + 1), arr2(), rng.uniform(0, 1e-7, pcols)
+    qc2, rliq2 = np.ones((L, pcols)), np.ones(pcols)
+    fx.update(in_cmfmc=cmfmc.copy(), in_qc=qc.copy(), in_rliq=rliq.copy(), in_pmid=pmid, ncol=np.asarray(ncol))
+    m.ns["convect_diagnostics_calc"](1800.0, FA(cmfmc), FA(qc), FA(qc2), FA(rliq), FA(rliq2), state, pbuf)
+    fx.update(out_cmfmc=cmfmc, out_qc=qc, out_qc2=qc2, out_rliq=rliq, out_rliq2=rliq2,
+              out_pcnt=hist["PCLDTOP"], out_pcnb=hist["PCLDBOT"])
+    fx.update({"pb_out_" + k: v for k, v in pb.items()})
+    path = os.path.join(HERE, "reftext_convect_diagnostics.npz")
+    np.savez_compressed(path, **fx)
+    print("convect_diagnostics_calc -> %s (%d KB)" % (os.path.basename(path), os.path.getsize(path) // 1024))
+
+
 CASES = [
     dict(name="config1_L32", ncols=16, pver=32, p_conv=1.0, nl={}),
     dict(name="mixed_ragged_L32", ncols=11, pver=32, p_conv=0.5, nl={}, col0=4000),
@@ -259,3 +337,7 @@ if __name__ == "__main__":
         if only and cs["name"] not in only:
             continue
         run_case(**cs)
+    if not only or "geopotential_t" in only:
+        run_geopotential()
+    if not only or "convect_diagnostics" in only:
+        run_convect_diagnostics()

@@ -248,3 +248,30 @@ def test_oracle_equals_reference_source_text(case):
             assert np.array_equal(dq[mth], g["convtran_dqdt"][mth]), ("convtran", mth)
         else:
             assert np.all(g["convtran_dqdt"][mth] == 7.25)      # the reference leaves inactive constituents untouched
+
+
+def test_oracle_geopotential_t_equals_reference_source_text():
+    """geopotential_t (physics/geopotential.F90:153-247): reference text executed through the translator."""
+    g = np.load(os.path.join(GOLD, "reftext_geopotential_t.npz"))
+    o, _, _ = get_oracle("libm", 16, 32)
+    for lr in (1, 0):
+        zi, zm = o.geopotential_t(int(g["ncol"]), lr, g["in_piln"], g["in_pint"], g["in_pmid"], g["in_pdel"], g["in_rpdel"],
+                                  g["in_t"], g["in_q"], g["in_rair"], float(g["gravit"]), g["in_zvir"])
+        n = int(g["ncol"])
+        assert np.array_equal(zi[:, :n], g["zi_lr%d" % lr][:, :n]) and np.array_equal(zm[:, :n], g["zm_lr%d" % lr][:, :n]), lr
+
+
+def test_oracle_convect_diagnostics_equals_reference_source_text():
+    """convect_diagnostics_calc (physics/convect_diagnostics.F90:115-249), CLUBB_SGS branch."""
+    g = np.load(os.path.join(GOLD, "reftext_convect_diagnostics.npz"))
+    o, _, _ = get_oracle("libm", 16, 32)
+    n = int(g["ncol"])
+    r = o.convect_diagnostics(n, g["in_cmfmc"], g["in_qc"], g["in_rliq"], g["in_pmid"], g["pb_in_rprddp"],
+                              g["pb_in_cldtop"], g["pb_in_cldbot"])
+    assert np.array_equal(r["cmfmc"][:, :n], g["out_cmfmc"][:, :n]) and np.array_equal(r["qc"][:, :n], g["out_qc"][:, :n])
+    assert np.array_equal(r["rliq"][:n], g["out_rliq"][:n])
+    assert np.all(r["qc2"] == 0.0) and np.all(g["out_qc2"] == 0.0) and np.all(r["rliq2"] == 0.0)
+    assert np.array_equal(r["cnt"][:n], g["pb_out_cldtop"][:n]) and np.array_equal(r["cnb"][:n], g["pb_out_cldbot"][:n])
+    assert np.array_equal(r["pcnt"][:n], g["out_pcnt"][:n]) and np.array_equal(r["pcnb"][:n], g["out_pcnb"][:n])
+    assert np.array_equal(r["rprdtot"][:, :n], g["pb_out_rprdtot"][:, :n])
+    assert np.all(r["cmfmc2"] == 0.0) and np.all(r["rprdsh"] == 0.0)
