@@ -4,15 +4,22 @@
 // (pcols,pver) column-major arrays, same k-outer / i-inner loop nests, same statement and
 // operation order (gfortran -O2 semantics: left-to-right, parentheses honoured, integer
 // powers as multiply chains, no FMA contraction => build with -ffp-contract=off).
-// Every routine cites the reference lines it follows.  The zm_org and zmconv_microp
-// branches are out of scope and are not restated.
+// Every routine cites the reference lines it follows.  The zmconv_microp branches are out of
+// scope (zm_microphysics is not in the reference tree) and are not restated; zm_org is.
 //
-// PARITY PINNING: the reference ships no tests/golden vectors and cannot be compiled here
-// (no Fortran compiler; 12 absent modules), so this oracle is pinned only by (a) review
-// against the cited lines, (b) the property tests in tests/test_oracle_properties.py
-// (inverse identities, water closure, zero-tendency rows), and (c) cross-agreement of two
-// math back-ends (glibc libm vs the portable zm_math.h).  External-module arithmetic is
-// defined in zm_externals.hpp ("parity unpinned", see there).
+// PARITY PINNING: the reference ships no tests/golden vectors and cannot be compiled here (no
+// Fortran compiler; 12 absent modules).  It is pinned instead against the reference's OWN SOURCE
+// TEXT: tests/golden/fortran_exec.py translates physics/zm_conv.F90 statement by statement into
+// Python and executes it (zm_convi, zm_convr with buoyan_dilute / buoyan / parcel_dilute / entropy /
+// enthalpy / ientropy / ienthalpy / qsat_hPa / cldprp / closure / q1q2_pjr inside, zm_conv_evap,
+// momtran, convtran; also geopotential_t and convect_diagnostics_calc); the committed fixtures
+// tests/golden/reftext_*.npz hold its outputs for 8 configurations, and the glibc-libm build of this
+// oracle reproduces every one of them BIT FOR BIT (tests/test_oracle.py::
+// test_oracle_equals_reference_source_text).  What stays unpinned: the arithmetic of modules that
+// are not in the reference tree (zm_externals.hpp: qsat_water, the qsat table, cldfrc_fice,
+// physconst values, qneg3) and the few glue statements of zm_conv_intr.F90 restated in
+// conv_tend_chunk.  Further checks: property tests (inverse identities, water closure, zero-tendency
+// rows) and cross-agreement of two math back-ends (glibc libm vs the portable zm_math.h).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library.
