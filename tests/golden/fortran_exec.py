@@ -135,7 +135,7 @@ def _fdiv(a, b):
 
 
 INTRINSICS = {
-    "abs": "abs", "min": "min", "max": "max", "log": "_log", "log10": "_log10", "exp": "math.exp",
+    "abs": "_abs", "min": "_min", "max": "_max", "log": "_log", "log10": "_log10", "exp": "math.exp",
     "sqrt": "math.sqrt", "sign": "_sign", "merge": "_merge", "nint": "_nint", "int": "int", "real": "_real",
     "mod": "math.fmod", "dble": "float", "minval": "_minval", "maxval": "_maxval", "present": "_present",
     "sum": "_sum", "size": "_size", "allocated": "_present", "associated": "_present", "_arr": "_arr",
@@ -144,6 +144,32 @@ INTRINSICS = {
 
 def _arr(*a):
     return list(a)
+
+
+def _elementwise(args):
+    return any(isinstance(a, np.ndarray) for a in args)
+
+
+def _min(*a):
+    if _elementwise(a):
+        r = a[0]
+        for b in a[1:]:
+            r = np.minimum(r, b)
+        return r
+    return min(a)
+
+
+def _max(*a):
+    if _elementwise(a):
+        r = a[0]
+        for b in a[1:]:
+            r = np.maximum(r, b)
+        return r
+    return max(a)
+
+
+def _abs(x):
+    return np.abs(x) if isinstance(x, np.ndarray) else abs(x)
 
 
 def _minval(a):
@@ -537,7 +563,8 @@ class Module:
         self.lenient = lenient
         self.lines = read_source(src_path)
         self.ns = dict(namespace)
-        self.ns.update(dict(math=math, np=np, FArr=FArr, FStruct=FStruct, _ipow=_ipow, _arr=_arr, r8=8, _sign=_sign, _merge=_merge, _nint=_nint, _frange=_frange,
+        self.ns.update(dict(math=math, np=np, FArr=FArr, FStruct=FStruct, _ipow=_ipow, _arr=_arr, r8=8, _min=_min, _max=_max,
+                            _abs=_abs, _sign=_sign, _merge=_merge, _nint=_nint, _frange=_frange,
                             _log=_log, _log10=_log10, _real=_real, FortranStop=FortranStop, _minval=_minval,
                             _maxval=_maxval, _present=_present, _sum=_sum, _size=_size))
         self.routines = {}
@@ -556,6 +583,19 @@ class Module:
             for v in d:
                 if v.init is not None:
                     self.ns[v.name] = eval(fix_div(tr.expr(v.init)), self.ns)
+
+    def run_lines(self, first_line, last_line, arrays=()):
+        """Translate and execute the executable statements of source lines [first_line, last_line] in the module
+        namespace (used for isolated glue statements of routines that are not translated as a whole)."""
+        arr = set(arrays) | {k for k, v in self.ns.items() if isinstance(v, FArr)}
+        tr = Translator(arr, {k for k, v in self.ns.items() if callable(v) and not k.startswith("_")})
+        out, ind, loops = [], 0, []
+        for n, text in logical_lines(self.lines[first_line - 1:last_line]):
+            ind = self._stmt(text, tr, emit_ind=lambda s, i=None: out.append("    " * (ind if i is None else i) + s),
+                             ind=ind, loops=loops, ret="pass", routine=None)
+        src = "\n".join(out)
+        exec(compile(src, "<fortran:lines %d-%d>" % (first_line, last_line), "exec"), self.ns)
+        return src
 
     def load(self, *names):
         for name in names:

@@ -26,6 +26,8 @@ import fortran_exec as F                      # noqa: E402
 from cam_nor_physics_b200 import soundings as S   # noqa: E402
 
 SRC = "/root/reference/physics/zm_conv.F90"
+INTR = "/root/reference/physics/zm_conv_intr.F90"
+PTYPES = "/root/reference/physics/physics_types.F90"
 ROUTINES = ["zm_convi", "qsat_hpa", "entropy", "enthalpy", "ientropy", "ienthalpy", "parcel_dilute", "buoyan_dilute",
             "buoyan", "cldprp", "closure", "q1q2_pjr", "zm_convr", "zm_conv_evap", "momtran", "convtran"]
 
@@ -197,9 +199,30 @@ def run_case(name, ncols, pver, p_conv, nl, ncol_used=None, org=False, cam3=Fals
     if org:
         fx.update(in_org=orgf, convr_orgt=orgt, convr_org2d=org2d)
 
-    # ---- zm_conv_evap on the state after physics_update (zm_conv_intr.F90:733-769; glue computed here) ----
-    t1 = inp["t"] + o["heat"] * float(ch.ztodt) / c["cpair"]
-    q1 = np.maximum(inp["q"] + o["qtnd"] * float(ch.ztodt), 1e-12)
+    # ---- glue statements of zm_conv_tend, executed from the reference text one statement block at a time ----
+    # mcon unit conversion (zm_conv_intr.F90:693)
+    tmcon = o["mcon"].copy()
+    mi = F.Module(INTR, dict(ncol=ncol, pver=L, pverp=L + 1, gravit=c["gravit"], mcon=FA(tmcon)))
+    mi.run_lines(693, 693)
+    fx["tend_mcon"] = tmcon
+    # physics_update of state1 with zm_convr's ptend (physics_types.F90:321-323 for q, :426-430 for t; the qneg3
+    # clip at qmin(1) = 1e-12 that follows :322 is an external and applied by hand)
+    st, pt = F.FStruct(), F.FStruct()
+    q3, dq3 = inp["q"][None].copy(), o["qtnd"][None].copy()
+    t1 = inp["t"].copy()
+    st.q, pt.q = F.FArr(q3.T.shape, data=q3.T), F.FArr(dq3.T.shape, data=dq3.T)
+    st.t, pt.s = FA(t1), FA(o["heat"])
+    pt.top_level, pt.bot_level = 1, L
+    cpv = np.full((L, pcols), c["cpair"])
+    mp_ = F.Module(PTYPES, dict(ncol=ncol, pver=L, m=1, dt=float(ch.ztodt), state=st, ptend=pt, tend=None,
+                               cpairv_loc=FA(cpv)))
+    mp_.run_lines(321, 323)
+    mp_.run_lines(426, 430)
+    q1 = np.maximum(q3[0], 1e-12)
+    assert np.array_equal(t1[:, :ncol], (inp["t"] + o["heat"] * float(ch.ztodt) / c["cpair"])[:, :ncol])
+    t1[:, ncol:] = inp["t"][:, ncol:]; q1[:, ncol:] = np.maximum(inp["q"][:, ncol:], 1e-12)
+
+    # ---- zm_conv_evap on that state (zm_conv_intr.F90:764-769) ----
     ev = dict(tend_s=z2(), tend_s_snwprd=z2(), tend_s_snwevmlt=z2(), tend_q=z2(), prec=o["prec"].copy(), snow=z1(),
               ntprprd=z2(), ntsnprd=z2(), flxprec=z2(L + 1), flxsnow=z2(L + 1))
     E = lambda k: FA(ev[k])                    # noqa: E731
@@ -208,6 +231,15 @@ def run_case(name, ncols, pver, p_conv, nl, ncol_used=None, org=False, cam3=Fals
                          float(ch.ztodt), E("prec"), E("snow"), E("ntprprd"), E("ntsnprd"), E("flxprec"), E("flxsnow"))
     fx.update(evap_in_t=t1, evap_in_q=q1)
     fx.update({"evap_" + k: v for k, v in ev.items()})
+    if org:
+        # organisation tendency (zm_conv_intr.F90:773-777) from the reference text
+        st2, pt2 = F.FStruct(), F.FStruct()
+        o3, t3 = orgf[None].copy(), np.zeros((1, L, pcols))
+        st2.q, pt2.q = F.FArr(o3.T.shape, data=o3.T), F.FArr(t3.T.shape, data=t3.T)
+        mo_ = F.Module(INTR, dict(ncol=ncol, pver=L, ixorg=1, ztodt=float(ch.ztodt), zmconv_org=True, state=st2,
+                                  ptend_loc=pt2, evapcdp=FA(ev["tend_q"])))
+        mo_.run_lines(773, 777)
+        fx["tend_orgt"] = t3[0]
 
     # ---- momtran (zm_conv_intr.F90:811-826) ----
     winds = np.stack([inp["u"], inp["v"]], axis=0)                     # [2][L][pcols] == Fortran (pcols,pver,2)

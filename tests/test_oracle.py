@@ -248,6 +248,24 @@ def test_oracle_equals_reference_source_text(case):
             assert np.array_equal(dq[mth], g["convtran_dqdt"][mth]), ("convtran", mth)
         else:
             assert np.all(g["convtran_dqdt"][mth] == 7.25)      # the reference leaves inactive constituents untouched
+    # the zm_conv_tend sequence: the oracle's fused driver against the pieces above combined the way zm_conv_intr.F90
+    # does (ptend_all = sum of the three ptend_loc, :736/:803/:833), with the glue statements (:693 mcon units,
+    # physics_update arithmetic, :773-777 organisation tendency) taken from the reference text as well
+    for k in ("u", "v", "cld"):
+        setattr(ch, k, g["in_" + k][None])
+    tr = o.conv_tend_batch(ch, org=org)
+    assert tr["rc"] == 0
+    c = slice(0, ncol)
+    assert np.array_equal(tr["mcon"][0][:, c], g["tend_mcon"][:, c])
+    assert np.array_equal(tr["ptend_s"][0][:, c], ((g["convr_heat"] + g["evap_tend_s"]) + g["momtran_seten"])[:, c])
+    assert np.array_equal(tr["ptend_q"][0][:, c], (g["convr_qtnd"] + g["evap_tend_q"])[:, c])
+    assert np.array_equal(tr["ptend_u"][0][:, c], g["momtran_dqdt"][0][:, c])
+    assert np.array_equal(tr["ptend_v"][0][:, c], g["momtran_dqdt"][1][:, c])
+    for k in ("prec", "snow", "flxprec", "flxsnow"):
+        assert np.array_equal(tr[k][0][..., c], g["evap_" + k][..., c]), k
+    assert np.array_equal(tr["evapcdp"][0][:, c], g["evap_tend_q"][:, c])
+    if org is not None:
+        assert np.array_equal(tr["orgt"][0][:, c], g["tend_orgt"][:, c])
 
 
 def test_oracle_geopotential_t_equals_reference_source_text():
