@@ -352,6 +352,44 @@ def run_convect_diagnostics():
     print("convect_diagnostics_calc -> %s (%d KB)" % (os.path.basename(path), os.path.getsize(path) // 1024))
 
 
+def run_sweep(nchunks=32, col0=20000, p_conv=0.5):
+    """zm_convr of the reference text over many chunks of mixed soundings (default namelist): broad branch coverage.
+    Inputs are NOT stored -- they are soundings.make_chunks(16*nchunks, 32, 16, p_conv, col0=col0), seeded."""
+    pcols, L = 16, 32
+    F.FArr.UNDEFINED = np.nan
+    ch = S.make_chunks(pcols * nchunks - 5, L, pcols, p_conv=p_conv, col0=col0)     # last chunk ragged
+    m, c = build_module(pcols, L)
+    m.ns["zm_convi"](S.limcnv_for(L), 0.0075, 0.03, 5.0e-6, 1.0e-5, 0.7, 0.7, 1, False, False, False, 0.5, 70.0, -1.0e-3,
+                     False, 3600.0)
+    keys2 = ["qtnd", "heat", "cme", "eurt", "dlf", "zdu", "rprd", "mu", "md", "du", "eu", "ed", "dp", "ql", "dif", "dnlf",
+             "dnif"]
+    keys2p = ["mcon", "pflx"]
+    keys1 = ["prec", "jctop", "jcbot", "cape", "dsubcld", "rliq", "rice"]
+    keysi = ["jt", "maxg", "ideep"]
+    out = {k: np.zeros((nchunks, L, pcols)) for k in keys2}
+    out.update({k: np.zeros((nchunks, L + 1, pcols)) for k in keys2p})
+    out.update({k: np.zeros((nchunks, pcols)) for k in keys1})
+    out.update({k: np.zeros((nchunks, pcols), np.int64) for k in keysi})
+    out["lengath"] = np.zeros(nchunks, np.int64)
+    for cc in range(nchunks):
+        I = lambda k: FA(np.ascontiguousarray(getattr(ch, k)[cc]))       # noqa: E731
+        A = lambda k, dt=float: FA(out[k][cc], dt)                        # noqa: E731
+        out["lengath"][cc], = m.ns["zm_convr"](
+            cc + 1, int(ch.ncol[cc]), I("t"), I("q"), A("prec"), A("jctop"), A("jcbot"), I("pblh"), I("zm"), I("phis"),
+            I("zi"), A("qtnd"), A("heat"), I("pmid"), I("pint"), I("pdel"), 0.5 * float(ch.ztodt), A("mcon"), A("cme"),
+            A("cape"), A("eurt"), I("tpert"), A("dlf"), A("pflx"), A("zdu"), A("rprd"), A("mu"), A("md"), A("du"),
+            A("eu"), A("ed"), A("dp"), A("dsubcld"), A("jt", int), A("maxg", int), A("ideep", int), None, A("ql"),
+            A("rliq"), I("landfrac"), None, None, None, A("dif"), A("dnlf"), A("dnif"), F.FStruct(), F.FStruct(),
+            A("rice"))
+    fx = {"convr_" + k: v for k, v in out.items()}
+    fx.update(nchunks=np.asarray(nchunks), col0=np.asarray(col0), p_conv=np.asarray(p_conv),
+              ncols=np.asarray(pcols * nchunks - 5))
+    path = os.path.join(HERE, "reftext_sweep_L32.npz")
+    np.savez_compressed(path, **fx)
+    print("sweep: %d chunks, %d convective columns -> %s (%d KB)" %
+          (nchunks, int(out["lengath"].sum()), os.path.basename(path), os.path.getsize(path) // 1024))
+
+
 CASES = [
     dict(name="config1_L32", ncols=16, pver=32, p_conv=1.0, nl={}),
     dict(name="mixed_ragged_L32", ncols=11, pver=32, p_conv=0.5, nl={}, col0=4000),
@@ -373,3 +411,5 @@ if __name__ == "__main__":
         run_geopotential()
     if not only or "convect_diagnostics" in only:
         run_convect_diagnostics()
+    if not only or "sweep" in only:
+        run_sweep()

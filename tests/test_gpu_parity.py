@@ -492,3 +492,19 @@ def test_cuda_vs_reference_source_text(built, case):
         if do[mth]:
             assert np.allclose(dq[0, mth], g["convtran_dqdt"][mth], rtol=RTOL, atol=1e-30), ("convtran", mth)
     init_cuda(16, 32)
+
+
+def test_cuda_vs_reference_source_text_sweep(built):
+    """507 mixed columns: CUDA zm_convr against the reference text's outputs (integers exact, r8 within tolerance)."""
+    g = np.load(os.path.join(GOLD, "reftext_sweep_L32.npz"))
+    Z = init_cuda(16, 32)
+    ch = S.make_chunks(int(g["ncols"]), 32, 16, p_conv=float(g["p_conv"]), col0=int(g["col0"]))
+    assert len(near_threshold_columns(g["convr_cape"])) == 0
+    out = cuda_convr(Z, ch)
+    ref = {k[6:]: g[k] for k in g.files if k.startswith("convr_")}
+    ref["lengath"] = ref["lengath"].astype(np.int32)
+    m = np.arange(16)[None, :] < ch.ncol[:, None]
+    for k in ("jctop", "jcbot"):
+        out[k] = out[k] * m
+        ref[k] = ref[k] * m
+    assert_same(out, ref, [k for k in REFTEXT_CONVR] + ["lengath"], 16, exact=False, what="CUDA vs reference text (sweep)")

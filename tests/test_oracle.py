@@ -293,3 +293,25 @@ def test_oracle_convect_diagnostics_equals_reference_source_text():
     assert np.array_equal(r["pcnt"][:n], g["out_pcnt"][:n]) and np.array_equal(r["pcnb"][:n], g["out_pcnb"][:n])
     assert np.array_equal(r["rprdtot"][:, :n], g["pb_out_rprdtot"][:, :n])
     assert np.all(r["cmfmc2"] == 0.0) and np.all(r["rprdsh"] == 0.0)
+
+
+def test_oracle_equals_reference_source_text_sweep():
+    """507 columns of mixed soundings (32 chunks, the last one ragged) through the reference text's zm_convr: the
+    glibc-libm oracle must reproduce every output bit for bit (inputs are regenerated from the seeded generator)."""
+    g = np.load(os.path.join(GOLD, "reftext_sweep_L32.npz"))
+    o, _, _ = get_oracle("libm", 16, 32)
+    ch = S.make_chunks(int(g["ncols"]), 32, 16, p_conv=float(g["p_conv"]), col0=int(g["col0"]))
+    r = o.convr_batch(ch)
+    assert r["rc"] == 0
+    assert np.array_equal(r["lengath"], g["convr_lengath"]) and r["lengath"].sum() > 200
+    bad = []
+    for k in REFTEXT_CONVR:
+        a, b = r[k], g["convr_" + k]
+        if k in ("mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg"):
+            a, b = masked(r, k, g["convr_lengath"], 16), masked({k: b}, k, g["convr_lengath"], 16)
+        if k in ("jctop", "jcbot"):
+            m = np.arange(16)[None, :] < ch.ncol[:, None]
+            a, b = a * m, b * m
+        if not np.array_equal(np.asarray(a, float), np.asarray(b, float)):
+            bad.append(k)
+    assert not bad, bad
