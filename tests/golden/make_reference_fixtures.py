@@ -147,9 +147,8 @@ def FA(a, dtype=float):
     return F.FArr(a.T.shape, dtype=dtype, data=a.T)
 
 
-def run_case(name, ncols, pver, p_conv, nl, ncol_used=None, org=False, cam3=False, col0=0, ncnst=6):
-    """One chunk (pcols = 16).  nl: namelist overrides of zm_convi."""
-    pcols = 16
+def run_case(name, ncols, pver, p_conv, nl, ncol_used=None, org=False, cam3=False, col0=0, ncnst=6, pcols=16):
+    """One chunk.  nl: namelist overrides of zm_convi."""
     L = pver
     # cam3: zm_convr tests `cin` (zm_conv.F90:909) although buoyan never defines it -- undefined behaviour in the
     # reference.  Undefined local reals read as 0.0 for that case (what fresh stack memory usually holds, and what
@@ -399,6 +398,13 @@ CASES = [
     dict(name="not_master_L32", ncols=16, pver=32, p_conv=0.7, nl={"masterproc": False, "dmpdz": -0.5e-3}, col0=3300),
     dict(name="zm_org_L32", ncols=16, pver=32, p_conv=0.7, nl={}, org=True, col0=5100),
     dict(name="cam3_L32", ncols=16, pver=32, p_conv=0.7, nl={"num_cin": 5}, cam3=True, col0=6000),
+    dict(name="parcel_pbl_numcin5_L32", ncols=16, pver=32, p_conv=0.9,
+         nl={"lparcel_pbl": True, "num_cin": 5, "tiedke_add": 0.0, "capelmt": 30.0}, col0=9100),
+    dict(name="pcols24_L26", ncols=19, pver=26, p_conv=0.8, nl={}, col0=9900, pcols=24),
+    dict(name="single_column_L32", ncols=1, pver=32, p_conv=1.0, nl={}, col0=10700),
+    dict(name="strong_entrainment_L32", ncols=16, pver=32, p_conv=1.0,
+         nl={"dmpdz": -2.5e-3, "tau": 1800.0, "c0_lnd": 0.0059, "c0_ocn": 0.045, "ke": 1.0e-6, "momcu": 0.4,
+             "momcd": 0.4}, col0=11500),
 ]
 
 if __name__ == "__main__":
