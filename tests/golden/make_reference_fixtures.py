@@ -147,7 +147,8 @@ def FA(a, dtype=float):
     return F.FArr(a.T.shape, dtype=dtype, data=a.T)
 
 
-def run_case(name, ncols, pver, p_conv, nl, ncol_used=None, org=False, cam3=False, col0=0, ncnst=6, pcols=16):
+def run_case(name, ncols, pver, p_conv, nl, ncol_used=None, org=False, cam3=False, col0=0, ncnst=6, pcols=16,
+             transform=None):
     """One chunk.  nl: namelist overrides of zm_convi."""
     L = pver
     # cam3: zm_convr tests `cin` (zm_conv.F90:909) although buoyan never defines it -- undefined behaviour in the
@@ -175,6 +176,8 @@ def run_case(name, ncols, pver, p_conv, nl, ncol_used=None, org=False, cam3=Fals
              ideep=np.zeros(pcols, np.int64), ql=z2(), rliq=z1(), dif=z2(), dnlf=z2(), dnif=z2(), rice=z1())
     inp = {k: np.ascontiguousarray(getattr(ch, k)[0]) for k in
            ("t", "q", "u", "v", "pmid", "pint", "pdel", "zm", "zi", "phis", "pblh", "tpert", "landfrac", "cld")}
+    if transform:                                   # stress cases: unusual soundings (inputs are stored, not regenerated)
+        STRESS[transform](inp, c)
     orgf = orgt = org2d = None
     if org:
         rng = np.random.default_rng(17)
@@ -389,6 +392,34 @@ def run_sweep(nchunks=32, col0=20000, p_conv=0.5):
           (nchunks, int(out["lengath"].sum()), os.path.basename(path), os.path.getsize(path) // 1024))
 
 
+def _st_cold(inp, c):
+    inp["t"] -= 14.0
+    inp["q"] *= 0.42
+
+
+def _st_near_saturated(inp, c):
+    L, pc = inp["t"].shape
+    for k in range(L):
+        for i in range(pc):
+            if inp["pmid"][k, i] > 3.0e4:
+                e = gg_water(inp["t"][k, i])
+                qs = c["epsilo"] * e / (inp["pmid"][k, i] - (1.0 - c["epsilo"]) * e)
+                inp["q"][k, i] = 0.97 * qs
+
+
+def _st_low_pbl_big_tpert(inp, c):
+    inp["pblh"][:] = 60.0
+    inp["tpert"][:] = 3.0
+
+
+def _st_high_pbl(inp, c):
+    inp["pblh"][:] = 3500.0
+    inp["landfrac"][:] = np.linspace(0.0, 1.0, inp["landfrac"].size)
+
+
+STRESS = {"cold": _st_cold, "near_saturated": _st_near_saturated, "low_pbl_big_tpert": _st_low_pbl_big_tpert,
+          "high_pbl": _st_high_pbl}
+
 CASES = [
     dict(name="config1_L32", ncols=16, pver=32, p_conv=1.0, nl={}),
     dict(name="mixed_ragged_L32", ncols=11, pver=32, p_conv=0.5, nl={}, col0=4000),
@@ -405,6 +436,11 @@ CASES = [
     dict(name="strong_entrainment_L32", ncols=16, pver=32, p_conv=1.0,
          nl={"dmpdz": -2.5e-3, "tau": 1800.0, "c0_lnd": 0.0059, "c0_ocn": 0.045, "ke": 1.0e-6, "momcu": 0.4,
              "momcd": 0.4}, col0=11500),
+    dict(name="stress_cold_L32", ncols=16, pver=32, p_conv=1.0, nl={}, col0=12300, transform="cold"),
+    dict(name="stress_near_saturated_L32", ncols=16, pver=32, p_conv=1.0, nl={}, col0=13100, transform="near_saturated"),
+    dict(name="stress_low_pbl_L32", ncols=16, pver=32, p_conv=1.0, nl={}, col0=13900, transform="low_pbl_big_tpert"),
+    dict(name="stress_high_pbl_L32", ncols=16, pver=32, p_conv=1.0, nl={"lparcel_pbl": True}, col0=14700,
+         transform="high_pbl"),
 ]
 
 if __name__ == "__main__":
