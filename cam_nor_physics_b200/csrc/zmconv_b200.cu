@@ -1179,6 +1179,14 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
     CK(cudaEventRecord(tp.final_back[b], tp.d2h_early));
   }
   if (rc == 0) copy_kind(5, 0, nchunks, tp.d2h_early);
+  // the Brent failure counters of all sub-batches ride back on the return stream (it has waited for every
+  // sub-batch): one synchronisation instead of one per sub-batch
+  int fail_cnt[TendPipe::MAXB][4] = {};
+  if (rc == 0)
+    for (int b = 0; b < NB; ++b)
+      if (tp.work[b].last_count &&
+          cudaMemcpyAsync(fail_cnt[b], tp.work[b].last_count, sizeof fail_cnt[b], cudaMemcpyDeviceToHost, tp.d2h_early) != cudaSuccess)
+        rc = -100;
   cudaError_t e1 = cudaStreamSynchronize(tp.d2h_early), e2 = cudaStreamSynchronize(tp.d2h_final),
               e3 = cudaStreamSynchronize(tp.h2d);
   for (int b = 0; b < NB; ++b)
@@ -1190,7 +1198,8 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   }
   int fails = 0;
   for (int b = NB - 1; b >= 0; --b) {        // first failing sub-batch's message wins
-    const int f = read_failures(tp.work[b], tp.work[b].stream);
+    if (fail_cnt[b][2] == 0) continue;
+    const int f = read_failures(tp.work[b], tp.work[b].stream);      // fetches the details and formats the message
     if (f < 0) return f;
     fails += f;
   }
