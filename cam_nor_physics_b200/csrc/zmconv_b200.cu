@@ -111,6 +111,24 @@ struct TendPipe {
     return nb;
   }
   static int first(int b, int nchunks, int nb) { return (int)((long long)nchunks * b / nb); }
+  // Host-pointer pipeline: sub-batch boundaries in sixteenths of the batch.  "ramp" (default for large batches)
+  // starts with two small sub-batches so that the first results reach the return stream early, then grows them
+  // (1,1,2,4,4,4 sixteenths): fewer and larger PCIe copies, while every sub-batch is still computed before the
+  // return stream gets to it.  ZM_TEND_SCHEDULE=uniform keeps ZM_TEND_SUBBATCHES equal parts.
+  int sched_nb = 0, sched_first[MAXB + 1] = {};
+  int plan(int nchunks) {
+    const char* e = getenv("ZM_TEND_SCHEDULE");
+    const bool ramp = !(e && !strcmp(e, "uniform")) && !getenv("ZM_TEND_SUBBATCHES") && nchunks >= 16 * 64;
+    if (ramp) {
+      static const int sixteenths[7] = {0, 1, 2, 4, 8, 12, 16};
+      sched_nb = 6;
+      for (int b = 0; b <= 6; ++b) sched_first[b] = (int)((long long)nchunks * sixteenths[b] / 16);
+    } else {
+      sched_nb = subbatches(nchunks);
+      for (int b = 0; b <= sched_nb; ++b) sched_first[b] = first(b, nchunks, sched_nb);
+    }
+    return sched_nb;
+  }
   void release() {
     for (int b = 0; b < MAXB; ++b) work[b].release();
     for (int b = 0; b < ninit; ++b) {
@@ -1075,7 +1093,7 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   // device allocation for the whole batch (sub-batches are chunk slices of it), so the pbuf mirror that
   // zm_conv_tend_2_batch reads stays contiguous.
   TendPipe& tp = tls_pipe;
-  int NB = tp.subbatches(nchunks);
+  const int NB = tp.plan(nchunks);
   if (tp.init(NB)) return -100;
   const size_t s2 = pc * L, s2p = pc * (L + 1), s1 = pc;            // per-chunk strides
   // kind 0 in, 1 late in, 2 early out, 3 final out; per-column/per-chunk arrays are small and travel once for the
@@ -1134,7 +1152,7 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   // Enqueue order on the host thread: inputs of sub-batch b+1 go out right after the kernels of sub-batch b
   // were launched, so neither the copy engine nor the SMs wait for the host to finish enqueueing.
   auto send_inputs = [&](int b) -> int {
-    const int c0 = tp.first(b, nchunks, NB), nb = tp.first(b + 1, nchunks, NB) - c0;
+    const int c0 = tp.sched_first[b], nb = tp.sched_first[b + 1] - c0;
     copy_kind(0, c0, nb, tp.h2d);
     CK(cudaEventRecord(tp.in_ready[b], tp.h2d));
     copy_kind(1, c0, nb, tp.h2d);
@@ -1145,7 +1163,7 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   copy_kind(4, 0, nchunks, tp.h2d);
   if (send_inputs(0)) return -100;
   for (int b = 0; b < NB && rc == 0; ++b) {
-    const int c0 = tp.first(b, nchunks, NB), nb = tp.first(b + 1, nchunks, NB) - c0;
+    const int c0 = tp.sched_first[b], nb = tp.sched_first[b + 1] - c0;
     Workspace& ws = tp.work[b];
     ws.chunk0 = c0;
     if (!ws.stream && ws.ensure(0)) return -100;

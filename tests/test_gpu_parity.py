@@ -338,24 +338,27 @@ def test_conv_tend_2_uses_device_mirror(built):
 
 def test_finalize_releases_and_reinit_reproduces(built):
     """zm_finalize frees the thread's arenas/streams; a fresh zm_init + step gives the same bits, and the
-    pipelined host API (8 sub-batches) equals the unpipelined one."""
+    pipelined host API (ramp schedule: 6 sub-batches of 1,1,2,4,4,4 sixteenths; then 8 equal ones) equals the
+    unpipelined one."""
     Z = init_cuda(16, 32)
-    ch = S.make_chunks(16 * 1100, 32, 16, p_conv=0.5)         # 1100 chunks: 8 sub-batches of >= 128 chunks
+    ch = S.make_chunks(16 * 1100, 32, 16, p_conv=0.5)         # 1100 chunks: enough for the ramp schedule
     out1 = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
     tr = Z.tend_trace()
-    assert tr.shape == (8, 6) and np.all(tr >= 0.0)
+    assert tr.shape == (6, 6) and np.all(tr >= 0.0)
     assert np.all(tr[:, 5] >= tr[:, 2])                        # outputs leave after zm_convr finished
     assert Z.lib().zm_finalize() == 0
     with pytest.raises(Z.ZmError):
         Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
     Z = init_cuda(16, 32)
-    os.environ["ZM_TEND_SUBBATCHES"] = "1"
-    try:
-        out2 = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
-    finally:
-        del os.environ["ZM_TEND_SUBBATCHES"]
-    for k in out1:
-        assert np.array_equal(out1[k], out2[k]), k
+    for nsub, shape in (("1", (1, 6)), ("8", (8, 6))):
+        os.environ["ZM_TEND_SUBBATCHES"] = nsub
+        try:
+            out2 = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
+            assert Z.tend_trace().shape == shape
+        finally:
+            del os.environ["ZM_TEND_SUBBATCHES"]
+        for k in out1:
+            assert np.array_equal(out1[k], out2[k]), (nsub, k)
     assert out1["lengath"].sum() > 0
 
 
