@@ -13,6 +13,7 @@
 #include <vector>
 #include <string>
 #include <mutex>
+#include <chrono>
 
 namespace {
 
@@ -119,6 +120,21 @@ struct TendPipe {
   int plan(int nchunks) {
     const char* e = getenv("ZM_TEND_SCHEDULE");
     const bool ramp = !(e && !strcmp(e, "uniform")) && !getenv("ZM_TEND_SUBBATCHES") && nchunks >= 16 * 64;
+    if (e && strchr(e, ',')) {                 // explicit sizes in sixteenths, e.g. "1,2,3,4,6"
+      int sizes[MAXB], n = 0, tot = 0;
+      for (const char* p = e; *p && n < MAXB;) {
+        sizes[n] = atoi(p); tot += sizes[n++];
+        p = strchr(p, ',');
+        if (!p) break;
+        ++p;
+      }
+      if (tot == 16 && nchunks >= 16 * 64) {
+        sched_nb = n;
+        int acc = 0;
+        for (int b = 0; b <= n; ++b) { sched_first[b] = (int)((long long)nchunks * acc / 16); if (b < n) acc += sizes[b]; }
+        return sched_nb;
+      }
+    }
     if (ramp) {
       static const int sixteenths[7] = {0, 1, 2, 4, 8, 12, 16};
       sched_nb = 6;
@@ -1093,6 +1109,9 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   // device allocation for the whole batch (sub-batches are chunk slices of it), so the pbuf mirror that
   // zm_conv_tend_2_batch reads stays contiguous.
   TendPipe& tp = tls_pipe;
+  const auto wall0 = std::chrono::steady_clock::now();
+  auto wall_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count(); };
+  const bool dbg = getenv("ZM_TEND_DEBUG") != nullptr;
   const int NB = tp.plan(nchunks);
   if (tp.init(NB)) return -100;
   const size_t s2 = pc * L, s2p = pc * (L + 1), s1 = pc;            // per-chunk strides
@@ -1160,6 +1179,7 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
     return 0;
   };
   CK(cudaEventRecord(tp.t0, tp.h2d));
+  const double w_t0 = wall_ms();
   copy_kind(4, 0, nchunks, tp.h2d);
   if (send_inputs(0)) return -100;
   for (int b = 0; b < NB && rc == 0; ++b) {
@@ -1184,8 +1204,10 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
 #undef O2P
 #undef O1
     if (rc) break;
+    const double w_k = wall_ms();
     CK(cudaEventRecord(tp.done[b], ws.stream));
     if (b + 1 < NB && send_inputs(b + 1)) return -100;
+    const double w_in = wall_ms();
     // device->host: zm_convr's outputs as soon as they are final, the rest when the sub-batch ends
     // one return stream, in the order results become final: by the time sub-batch b's zm_convr outputs are
     // across, its evap/momtran kernels have finished too
@@ -1195,6 +1217,8 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
     CK(cudaStreamWaitEvent(tp.d2h_early, tp.done[b], 0));
     copy_kind(3, c0, nb, tp.d2h_early);
     CK(cudaEventRecord(tp.final_back[b], tp.d2h_early));
+    if (dbg) fprintf(stderr, "  sub-batch %d: kernels enqueued %.3f, next inputs enqueued %.3f, returns enqueued %.3f ms\n",
+                     b, w_k, w_in, wall_ms());
   }
   if (rc == 0) copy_kind(5, 0, nchunks, tp.d2h_early);
   // the Brent failure counters of all sub-batches ride back on the return stream (it has waited for every
@@ -1205,8 +1229,11 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
       if (tp.work[b].last_count &&
           cudaMemcpyAsync(fail_cnt[b], tp.work[b].last_count, sizeof fail_cnt[b], cudaMemcpyDeviceToHost, tp.d2h_early) != cudaSuccess)
         rc = -100;
+  const double w_enq = wall_ms();
   cudaError_t e1 = cudaStreamSynchronize(tp.d2h_early), e2 = cudaStreamSynchronize(tp.d2h_final),
               e3 = cudaStreamSynchronize(tp.h2d);
+  if (dbg) fprintf(stderr, "zm_conv_tend_batch host thread: t0 recorded at %.3f ms, everything enqueued at %.3f ms, "
+                           "streams drained at %.3f ms\n", w_t0, w_enq, wall_ms());
   for (int b = 0; b < NB; ++b)
     if (tp.work[b].stream && cudaStreamSynchronize(tp.work[b].stream) != cudaSuccess) rc = -100;
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) rc = -100;

@@ -135,7 +135,8 @@ int zm_convtran_batch_dev(int nchunks, const int* doconvtran, const double* q, i
  *   host-pointer variant: the batch is pipelined over sub-batches of whole chunks so that host->device copies,
  *     kernels and device->host copies overlap; results do not depend on it.  Default for >= 1024 chunks: six
  *     sub-batches of 1,1,2,4,4,4 sixteenths (early first results, then large PCIe copies); ZM_TEND_SUBBATCHES=n
- *     (1..8) or ZM_TEND_SCHEDULE=uniform selects equal parts (default 8, never below 128 chunks each).
+ *     (1..8) or ZM_TEND_SCHEDULE=uniform selects equal parts (default 8, never below 128 chunks each);
+ *     ZM_TEND_SCHEDULE="1,2,3,4,6" gives explicit sizes in sixteenths; ZM_TEND_DEBUG prints the host-side timing.
  *   _dev variant: from the third call with an identical argument list on, the step is replayed as a CUDA graph on
  *     `stream` (ZM_DEV_GRAPH=0 disables); ZM_DEV_SUBBATCHES (default 1) optionally splits the step over the
  *     library's own prioritised streams, joined back into `stream`. */
