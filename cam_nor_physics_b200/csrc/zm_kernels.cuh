@@ -85,11 +85,14 @@ __global__ void k_convr_init(ConvrIn in, ConvrOut o, ConvrWork w) {
 // ---- buoyan_dilute + parcel_dilute, one thread per column ----------------------------------
 // zm_conv.F90:4425-4819 and 4824-5277.  PASS 1: every column.  PASS 2: worklist wl1 only.
 // ORG = true adds the zm_org branches of parcel_dilute (zm_conv.F90:5066-5074, 5186-5188, 5255-5257).
-template <int PASS, bool ORG = false>
-__global__ void __launch_bounds__(128, PASS == 1 ? 3 : 2)      // pass 2 has few warps: let it keep everything in registers
+// LAT = true: latency mode for launches with few columns (second pass; first pass of small batches): paired bracket
+// evaluation and up to 255 registers; LAT = false: throughput mode (168 registers so that a whole f09 shard is
+// resident in one wave, single-site evaluation).
+template <int PASS, bool ORG = false, bool LAT = (PASS == 2)>
+__global__ void __launch_bounds__(128, LAT ? 2 : 3)
 k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   extern __shared__ double sm_buoy[];               // [pver+2][blockDim.x]
-  constexpr bool PAIR = (PASS == 2);                 // paired bracket evaluation only where latency-bound
+  constexpr bool PAIR = LAT;                         // paired bracket evaluation only where latency-bound
   zmm::hot_tables_load();                            // before any early return (block-wide barrier inside)
   const int pcols = P.pcols, pver = P.pver, msg = P.msg;
   const int ncolpad = in.nchunks * pcols;

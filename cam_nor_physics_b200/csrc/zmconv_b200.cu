@@ -250,6 +250,7 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   CK(cudaFuncSetAttribute(k_plm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
   if (smem > 48 * 1024) {
     CK(cudaFuncSetAttribute(k_buoyan_dilute<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((k_buoyan_dilute<1, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_buoyan_dilute<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_buoyan_undilute, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute((k_buoyan_dilute<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -263,6 +264,8 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   tick(ws, s, "convr_init");
   if (g_params.cam3) k_buoyan_undilute<<<nblk_cols, TB, smem, s>>>(in, w);     // zm_conv.F90:871-880
   else if (org_on)   k_buoyan_dilute<1, true><<<nblk_cols, TB, smem, s>>>(in, w);
+  else if (ncolpad <= 24576)                 // few columns: the per-column chain is all that counts (latency mode)
+    k_buoyan_dilute<1, false, true><<<nblk_cols, TB, smem, s>>>(in, w);
   else               k_buoyan_dilute<1><<<nblk_cols, TB, smem, s>>>(in, w);
   ++tls_launches;
   tick(ws, s, "buoyan_dilute_pass1");
