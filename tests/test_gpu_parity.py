@@ -511,3 +511,32 @@ def test_cuda_vs_reference_source_text_sweep(built):
         out[k] = out[k] * m
         ref[k] = ref[k] * m
     assert_same(out, ref, [k for k in REFTEXT_CONVR] + ["lengath"], 16, exact=False, what="CUDA vs reference text (sweep)")
+
+
+def test_convtran_zero_and_negative_tracers(built):
+    """Tracer columns with exact zeros, tiny values and slightly negative entries (CAM tracers do go negative before
+    qneg3): the interface-value branches of zm_conv.F90:2119-2139 (minc < 0, both zero, one zero) bit-exact vs oracle."""
+    Z = init_cuda(16, 32)
+    o, p, _ = get_oracle("pm", 16, 32)
+    ch = S.make_chunks(640, 32, 16, p_conv=0.7, col0=31000)
+    ref = o.convr_batch(ch)
+    ncnst = 7
+    q, fracis, pdeldry = S.make_tracers(ch, ncnst)
+    rng = np.random.default_rng(77)
+    u = rng.uniform(size=q.shape)
+    q[(u < 0.06)] = 0.0
+    q[(u >= 0.06) & (u < 0.09)] *= -0.01
+    q[(u >= 0.09) & (u < 0.12)] *= 1e-25
+    q[:, 5] = 0.0                                   # an all-zero constituent
+    do = [0, 1, 1, 1, 1, 1, 1]
+    dry = [0, 0, 1, 0, 1, 0, 1]
+    dpdry = dpdry_gathered(ch, ref, pdeldry)
+    dq = Z.convtran(do, q, ref["mu"], ref["md"], ref["du"], ref["eu"], ref["ed"], ref["dp"], ref["dsubcld"],
+                    ref["jt"], ref["maxg"], ref["ideep"], ref["lengath"], fracis, dpdry, ch.ztodt, dry)
+    for c in range(ch.nchunks):
+        r = o.convtran(do, q[c], ref["mu"][c], ref["md"][c], ref["du"][c], ref["eu"][c], ref["ed"][c], ref["dp"][c],
+                       ref["dsubcld"][c], ref["jt"][c], ref["maxg"][c], ref["ideep"][c], ref["lengath"][c],
+                       fracis[c], dpdry[c], ch.ztodt, dry)
+        for m in range(1, ncnst):
+            assert np.array_equal(dq[c, m], r[m]), (c, m)
+    assert np.all(dq[:, 5] == 0.0) and np.count_nonzero(dq) > 0 and np.all(np.isfinite(dq))
