@@ -148,7 +148,7 @@ def FA(a, dtype=float):
 
 
 def run_case(name, ncols, pver, p_conv, nl, ncol_used=None, org=False, cam3=False, col0=0, ncnst=6, pcols=16,
-             transform=None):
+             transform=None, tracer_edge=False):
     """One chunk.  nl: namelist overrides of zm_convi."""
     L = pver
     # cam3: zm_convr tests `cin` (zm_conv.F90:909) although buoyan never defines it -- undefined behaviour in the
@@ -258,6 +258,11 @@ def run_case(name, ncols, pver, p_conv, nl, ncol_used=None, org=False, cam3=Fals
     # ---- convtran (zm_conv_intr.F90:1014-1024 dpdry gather; :875 / :1020 call) ----
     qtr, fracis, pdeldry = S.make_tracers(ch, ncnst)
     qtr, fracis, pdeldry = qtr[0], fracis[0], pdeldry[0]
+    if tracer_edge:       # exact zeros, tiny and slightly negative mixing ratios: the chat branches of :2119-2139
+        u = np.random.default_rng(5).uniform(size=qtr.shape)
+        qtr[u < 0.08] = 0.0
+        qtr[(u >= 0.08) & (u < 0.12)] *= -0.01
+        qtr[(u >= 0.12) & (u < 0.16)] *= 1e-25
     dpdry = np.zeros((L, pcols))
     n = int(lengath)
     idx = o["ideep"][:n] - 1
@@ -435,7 +440,7 @@ CASES = [
     dict(name="single_column_L32", ncols=1, pver=32, p_conv=1.0, nl={}, col0=10700),
     dict(name="strong_entrainment_L32", ncols=16, pver=32, p_conv=1.0,
          nl={"dmpdz": -2.5e-3, "tau": 1800.0, "c0_lnd": 0.0059, "c0_ocn": 0.045, "ke": 1.0e-6, "momcu": 0.4,
-             "momcd": 0.4}, col0=11500),
+             "momcd": 0.4}, col0=11500, tracer_edge=True),
     dict(name="stress_cold_L32", ncols=16, pver=32, p_conv=1.0, nl={}, col0=12300, transform="cold"),
     dict(name="stress_near_saturated_L32", ncols=16, pver=32, p_conv=1.0, nl={}, col0=13100, transform="near_saturated"),
     dict(name="stress_low_pbl_L32", ncols=16, pver=32, p_conv=1.0, nl={}, col0=13900, transform="low_pbl_big_tpert"),
