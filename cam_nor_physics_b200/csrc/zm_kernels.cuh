@@ -20,6 +20,8 @@
 #include "zm_device.cuh"
 
 #define ZM_MAXCIN 5
+#define ZM_ORD_KEYS 132                 // launch levels 1..pver <= 128 (+ slack)
+#define ZM_ORD_INTS (4 * ZM_ORD_KEYS)   // per CAPE pass: bucket sizes, bucket cursors
 
 // ---- argument blocks ----------------------------------------------------------------------
 struct ConvrIn {
@@ -41,7 +43,10 @@ struct ConvrWork {
   int *lcl, *lel, *mx;                   // [ncolpad]
   double *tp, *qstp;                     // [pver][ncolpad]
   int *wl1, *wl2;                        // worklists: pass-1 columns; final (col, slot) pairs
-  int *count;                            // [0]=n pass-1, [1]=n final, [2]=brent failures
+  int *okey;                             // [ncolpad] launch level of the dilute parcel (the CAPE kernels' work key)
+  int *ord1, *ord2;                      // [ncolpad] columns of CAPE pass 1 / pass 2, most parcel levels first
+  int *count;                            // [0]=n pass-1, [1]=n final, [2]=brent failures, [3]=real columns;
+                                         // then ZM_ORD_INTS work-ordering counters (see k_order_*)
   double *errinfo;                       // first failure: rcall, col, p, Tfg, qt, s
 };
 
@@ -79,11 +84,113 @@ __global__ void k_convr_init(ConvrIn in, ConvrOut o, ConvrWork w) {
     w.dmpdz[e] = -P.tentrm;
   }
   for (size_t e = tid; e < (size_t)in.nchunks; e += nth) o.lengath[e] = 0;
-  if (tid < 3) w.count[tid] = 0;
+  if (tid < 4 + ZM_ORD_INTS) w.count[tid] = 0;
+}
+
+// ---- launch level of the dilute parcel and the work ordering of the CAPE passes ---------------------
+// boundary-layer top level (zm_conv.F90:839-843)
+__device__ __forceinline__ int pbl_top_level(const ConvrIn& in, int c, int i, double zs, double pblh) {
+  const int pver = P.pver, msg = P.msg;
+  int pblt = pver;
+  for (int k = pver - 1; k >= msg + 1; --k) {
+    const double zk = in.zm[cidx(c, k - 1, i, pver)] + zs;
+    const double zfk = in.zi[cidx(c, k - 1, i, pver + 1)] + zs, zfk1 = in.zi[cidx(c, k, i, pver + 1)] + zs;
+    if (fabs(zk - zs - pblh) < (zfk - zfk1) * 0.5) pblt = k;
+  }
+  return pblt;
+}
+// moist static energy that picks the launch level (zm_conv.F90:4677-4689; same expression at 4650-4652)
+__device__ __forceinline__ double hmn_launch(double tk, double qk, double zk) {
+  return (P.cpres + qk * P.cpliq) * tk / (1.0 + qk) + (1.0 + qk / P.eps1) / (1.0 + qk) * P.grav * zk +
+         (P.rl - (P.cpliq - P.cpwv) * (tk - P.tfreez)) * qk;
+}
+// level the parcel is launched from: `mx` of buoyan_dilute (zm_conv.F90:4677-4689), or the top level of the
+// mixed parcel layer when parcel_pbl is on (zm_conv.F90:4638-4673).  Used only as the work key below; the CAPE
+// kernel derives the level itself from the same two functions.
+__device__ __forceinline__ int launch_level(const ConvrIn& in, int c, int i) {
+  const int pcols = P.pcols, pver = P.pver, msg = P.msg;
+  const double zs = in.geos[(size_t)c * pcols + i] * P.rgrav;
+  const int pblt = pbl_top_level(in, c, i, zs, in.pblh[(size_t)c * pcols + i]);
+  if (P.lparcel_pbl) {
+    const double pbl_dz = (in.zm[cidx(c, pblt - 1, i, pver)] + zs) - zs;
+    const double parcel_dz = fmax2(in.zi[cidx(c, pver - 1, i, pver + 1)], P.parcel_hscale * pbl_dz);
+    int ipar = pver;
+    for (int k = pver; k >= msg + 1; --k)
+      if (in.zi[cidx(c, k, i, pver + 1)] <= parcel_dz) ipar = k;
+    return ipar;
+  }
+  const int lon = min(pver, pblt + 2);
+  int mx = lon;
+  double hmax = 0.0;
+  for (int k = lon; k >= max(pblt, msg + 1); --k) {
+    const double hmn = hmn_launch(in.t[cidx(c, k - 1, i, pver)], in.qh[cidx(c, k - 1, i, pver)],
+                                  in.zm[cidx(c, k - 1, i, pver)] + zs);
+    if (hmn > hmax) { hmax = hmn; mx = k; }
+  }
+  return mx;
+}
+
+// A column's parcel sweep climbs from its launch level to level msg+1 with three Brent inversions per level, and a
+// warp of k_buoyan_dilute lasts as long as its longest lane.  Both CAPE passes therefore take their columns from a
+// list bucketed by launch level, most levels first (counting sort): lanes of a warp then climb the same levels (the
+// iteration counts of the inversions follow the level closely), and every SM receives long and short blocks.
+// The order changes nothing in the results: columns are independent.
+//   counters (w.count + 4): [0,K) bucket sizes pass 1, [K,2K) cursors pass 1, [2K,3K) sizes pass 2, [3K,4K) cursors
+template <int PASS>
+__global__ void __launch_bounds__(256) k_order_count(ConvrIn in, ConvrWork w) {
+  __shared__ int s_n[ZM_ORD_KEYS];
+  for (int t = threadIdx.x; t < ZM_ORD_KEYS; t += blockDim.x) s_n[t] = 0;
+  __syncthreads();
+  const int pcols = P.pcols;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = PASS == 1 ? in.nchunks * pcols : w.count[0];
+  if (gid < n) {
+    const int col = PASS == 1 ? gid : w.wl1[gid];
+    const int c = col / pcols, i = col - c * pcols;
+    if (i < in.ncol[c]) {
+      int key;
+      if (PASS == 1) { key = min(max(launch_level(in, c, i), 0), ZM_ORD_KEYS - 1); w.okey[col] = key; }
+      else key = w.okey[col];
+      atomicAdd(&s_n[key], 1);
+    }
+  }
+  __syncthreads();
+  int* sizes = w.count + 4 + (PASS == 1 ? 0 : 2 * ZM_ORD_KEYS);
+  for (int t = threadIdx.x; t < ZM_ORD_KEYS; t += blockDim.x)
+    if (s_n[t]) atomicAdd(&sizes[t], s_n[t]);
+}
+template <int PASS>
+__global__ void __launch_bounds__(256) k_order_scatter(ConvrIn in, ConvrWork w) {
+  __shared__ int s_size[ZM_ORD_KEYS], s_base[ZM_ORD_KEYS], s_n[ZM_ORD_KEYS], s_off[ZM_ORD_KEYS];
+  const int* sizes = w.count + 4 + (PASS == 1 ? 0 : 2 * ZM_ORD_KEYS);
+  int* cursors = w.count + 4 + (PASS == 1 ? 1 : 3) * ZM_ORD_KEYS;
+  for (int t = threadIdx.x; t < ZM_ORD_KEYS; t += blockDim.x) { s_size[t] = sizes[t]; s_n[t] = 0; }
+  __syncthreads();
+  for (int t = threadIdx.x; t < ZM_ORD_KEYS; t += blockDim.x) {      // bucket start: everything with a larger key
+    int b = 0;
+    for (int u = t + 1; u < ZM_ORD_KEYS; ++u) b += s_size[u];
+    s_base[t] = b;
+    if (PASS == 1 && t == 0 && blockIdx.x == 0) w.count[3] = b + s_size[0];
+  }
+  const int pcols = P.pcols;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = PASS == 1 ? in.nchunks * pcols : w.count[0];
+  int col = -1, key = 0, r = 0;
+  if (gid < n) {
+    col = PASS == 1 ? gid : w.wl1[gid];
+    const int c = col / pcols, i = col - c * pcols;
+    if (i < in.ncol[c]) { key = w.okey[col]; r = atomicAdd(&s_n[key], 1); }
+    else col = -1;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < ZM_ORD_KEYS; t += blockDim.x)
+    if (s_n[t]) s_off[t] = atomicAdd(&cursors[t], s_n[t]);
+  __syncthreads();
+  if (col >= 0) (PASS == 1 ? w.ord1 : w.ord2)[s_base[key] + s_off[key] + r] = col;
 }
 
 // ---- buoyan_dilute + parcel_dilute, one thread per column ----------------------------------
-// zm_conv.F90:4425-4819 and 4824-5277.  PASS 1: every column.  PASS 2: worklist wl1 only.
+// zm_conv.F90:4425-4819 and 4824-5277.  PASS 1: every column (list ord1).  PASS 2: worklist wl1 only (as ord2).
 // ORG = true adds the zm_org branches of parcel_dilute (zm_conv.F90:5066-5074, 5186-5188, 5255-5257).
 // LAT = true: latency mode for launches with few columns (second pass; first pass of small batches): paired bracket
 // evaluation and up to 255 registers; LAT = false: throughput mode (168 registers so that a whole f09 shard is
@@ -99,10 +206,9 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   const int nthr = blockDim.x;
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int col;
-  if (PASS == 1) { if (gid >= ncolpad) return; col = gid; }
-  else           { if (gid >= w.count[0]) return; col = w.wl1[gid]; }
+  if (PASS == 1) { if (gid >= w.count[3]) return; col = w.ord1[gid]; }     // work-ordered lists (k_order_*)
+  else           { if (gid >= w.count[0]) return; col = w.ord2[gid]; }
   const int c = col / pcols, i = col - c * pcols;
-  if (i >= in.ncol[c]) return;
 #define BUOY(k) sm_buoy[(k) * nthr + threadIdx.x]
 #define IN2(a, k) in.a[cidx(c, (k) - 1, i, pver)]
 #define IN2P(a, k) in.a[cidx(c, (k) - 1, i, pver + 1)]
@@ -115,13 +221,7 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   const double landfrac = ORG ? in.landfrac[(size_t)c * pcols + i] : 0.0;
   const double org2rkm = 10.0, org2Tpert = 0.0;     // zm_conv.F90:4948-4951
 
-  // pblt (zm_conv.F90:839-843)
-  int pblt = pver;
-  for (int k = pver - 1; k >= msg + 1; --k) {
-    double zk = IN2(zm, k) + zs;
-    double zfk = IN2P(zi, k) + zs, zfk1 = IN2P(zi, k + 1) + zs;
-    if (fabs(zk - zs - pblh) < (zfk - zfk1) * 0.5) pblt = k;
-  }
+  const int pblt = pbl_top_level(in, c, i, zs, pblh);
   const int lon = min(pver, pblt + 2);
   int mx = lon;
   double tl, ql, pl, zl = 0.0;
@@ -139,8 +239,7 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
         if (k == pver) dp_zfrac = 1.0;
         else dp_zfrac = fmin2(1.0, (parcel_dz - IN2P(zi, k + 1)) / (IN2P(zi, k) - IN2P(zi, k + 1)));
         double qk = IN2(qh, k), tk = IN2(t, k), zk = IN2(zm, k) + zs;
-        double hmn_lev = (cp + qk * P.cpliq) * tk / (1.0 + qk) + (1.0 + qk / eps1) / (1.0 + qk) * grav * zk +
-                         (rl - (P.cpliq - P.cpwv) * (tk - P.tfreez)) * qk;
+        double hmn_lev = hmn_launch(tk, qk, zk);
         double dp_lev = IN2P(paph, k + 1) * 0.01 - IN2P(paph, k) * 0.01;
         parcel_hdp = parcel_hdp + (hmn_lev * dp_lev) * dp_zfrac;
         parcel_qdp = parcel_qdp + (qk * dp_lev) * dp_zfrac;
@@ -157,8 +256,7 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
     double hmax = 0.0;
     for (int k = lon; k >= max(pblt, msg + 1); --k) {
       double qk = IN2(qh, k), tk = IN2(t, k), zk = IN2(zm, k) + zs;
-      double hmn = (cp + qk * P.cpliq) * tk / (1.0 + qk) + (1.0 + qk / eps1) / (1.0 + qk) * grav * zk +
-                   (rl - (P.cpliq - P.cpwv) * (tk - P.tfreez)) * qk;
+      double hmn = hmn_launch(tk, qk, zk);
       if (hmn > hmax) { hmax = hmn; mx = k; }
     }
     tl = IN2(t, mx);

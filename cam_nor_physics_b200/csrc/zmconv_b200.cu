@@ -210,7 +210,7 @@ int lmax_for(int pver) { return pver <= 32 ? 32 : (pver <= 64 ? 64 : (pver <= 12
 
 size_t convr_work_bytes(size_t ncolpad, int pver) {
   return 4 * al(ncolpad, 8) + 3 * al(ncolpad, 4) + 2 * al(ncolpad * pver, 8) + al(ncolpad, 4) +
-         al(2 * ncolpad, 4) + al(4, 4) + al(8, 8) + 4096;
+         al(2 * ncolpad, 4) + 3 * al(ncolpad, 4) + al(4 + ZM_ORD_INTS, 4) + al(8, 8) + 4096;
 }
 
 // enqueue the whole zm_convr pipeline on stream s (no host synchronisation)
@@ -230,7 +230,8 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   w.lcl = ws.take<int>(ncolpad); w.lel = ws.take<int>(ncolpad); w.mx = ws.take<int>(ncolpad);
   w.tp = ws.take<double>(ncolpad * pver); w.qstp = ws.take<double>(ncolpad * pver);
   w.wl1 = ws.take<int>(ncolpad); w.wl2 = ws.take<int>(2 * ncolpad);
-  w.count = ws.take<int>(4); w.errinfo = ws.take<double>(8);
+  w.okey = ws.take<int>(ncolpad); w.ord1 = ws.take<int>(ncolpad); w.ord2 = ws.take<int>(ncolpad);
+  w.count = ws.take<int>(4 + ZM_ORD_INTS); w.errinfo = ws.take<double>(8);
   ws.last_count = w.count; ws.last_err = w.errinfo;
   for (auto e : ws.tev) cudaEventDestroy(e);
   ws.tev.clear(); ws.tnames.clear();
@@ -261,6 +262,9 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   if (org_on) {      // zm_conv.F90:555-556, 793-819
     k_org2d<<<nblk_cols, TB, 0, s>>>(in.nchunks, in.ncol, in.org, in.dpp, orgt, org2d); ++tls_launches;
   }
+  const int nblk_ord = (int)((ncolpad + 255) / 256);
+  k_order_count<1><<<nblk_ord, 256, 0, s>>>(in, w); ++tls_launches;           // CAPE work order: most parcel levels first
+  k_order_scatter<1><<<nblk_ord, 256, 0, s>>>(in, w); ++tls_launches;
   tick(ws, s, "convr_init");
   if (g_params.cam3) k_buoyan_undilute<<<nblk_cols, TB, smem, s>>>(in, w);     // zm_conv.F90:871-880
   else if (org_on)   k_buoyan_dilute<1, true><<<nblk_cols, TB, smem, s>>>(in, w);
@@ -270,6 +274,8 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   ++tls_launches;
   tick(ws, s, "buoyan_dilute_pass1");
   k_trigger<0><<<nwarpblk, 128, 0, s>>>(in, o, w); ++tls_launches;
+  k_order_count<2><<<nblk_ord, 256, 0, s>>>(in, w); ++tls_launches;
+  k_order_scatter<2><<<nblk_ord, 256, 0, s>>>(in, w); ++tls_launches;
   tick(ws, s, "trigger_pass1");
   k_cld1<<<nblk_pl, 32 * pl_warps, smem_pl, s>>>(in, w);
   ++tls_launches;
