@@ -186,7 +186,7 @@ struct TendPipe {
 };
 thread_local TendPipe tls_pipe;
 
-// CUDA graph of one device-resident zm_conv_tend step (15 kernels, one memset, a fork/join with the side stream).
+// CUDA graph of one device-resident zm_conv_tend step (19 kernels, one memset, a fork/join with the side stream).
 // A step is launch-gap sensitive (several kernels run 10-50 us), and a model calls it every time step with the same
 // device arrays: the second call with an identical argument list is captured, later ones replay the graph.
 struct TendGraph {
