@@ -125,6 +125,11 @@ def main():
     ap.add_argument("--parcel-pbl", action="store_true", help="zmconv_parcel_pbl=.true. (CAM6 L58 default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries the JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its
+    # version banner there) are sent to stderr for the whole run, the line goes to the saved descriptor
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -171,7 +176,7 @@ def main():
                                  "sample": f"full step on {args.ncols} columns, CPU oracle ({backend}), "
                                            "OpenMP over pcols=16 chunks"},
                 "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n"); json_out.flush()
         return
 
     # ---------------- B200 arm ---------------------------------------------------------------------
@@ -337,7 +342,7 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"full step on all {args.ncols} columns x3 (best), CPU oracle "
                                               f"({backend}) with OpenMP over pcols=16 chunks; {best*1e3:.1f} ms/step"}
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n"); json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
