@@ -280,8 +280,15 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   k_cld1<<<nblk_pl, 32 * pl_warps, smem_pl, s>>>(in, w);
   ++tls_launches;
   tick(ws, s, "cldprp_pass1");
-  if (org_on) k_buoyan_dilute<2, true><<<nblk_cols, TB, smem, s>>>(in, w);
-  else        k_buoyan_dilute<2><<<nblk_cols, TB, smem, s>>>(in, w);
+  // The reference's second call covers every column (zm_conv.F90:1080-1091).  After a dilute first pass the columns
+  // that did not trigger keep their dmpdz row, so their second-pass result is the first-pass result and only the
+  // worklist is recomputed; after cam3's undilute first pass (zm_conv.F90:871) every column needs the dilute pass.
+  if (g_params.cam3) {
+    if (org_on)                k_buoyan_dilute<1, true><<<nblk_cols, TB, smem, s>>>(in, w);
+    else if (ncolpad <= 24576) k_buoyan_dilute<1, false, true><<<nblk_cols, TB, smem, s>>>(in, w);
+    else                       k_buoyan_dilute<1><<<nblk_cols, TB, smem, s>>>(in, w);
+  } else if (org_on) k_buoyan_dilute<2, true><<<nblk_cols, TB, smem, s>>>(in, w);
+  else               k_buoyan_dilute<2><<<nblk_cols, TB, smem, s>>>(in, w);
   ++tls_launches;
   tick(ws, s, "buoyan_dilute_pass2");
   k_trigger<1><<<nwarpblk, 128, 0, s>>>(in, o, w); ++tls_launches;

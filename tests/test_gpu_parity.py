@@ -88,6 +88,20 @@ def test_zm_convr_bit_exact_vs_oracle(built, ncols, pconv, pver, over):
         assert out["lengath"].sum() > 0
 
 
+def test_cam3_second_pass_covers_every_column(built):
+    """cam3: the first trigger pass is the undilute buoyan, so the dilute second call (zm_conv.F90:1080-1091, all ncol
+    columns) changes cape / tp / qstp of columns that did NOT trigger too.  Found by scripts/parity_fuzz.py: two
+    columns of this batch have a small undilute CAPE (7 and 18 J/kg) and a dilute CAPE of 0."""
+    over = {"cam3": 1, "num_cin": 5}
+    Z = init_cuda(16, 72, **over)
+    o, _, rc = get_oracle("pm", 16, 72, **over)
+    assert rc == 0
+    ch = S.make_chunks(4643, 72, 16, p_conv=0.1, seed=2145566664)
+    ref = o.convr_batch(ch)
+    out = cuda_convr(Z, ch)
+    assert_same(out, ref, CONVR_KEYS, 16, exact=True, what="cam3 L72 fuzz case")
+
+
 def test_large_pcols_chunk(built):
     """pcols = 128 (CAM allows large pcols): compaction spans several warp sweeps."""
     Z = init_cuda(128, 32)
