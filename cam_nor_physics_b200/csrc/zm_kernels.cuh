@@ -48,6 +48,8 @@ struct ConvrWork {
   int *count;                            // [0]=n pass-1, [1]=n final, [2]=brent failures, [3]=real columns;
                                          // then ZM_ORD_INTS work-ordering counters (see k_order_*)
   double *errinfo;                       // first failure: rcall, col, p, Tfg, qt, s
+  int *n1chunk;                          // [nchunks] pass-1 convective columns per chunk (k_trigger<0>)
+  int skip_idle_chunks;                  // CAPE kernel: leave chunks with n1chunk == 0 alone (cam3 second pass)
 };
 
 __device__ __forceinline__ size_t cidx(int c, int k0, int i, int nlev) {
@@ -209,6 +211,9 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   if (PASS == 1) { if (gid >= w.count[3]) return; col = w.ord1[gid]; }     // work-ordered lists (k_order_*)
   else           { if (gid >= w.count[0]) return; col = w.ord2[gid]; }
   const int c = col / pcols, i = col - c * pcols;
+  // zm_convr returns after the first gather when a chunk has no convective column (zm_conv.F90:917): its
+  // first-pass results stand
+  if (w.skip_idle_chunks && w.n1chunk[c] == 0) return;
 #define BUOY(k) sm_buoy[(k) * nthr + threadIdx.x]
 #define IN2(a, k) in.a[cidx(c, (k) - 1, i, pver)]
 #define IN2P(a, k) in.a[cidx(c, (k) - 1, i, pver + 1)]
@@ -619,6 +624,7 @@ __global__ void k_trigger(ConvrIn in, ConvrOut o, ConvrWork w) {
     }
     base += __popc(m);
   }
+  if (!FINAL && lane == 0) w.n1chunk[c] = total;
   if (FINAL) {
     if (lane == 0) o.lengath[c] = total;
     for (int i = lane; i < ncol; i += 32) o.cape[(size_t)c * pcols + i] = w.cape[c * pcols + i];

@@ -210,7 +210,7 @@ int lmax_for(int pver) { return pver <= 32 ? 32 : (pver <= 64 ? 64 : (pver <= 12
 
 size_t convr_work_bytes(size_t ncolpad, int pver) {
   return 4 * al(ncolpad, 8) + 3 * al(ncolpad, 4) + 2 * al(ncolpad * pver, 8) + al(ncolpad, 4) +
-         al(2 * ncolpad, 4) + 3 * al(ncolpad, 4) + al(4 + ZM_ORD_INTS, 4) + al(8, 8) + 4096;
+         al(2 * ncolpad, 4) + 4 * al(ncolpad, 4) + al(4 + ZM_ORD_INTS, 4) + al(8, 8) + 4096;
 }
 
 // enqueue the whole zm_convr pipeline on stream s (no host synchronisation)
@@ -232,6 +232,7 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   w.wl1 = ws.take<int>(ncolpad); w.wl2 = ws.take<int>(2 * ncolpad);
   w.okey = ws.take<int>(ncolpad); w.ord1 = ws.take<int>(ncolpad); w.ord2 = ws.take<int>(ncolpad);
   w.count = ws.take<int>(4 + ZM_ORD_INTS); w.errinfo = ws.take<double>(8);
+  w.n1chunk = ws.take<int>((size_t)in.nchunks); w.skip_idle_chunks = 0;
   ws.last_count = w.count; ws.last_err = w.errinfo;
   for (auto e : ws.tev) cudaEventDestroy(e);
   ws.tev.clear(); ws.tnames.clear();
@@ -280,13 +281,16 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   k_cld1<<<nblk_pl, 32 * pl_warps, smem_pl, s>>>(in, w);
   ++tls_launches;
   tick(ws, s, "cldprp_pass1");
-  // The reference's second call covers every column (zm_conv.F90:1080-1091).  After a dilute first pass the columns
-  // that did not trigger keep their dmpdz row, so their second-pass result is the first-pass result and only the
-  // worklist is recomputed; after cam3's undilute first pass (zm_conv.F90:871) every column needs the dilute pass.
+  // The reference's second call covers every column of a chunk that has a convective column after the first gather
+  // (zm_conv.F90:917, 1080-1091).  After a dilute first pass the columns that did not trigger keep their dmpdz row,
+  // so their second-pass result is the first-pass result and only the worklist is recomputed; after cam3's undilute
+  // first pass (zm_conv.F90:871) every column of those chunks needs the dilute pass.
   if (g_params.cam3) {
-    if (org_on)                k_buoyan_dilute<1, true><<<nblk_cols, TB, smem, s>>>(in, w);
-    else if (ncolpad <= 24576) k_buoyan_dilute<1, false, true><<<nblk_cols, TB, smem, s>>>(in, w);
-    else                       k_buoyan_dilute<1><<<nblk_cols, TB, smem, s>>>(in, w);
+    ConvrWork w2 = w;
+    w2.skip_idle_chunks = 1;
+    if (org_on)                k_buoyan_dilute<1, true><<<nblk_cols, TB, smem, s>>>(in, w2);
+    else if (ncolpad <= 24576) k_buoyan_dilute<1, false, true><<<nblk_cols, TB, smem, s>>>(in, w2);
+    else                       k_buoyan_dilute<1><<<nblk_cols, TB, smem, s>>>(in, w2);
   } else if (org_on) k_buoyan_dilute<2, true><<<nblk_cols, TB, smem, s>>>(in, w);
   else               k_buoyan_dilute<2><<<nblk_cols, TB, smem, s>>>(in, w);
   ++tls_launches;

@@ -88,18 +88,24 @@ def test_zm_convr_bit_exact_vs_oracle(built, ncols, pconv, pver, over):
         assert out["lengath"].sum() > 0
 
 
-def test_cam3_second_pass_covers_every_column(built):
+@pytest.mark.parametrize("pver,pcols,ncols,pconv,seed", [
+    (72, 16, 4643, 0.1, 2145566664),     # two columns with a small undilute CAPE (7, 18 J/kg) and a dilute CAPE of 0
+    (58, 8, 2926, 0.0, 1233135682),      # a chunk without any first-gather column keeps its undilute CAPE
+])
+def test_cam3_second_pass_coverage(built, pver, pcols, ncols, pconv, seed):
     """cam3: the first trigger pass is the undilute buoyan, so the dilute second call (zm_conv.F90:1080-1091, all ncol
-    columns) changes cape / tp / qstp of columns that did NOT trigger too.  Found by scripts/parity_fuzz.py: two
-    columns of this batch have a small undilute CAPE (7 and 18 J/kg) and a dilute CAPE of 0."""
+    columns) changes cape / tp / qstp of columns that did NOT trigger too -- but only in chunks that have a
+    convective column after the first gather (zm_conv.F90:917 returns otherwise).  Both found by
+    scripts/parity_fuzz.py."""
     over = {"cam3": 1, "num_cin": 5}
-    Z = init_cuda(16, 72, **over)
-    o, _, rc = get_oracle("pm", 16, 72, **over)
+    Z = init_cuda(pcols, pver, **over)
+    o, _, rc = get_oracle("pm", pcols, pver, **over)
     assert rc == 0
-    ch = S.make_chunks(4643, 72, 16, p_conv=0.1, seed=2145566664)
+    ch = S.make_chunks(ncols, pver, pcols, p_conv=pconv, seed=seed)
     ref = o.convr_batch(ch)
     out = cuda_convr(Z, ch)
-    assert_same(out, ref, CONVR_KEYS, 16, exact=True, what="cam3 L72 fuzz case")
+    assert_same(out, ref, CONVR_KEYS, pcols, exact=True, what="cam3 fuzz case")
+    init_cuda(16, 32)
 
 
 def test_large_pcols_chunk(built):
