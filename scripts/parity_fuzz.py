@@ -1,4 +1,4 @@
-"""Randomised parity sweep: CUDA zm_convr / zm_conv_tend vs the CPU oracle (portable-math flavour, bit-exact) over random seeds,
+"""Randomised parity sweep: CUDA zm_convr / zm_conv_tend (with and without zm_org) / convtran vs the CPU oracle (portable-math flavour, bit-exact) over random seeds,
 batch sizes, chunk widths, level counts, convective fractions and namelist options.  Runs on the GPU box
 (`gpurun -- python scripts/parity_fuzz.py [ncases] [seed]`); the oracle is the checker, never the thing measured."""
 import sys, os, json, time
@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from cam_nor_physics_b200 import soundings as S
-from helpers import get_oracle, init_cuda, cuda_convr, assert_same, state_of, CONVR_KEYS, TEND_KEYS
+from helpers import get_oracle, init_cuda, cuda_convr, assert_same, state_of, dpdry_gathered, CONVR_KEYS, TEND_KEYS
 
 ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 7)
@@ -25,18 +25,66 @@ for case in range(ncases):
     o, _, rc = get_oracle("pm", pcols, pver, **over)
     assert rc == 0, (rc, over)
     ch = S.make_chunks(ncols, pver, pcols, p_conv=pconv, seed=seed)
-    if case % 2 == 0:                         # zm_convr alone / the whole zm_conv_tend sequence, alternating
-        ref = o.convr_batch(ch)
-        out = cuda_convr(Z, ch)
-        assert_same(out, ref, CONVR_KEYS, pcols, exact=True, what=f"fuzz case {case} (zm_convr)")
-    else:
-        ref = o.conv_tend_batch(ch)
-        out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
-        assert_same(out, ref, TEND_KEYS, pcols, exact=True, what=f"fuzz case {case} (zm_conv_tend)")
+    perturbed = bool(rng.random() < 0.35)
+    if perturbed:                             # level-wise noise: super-saturated / very dry layers, inversions, odd PBLs
+        ch.t[...] = ch.t + rng.normal(0.0, 2.5, ch.t.shape)
+        ch.q[...] = np.maximum(ch.q * rng.uniform(0.3, 1.7, ch.q.shape), 1e-12)
+        ch.pblh[...] = rng.uniform(20.0, 4000.0, ch.pblh.shape)
+        ch.tpert[...] = rng.uniform(0.0, 4.0, ch.tpert.shape)
+        ch.landfrac[...] = rng.choice([0.0, 1.0, 0.37], size=ch.landfrac.shape)
+    try:
+        kind = case % 4
+        use_org = kind == 3 and not over.get("cam3")
+        if use_org:                               # organisation tracer branches (zm_org), values in [0, 1] with zeros
+            over["zm_org"] = 1
+            Z = init_cuda(pcols, pver, **over)
+            o, _, rc = get_oracle("pm", pcols, pver, **over)
+            org = np.maximum(rng.uniform(-0.3, 1.0, ch.t.shape), 0.0)
+        if kind in (0, 2):                        # zm_convr alone
+            ref = o.convr_batch(ch)
+            out = cuda_convr(Z, ch)
+            assert_same(out, ref, CONVR_KEYS, pcols, exact=True, what=f"fuzz case {case} (zm_convr)")
+        elif use_org:
+            st = state_of(ch); st["org"] = org
+            ref = o.conv_tend_batch(ch, org=org)
+            out = Z.zm_conv_tend(ch.ncol, st, ch.ztodt)
+            assert_same(out, ref, TEND_KEYS + ["orgt", "org2d"], pcols, exact=True, what=f"fuzz case {case} (zm_conv_tend, zm_org)")
+        else:                                     # the whole zm_conv_tend sequence
+            ref = o.conv_tend_batch(ch)
+            out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
+            assert_same(out, ref, TEND_KEYS, pcols, exact=True, what=f"fuzz case {case} (zm_conv_tend)")
+        if kind == 2 and ncols <= 3000:           # convtran over a random constituent set (zeros / negatives included)
+            ncnst = int(rng.integers(2, 14))
+            q, fracis, pdeldry = S.make_tracers(ch, ncnst)
+            q = q * rng.choice([0.0, 1.0, 1.0, 1.0, -1.0, 1e-30], size=q.shape)
+            do = [0] + [int(x) for x in rng.integers(0, 2, ncnst - 1)]
+            dry = [int(x) for x in rng.integers(0, 2, ncnst)]
+            dpdry = dpdry_gathered(ch, ref, pdeldry)
+            dq = Z.convtran(do, q, ref["mu"], ref["md"], ref["du"], ref["eu"], ref["ed"], ref["dp"], ref["dsubcld"],
+                            ref["jt"], ref["maxg"], ref["ideep"], ref["lengath"], fracis, dpdry, ch.ztodt, dry,
+                            dqdt=np.full_like(q, 7.25))
+            for c in range(ch.nchunks):
+                r = o.convtran(do, q[c], ref["mu"][c], ref["md"][c], ref["du"][c], ref["eu"][c], ref["ed"][c], ref["dp"][c],
+                               ref["dsubcld"][c], ref["jt"][c], ref["maxg"][c], ref["ideep"][c], ref["lengath"][c],
+                               fracis[c], dpdry[c], ch.ztodt, dry)
+                for m in range(ncnst):
+                    if do[m] and m >= 1:
+                        assert np.array_equal(dq[c, m], r[m], equal_nan=True), ("convtran", case, c, m)
+                    else:
+                        assert np.all(dq[c, m] == 7.25), ("convtran untouched", case, c, m)
+    except Z.ZmEndrun as e:                   # Brent did not converge: the oracle must say so too (endrun in the reference)
+        assert ref["rc"] > 0, ("CUDA reports non-convergence, the oracle does not", case, str(e)[:200])
+        report.append(dict(case=case, pver=pver, pcols=pcols, ncols=ncols, p_conv=pconv, seed=seed, options=over,
+                           perturbed=perturbed, endrun=True))
+        print(report[-1], flush=True)
+        continue
+    assert ref["rc"] == 0, ("the oracle reports non-convergence, CUDA does not", case)
     assert Z.lib().zm_sync_check(None) == 0
-    rec = dict(case=case, pver=pver, pcols=pcols, ncols=ncols, p_conv=pconv, seed=seed, options=over,
+    rec = dict(case=case, pver=pver, pcols=pcols, ncols=ncols, p_conv=pconv, seed=seed, options=over, perturbed=perturbed,
                convective=int(out["lengath"].sum()), oracle_rc=int(ref["rc"]))
     report.append(rec)
     print(rec, flush=True)
 print(json.dumps({"cases": len(report), "all_bit_exact": True, "seconds": round(time.time() - t00, 1),
-                  "convective_columns": sum(r["convective"] for r in report)}))
+                  "perturbed_cases": sum(1 for r in report if r["perturbed"]),
+                  "endrun_cases": sum(1 for r in report if r.get("endrun")),
+                  "convective_columns": sum(r.get("convective", 0) for r in report)}))
