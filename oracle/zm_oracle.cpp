@@ -13,7 +13,7 @@
 // Python and executes it (zm_convi, zm_convr with buoyan_dilute / buoyan / parcel_dilute / entropy /
 // enthalpy / ientropy / ienthalpy / qsat_hPa / cldprp / closure / q1q2_pjr inside, zm_conv_evap,
 // momtran, convtran; also geopotential_t and convect_diagnostics_calc); the committed fixtures
-// tests/golden/reftext_*.npz hold its outputs for 16 configurations and a 507-column sweep, and the glibc-libm build of this
+// tests/golden/reftext_*.npz hold its outputs for 18 configurations and a 507-column sweep, and the glibc-libm build of this
 // oracle reproduces every one of them BIT FOR BIT (tests/test_oracle.py::
 // test_oracle_equals_reference_source_text).  What stays unpinned: the arithmetic of modules that
 // are not in the reference tree (zm_externals.hpp: qsat_water, the qsat table, cldfrc_fice,

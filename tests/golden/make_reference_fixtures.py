@@ -422,7 +422,27 @@ def _st_high_pbl(inp, c):
     inp["landfrac"][:] = np.linspace(0.0, 1.0, inp["landfrac"].size)
 
 
-STRESS = {"cold": _st_cold, "near_saturated": _st_near_saturated, "low_pbl_big_tpert": _st_low_pbl_big_tpert,
+def _pick_columns(inp, cols, col0=20000, p_conv=0.1):
+    """Replace the chunk by hand-picked columns of the seeded generator (column j <- global column col0 + cols[j])."""
+    L = inp["t"].shape[0]
+    for j, idx in enumerate(cols):
+        one = S.make_chunks(1, L, 1, p_conv=p_conv, col0=col0 + idx)
+        for k in inp:
+            inp[k][..., j] = getattr(one, k)[0][..., 0]
+
+
+# cam3: columns 969, 4568, 8331, 18573, 20141 (+20000) have an undilute CAPE of 10-24 J/kg (below capelmt) and a dilute
+# CAPE of 0 -- they show what the second buoyan_dilute call (zm_conv.F90:1080-1091, all ncol columns) does to columns
+# outside the first gather, and that a chunk without any first-gather column returns before it (zm_conv.F90:917).
+def _st_cam3_partial(inp, c):
+    _pick_columns(inp, [969, 8, 4568, 22, 0, 8331, 24, 1, 18573, 28, 20141, 36, 2, 37, 3, 39])
+
+
+def _st_cam3_idle(inp, c):
+    _pick_columns(inp, [969, 0, 4568, 1, 8331, 2, 18573, 3, 20141, 4, 5, 6, 7, 9, 10, 11])
+
+
+STRESS = {"cam3_partial": _st_cam3_partial, "cam3_idle": _st_cam3_idle, "cold": _st_cold, "near_saturated": _st_near_saturated, "low_pbl_big_tpert": _st_low_pbl_big_tpert,
           "high_pbl": _st_high_pbl}
 
 CASES = [
@@ -441,6 +461,10 @@ CASES = [
     dict(name="strong_entrainment_L32", ncols=16, pver=32, p_conv=1.0,
          nl={"dmpdz": -2.5e-3, "tau": 1800.0, "c0_lnd": 0.0059, "c0_ocn": 0.045, "ke": 1.0e-6, "momcu": 0.4,
              "momcd": 0.4}, col0=11500, tracer_edge=True),
+    dict(name="cam3_partial_second_pass_L32", ncols=16, pver=32, p_conv=0.1, nl={"num_cin": 5}, cam3=True, col0=20000,
+         transform="cam3_partial"),
+    dict(name="cam3_idle_chunk_L32", ncols=16, pver=32, p_conv=0.1, nl={"num_cin": 5}, cam3=True, col0=20000,
+         transform="cam3_idle"),
     dict(name="stress_cold_L32", ncols=16, pver=32, p_conv=1.0, nl={}, col0=12300, transform="cold"),
     dict(name="stress_near_saturated_L32", ncols=16, pver=32, p_conv=1.0, nl={}, col0=13100, transform="near_saturated"),
     dict(name="stress_low_pbl_L32", ncols=16, pver=32, p_conv=1.0, nl={}, col0=13900, transform="low_pbl_big_tpert"),

@@ -92,7 +92,7 @@ def dpdry_gathered(ch, ref, pdeldry):
 REFTEXT_CASES = ["config1_L32", "mixed_ragged_L32", "parcel_pbl_L58", "num_cin3_L32", "no_deep_pbl_L32",
                  "not_master_L32", "zm_org_L32", "cam3_L32", "parcel_pbl_numcin5_L32", "pcols24_L26",
                  "single_column_L32", "strong_entrainment_L32", "stress_cold_L32", "stress_near_saturated_L32",
-                 "stress_low_pbl_L32", "stress_high_pbl_L32"]
+                 "stress_low_pbl_L32", "stress_high_pbl_L32", "cam3_partial_second_pass_L32", "cam3_idle_chunk_L32"]
 REFTEXT_CONVR = ["prec", "jctop", "jcbot", "qtnd", "heat", "mcon", "cme", "cape", "eurt", "dlf", "pflx", "zdu", "rprd",
                  "mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg", "ideep", "ql", "rliq", "dif", "dnlf",
                  "dnif", "rice"]
