@@ -18,6 +18,8 @@ for case in range(ncases):
     pver = int(rng.choice([24, 26, 32, 32, 32, 58, 72]))
     pcols = int(rng.choice([8, 16, 16, 16, 24, 48, 128]))
     ncols = int(rng.integers(1, 6000))
+    if rng.random() < 0.12:                   # a few large batches: the pipelined host API cuts them into sub-batches
+        ncols = int(rng.integers(16000, 60000))
     pconv = float(rng.choice([0.0, 0.1, 0.35, 0.6, 1.0]))
     seed = int(rng.integers(1, 2**31))
     over = dict(OPTS[int(rng.integers(0, len(OPTS)))])
@@ -51,8 +53,40 @@ for case in range(ncases):
             assert_same(out, ref, TEND_KEYS + ["orgt", "org2d"], pcols, exact=True, what=f"fuzz case {case} (zm_conv_tend, zm_org)")
         else:                                     # the whole zm_conv_tend sequence
             ref = o.conv_tend_batch(ch)
-            out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
-            assert_same(out, ref, TEND_KEYS, pcols, exact=True, what=f"fuzz case {case} (zm_conv_tend)")
+            mirror = bool(rng.random() < 0.5)     # pbuf mass-flux fields stay on the device, zm_conv_tend_2 follows
+            out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt, keep_pbuf_on_device=mirror)
+            keys = [k for k in TEND_KEYS if k not in ("mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg")] if mirror else TEND_KEYS
+            assert_same(out, ref, keys, pcols, exact=True, what=f"fuzz case {case} (zm_conv_tend, mirror={mirror})")
+            if mirror and ncols <= 3000:
+                ncnst = int(rng.integers(2, 10))
+                q, fracis, pdeldry = S.make_tracers(ch, ncnst)
+                do = [0] + [int(x) for x in rng.integers(0, 2, ncnst - 1)]
+                dry = [int(x) for x in rng.integers(0, 2, ncnst)]
+                dq = Z.zm_conv_tend_2(do, q, pdeldry, fracis, ch.ztodt, dry)
+                dpdry = dpdry_gathered(ch, ref, pdeldry)
+                for c in range(ch.nchunks):
+                    r = o.convtran(do, q[c], ref["mu"][c], ref["md"][c], ref["du"][c], ref["eu"][c], ref["ed"][c],
+                                   ref["dp"][c], ref["dsubcld"][c], ref["jt"][c], ref["maxg"][c], ref["ideep"][c],
+                                   ref["lengath"][c], fracis[c], dpdry[c], ch.ztodt, dry)
+                    for m in range(ncnst):
+                        assert np.array_equal(dq[c, m], r[m] if do[m] else np.zeros_like(r[m])), ("tend_2", case, c, m)
+            if kind == 1 and ncols <= 2000:       # N4: geopotential_t (both branches) and convect_diagnostics_calc
+                zvir = np.full_like(ch.t, S.ZVIR); rair = np.full_like(ch.t, S.RAIR)
+                piln, rpdel = np.log(ch.pint), 1.0 / ch.pdel
+                lr = bool(rng.random() < 0.5)
+                zi, zm = Z.geopotential_t(ch.ncol, piln, np.log(ch.pmid), ch.pint, ch.pmid, ch.pdel, rpdel, ch.t, ch.q,
+                                          rair, S.GRAVIT, zvir, dycore_lr=lr)
+                dg = Z.convect_diagnostics_calc(ch.ncol, ref["mcon"], ref["dlf"], ref["rliq"], ch.pmid, ref["rprd"],
+                                                ref["jctop"], ref["jcbot"])
+                for c in range(ch.nchunks):
+                    n = int(ch.ncol[c])
+                    rzi, rzm = o.geopotential_t(n, lr, piln[c], ch.pint[c], ch.pmid[c], ch.pdel[c], rpdel[c], ch.t[c],
+                                                ch.q[c], rair[c], S.GRAVIT, zvir[c])
+                    assert np.array_equal(zi[c][:, :n], rzi[:, :n]) and np.array_equal(zm[c][:, :n], rzm[:, :n]), ("geopotential", case, c)
+                    r = o.convect_diagnostics(n, ref["mcon"][c], ref["dlf"][c], ref["rliq"][c], ch.pmid[c], ref["rprd"][c],
+                                              ref["jctop"][c], ref["jcbot"][c])
+                    for k in r:
+                        assert np.array_equal(dg[k][c][..., :n], r[k][..., :n]), ("convect_diagnostics", case, c, k)
         if kind == 2 and ncols <= 3000:           # convtran over a random constituent set (zeros / negatives included)
             ncnst = int(rng.integers(2, 14))
             q, fracis, pdeldry = S.make_tracers(ch, ncnst)

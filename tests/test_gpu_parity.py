@@ -560,3 +560,17 @@ def test_convtran_zero_and_negative_tracers(built):
         for m in range(1, ncnst):
             assert np.array_equal(dq[c, m], r[m]), (c, m)
     assert np.all(dq[:, 5] == 0.0) and np.count_nonzero(dq) > 0 and np.all(np.isfinite(dq))
+
+
+def test_randomised_parity_sweep(built):
+    """A short run of scripts/parity_fuzz.py (random seeds, sizes, pcols, level counts, options, perturbed soundings;
+    zm_convr / zm_conv_tend / zm_org / device mirror + zm_conv_tend_2 / convtran / N4 routines, bit-exact vs the
+    oracle).  The 160-case run of round 1 is profiles/parity_fuzz_r1_*.log."""
+    import subprocess, sys, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "parity_fuzz.py"), "24", "101"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    summary = json.loads(r.stdout.strip().splitlines()[-1])
+    assert summary["cases"] == 24 and summary["all_bit_exact"]
+    init_cuda(16, 32)
