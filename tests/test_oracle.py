@@ -315,3 +315,17 @@ def test_oracle_equals_reference_source_text_sweep():
         if not np.array_equal(np.asarray(a, float), np.asarray(b, float)):
             bad.append(k)
     assert not bad, bad
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/physics"),
+                    reason="executes the reference source text: build container only, never on the GPU box")
+def test_oracle_equals_reference_source_text_random_chunks():
+    """A short run of tests/golden/reference_text_fuzz.py: random chunks / namelist values / zm_org / cam3 / perturbed
+    soundings through the reference text and the glibc-libm oracle, bit for bit (the 300-case run of round 1 is
+    profiles/reference_text_fuzz_r1_*.log)."""
+    import subprocess, sys, json
+    r = subprocess.run([sys.executable, os.path.join(GOLD, "reference_text_fuzz.py"), "8", "515"],
+                       capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    s = json.loads(r.stdout.strip().splitlines()[-1])
+    assert s["cases"] == 8 and s["oracle_equals_reference_text_bit_for_bit"]
