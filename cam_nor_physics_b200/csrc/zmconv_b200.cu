@@ -420,16 +420,23 @@ int convtran_launch(Workspace& ws, cudaStream_t s, TranArgs a, const int* doconv
 // ---- zm_conv_tend glue (zm_conv_intr.F90:662-836) ------------------------------------------------
 // state1 after physics_update(ptend_loc of zm_convr): physics_types.F90:322-329 (q + qneg3 clip at
 // qmin(1)=1e-12) and :427 (t += s*dt/cpair); winds(:,:,1:2) = state1%u,v (zm_conv_intr.F90:815-816)
+// PART 0: both; 1: t1, q1 only (what zm_conv_evap needs); 2: winds only (what momtran needs) -- the two halves run on
+// the two branches of the evap / momtran fork
+template <int PART>
 __global__ void k_state_update(int n2, int nper, const double* t, const double* q, const double* heat,
                                const double* qtnd, const double* u, const double* v, double ztodt,
                                double* t1, double* q1, double* winds) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += gridDim.x * blockDim.x) {
-    t1[e] = t[e] + heat[e] * ztodt / P.cpair;
-    double qn = q[e] + qtnd[e] * ztodt;
-    q1[e] = (qn < 1.e-12) ? 1.e-12 : qn;
-    int c = e / nper, r = e - c * nper;            // nper = pcols*pver
-    winds[(size_t)c * 2 * nper + r] = u[e];
-    winds[(size_t)c * 2 * nper + nper + r] = v[e];
+    if (PART != 2) {
+      t1[e] = t[e] + heat[e] * ztodt / P.cpair;
+      double qn = q[e] + qtnd[e] * ztodt;
+      q1[e] = (qn < 1.e-12) ? 1.e-12 : qn;
+    }
+    if (PART != 1) {
+      int c = e / nper, r = e - c * nper;            // nper = pcols*pver
+      winds[(size_t)c * 2 * nper + r] = u[e];
+      winds[(size_t)c * 2 * nper + nper + r] = v[e];
+    }
   }
 }
 // ptend_all = sum of the three ptend_loc (physics_ptend_sum, physics_types.F90:698-844) and the
@@ -963,13 +970,11 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
     CK(cudaStreamWaitEvent(s, hooks->late_inputs, 0));    // u, v, cld have arrived
   }
   const int nper = (int)(pc * L);
-  k_state_update<<<1184, 256, 0, s>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
-  ++tls_launches;
-  tick(ws, s, "state_update");
   EvapArgs ea{nchunks, ncol, t1, pmid, pdel, q1, landfrac, rprd, cld, ev_s, snwprd, snwevmlt, ev_q,
               prec, snow, ntprprd, ntsnprd, flxprec, flxsnow, ztodt};
   // zm_conv_evap and momtran both depend only on zm_convr's outputs (zm_conv_intr.F90:764, 822): evap
-  // goes to a side stream and overlaps momtran (kept serial while per-kernel profiling is on)
+  // (with the t, q half of the state update) goes to a side stream and overlaps momtran (which only waits for
+  // the wind half); kept serial while per-kernel profiling is on
   const bool fork = !g_profile;
   if (fork) {
     if (!ws.side) {
@@ -979,7 +984,14 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
     }
     CK(cudaEventRecord(ws.ev_fork, s));
     CK(cudaStreamWaitEvent(ws.side, ws.ev_fork, 0));
+    k_state_update<1><<<1184, 256, 0, ws.side>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
+    k_state_update<2><<<1184, 256, 0, s>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
+    tls_launches += 2;
+  } else {
+    k_state_update<0><<<1184, 256, 0, s>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
+    ++tls_launches;
   }
+  tick(ws, s, "state_update");
   rc = evap_launch(fork ? ws.side : s, ea);
   if (rc) return rc;
   if (g_params.zm_org) {     // zm_conv_intr.F90:773-777 (needs evapcdp = ev_q)
