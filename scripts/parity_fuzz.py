@@ -27,6 +27,8 @@ for case in range(ncases):
     o, _, rc = get_oracle("pm", pcols, pver, **over)
     assert rc == 0, (rc, over)
     ch = S.make_chunks(ncols, pver, pcols, p_conv=pconv, seed=seed)
+    if rng.random() < 0.3:                     # ragged chunks everywhere, not only at the end (CAM chunks differ in ncol)
+        ch.ncol[...] = rng.integers(1, pcols + 1, ch.ncol.shape).astype(ch.ncol.dtype)
     perturbed = bool(rng.random() < 0.35)
     if perturbed:                             # level-wise noise: super-saturated / very dry layers, inversions, odd PBLs
         ch.t[...] = ch.t + rng.normal(0.0, 2.5, ch.t.shape)
