@@ -10,7 +10,10 @@
 //     device-side worklist so that later kernels run only on convective columns and the host
 //     never synchronises inside a step;
 //   * pass 2 of the dilute CAPE runs only on pass-1 triggered columns (the others are provably
-//     unchanged: their dmpdz row is untouched, zm_conv.F90:544,1053,1074);
+//     unchanged: their dmpdz row is untouched, zm_conv.F90:544,1053,1074); after cam3's undilute first
+//     pass it runs on every column of the chunks that have a first-gather column, as the reference does;
+//   * both CAPE passes take their columns from a list bucketed by parcel launch level, most levels
+//     first (k_order_*): a warp lasts as long as its longest lane, and the level count decides that;
 //   * cldprp + closure + q1q2_pjr + scatter + precipitation are one fused per-column kernel;
 //   * zm_conv_evap / momtran are thread-per-column level scans; convtran is a 2-D
 //     (gathered column x constituent) grid.
