@@ -18,8 +18,14 @@ for case in range(ncases):
     pver = int(rng.choice([24, 26, 32, 32, 32, 58, 72]))
     pcols = int(rng.choice([8, 16, 16, 16, 24, 48, 128]))
     ncols = int(rng.integers(1, 6000))
+    for k in ("ZM_TEND_SUBBATCHES", "ZM_TEND_SCHEDULE"):
+        os.environ.pop(k, None)
     if rng.random() < 0.12:                   # a few large batches: the pipelined host API cuts them into sub-batches
         ncols = int(rng.integers(16000, 60000))
+        mode = int(rng.integers(0, 4))        # default ramp / equal parts / explicit sixteenths / unpipelined
+        if mode == 1: os.environ["ZM_TEND_SUBBATCHES"] = str(int(rng.integers(2, 9)))
+        if mode == 2: os.environ["ZM_TEND_SCHEDULE"] = str(rng.choice(["1,2,3,4,6", "2,2,4,8", "1,1,1,1,4,8", "8,8"]))
+        if mode == 3: os.environ["ZM_TEND_SUBBATCHES"] = "1"
     pconv = float(rng.choice([0.0, 0.1, 0.35, 0.6, 1.0]))
     seed = int(rng.integers(1, 2**31))
     over = dict(OPTS[int(rng.integers(0, len(OPTS)))])
