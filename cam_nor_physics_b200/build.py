@@ -7,9 +7,9 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "zmconv_b200.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in
-        ("zmconv_b200.cu", "zm_math.h", "zm_device.cuh", "zm_kernels.cuh", "zm_plume_warp.cuh",
-         "zm_transport.cuh")] + [os.path.join(os.path.dirname(HERE), "include", "zmconv_b200.h")]
+import glob
+DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")) + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) +
+              glob.glob(os.path.join(HERE, "csrc", "*.h"))) + [os.path.join(os.path.dirname(HERE), "include", "zmconv_b200.h")]
 LIB = os.path.join(HERE, "libzmconv_b200.so")
 
 NVCC_FLAGS = [

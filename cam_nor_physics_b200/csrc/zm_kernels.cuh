@@ -206,6 +206,7 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   extern __shared__ double sm_buoy[];               // [pver+2][blockDim.x]
   constexpr bool PAIR = LAT;                         // paired bracket evaluation only where latency-bound
   zmm::hot_tables_load();                            // before any early return (block-wide barrier inside)
+  zmm::hot_svp_load();
   const int pcols = P.pcols, pver = P.pver, msg = P.msg;
   const int ncolpad = in.nchunks * pcols;
   const int nthr = blockDim.x;

@@ -20,6 +20,7 @@
 #pragma once
 #include <stdint.h>
 #include "zm_math_tables.h"
+#include "zm_svp_table.h"
 #if !defined(__CUDACC__)
 #include <math.h>
 #include <string.h>
@@ -33,9 +34,11 @@ namespace zmm {
 #if defined(__CUDACC__)
 __device__ const double d_log_tab[384] = ZMM_LOG_TAB_VALUES;
 __device__ const double d_exp2_tab[256] = ZMM_EXP2_TAB_VALUES;
+__device__ __align__(16) const double d_svp_tab[ZMM_SVP_NCELL * ZMM_SVP_NCOEF] = ZMM_SVP_TAB_VALUES;
 #endif
 static const double h_log_tab[384] = ZMM_LOG_TAB_VALUES;
 static const double h_exp2_tab[256] = ZMM_EXP2_TAB_VALUES;
+static const double h_svp_tab[ZMM_SVP_NCELL * ZMM_SVP_NCOEF] = ZMM_SVP_TAB_VALUES;
 
 #if defined(__CUDACC__)
 // Shared-memory copies used by the *_hot variants (one LDS.128 per entry instead of __ldg loads that each
@@ -44,12 +47,21 @@ static const double h_exp2_tab[256] = ZMM_EXP2_TAB_VALUES;
 __shared__ double2 s_log_a[128];      // (invc, logc_hi)
 __shared__ double  s_log_b[128];      // logc_lo
 __shared__ double2 s_exp2[128];       // (2^(j/128) hi, lo)
+// saturation vapour pressure cells, 80 bytes each: consecutive cells start 20 banks apart, so the eight lanes of an
+// LDS.128 phase that read eight different cells spread over all 32 banks
+__shared__ double2 s_svp[ZMM_SVP_NCELL * ZMM_SVP_NCOEF / 2];
 __device__ __forceinline__ void hot_tables_load() {
   for (int i = threadIdx.x; i < 128; i += blockDim.x) {
     s_log_a[i] = make_double2(d_log_tab[3 * i], d_log_tab[3 * i + 1]);
     s_log_b[i] = d_log_tab[3 * i + 2];
     s_exp2[i] = make_double2(d_exp2_tab[2 * i], d_exp2_tab[2 * i + 1]);
   }
+  __syncthreads();
+}
+// kernels that evaluate svp_water<true> (the state function of the CAPE passes) call this as well
+__device__ __forceinline__ void hot_svp_load() {
+  for (int i = threadIdx.x; i < ZMM_SVP_NCELL * ZMM_SVP_NCOEF / 2; i += blockDim.x)
+    s_svp[i] = make_double2(d_svp_tab[2 * i], d_svp_tab[2 * i + 1]);
   __syncthreads();
 }
 #endif
@@ -157,11 +169,41 @@ ZM_HD double log_fixup(double x, double res) {
   return ok ? res : sp;
 }
 
-// natural log, < 0.6 ulp
-ZM_HD double log_(double x) {
-  double hi, lo; log_core(x, hi, lo);
-  return log_fixup(x, hi);
+// Natural log in one double, < 0.6 ulp: the same reduction as log_core (x = 2^k z, r = z*invc - 1, |r| < 0.004),
+//   log x = (k ln2 + logc) + r - r^2/2 + r^3 (1/3 - r/4 + ... - r^5/8)
+// with one compensated step (hi + lo = w + r exactly, |w| >= |r| or w = 0) instead of the double-double bookkeeping
+// log10 / pow need: 19 floating-point operations against 28.  HOT = true: positive NORMAL finite x only.
+template <bool HOT> ZM_HD double log1_t(double x) {
+  uint64_t ix = d2u(x);
+  bool sub = false;
+  if (!HOT) {
+    sub = ix < 0x0010000000000000ULL;
+    const uint64_t ixs = d2u(x * 18014398509481984.0);
+    ix = sub ? ixs : ix;
+  }
+  const uint64_t tmp = ix - 0x3fe5f00000000000ULL;
+  const int i = (int)((tmp >> 45) & 127);
+  int k = (int)((int64_t)tmp >> 52);
+  if (!HOT) k = sub ? k - 54 : k;
+  const double z = u2d(ix - (tmp & 0xfff0000000000000ULL));
+  double invc, lch, lcl;
+  log_entry<HOT>(i, invc, lch, lcl);
+  const double r = fma(z, invc, -1.0);
+  const double kd = (double)k;
+  const double w = fma(kd, ZMM_LN2_HI32, lch);            // exact: both are multiples of 2^-32
+  const double hi = w + r;
+  const double lo = ((w - hi) + r) + fma(kd, ZMM_LN2_LO32, lcl);
+  const double r2 = r * r;
+  const double r4 = r2 * r2;
+  const double r3 = r2 * r;
+  const double p01 = fma(r, -0.25, 0.3333333333333333);
+  const double p23 = fma(r, -0.16666666666666666, 0.2);
+  const double p45 = fma(r, -0.125, 0.14285714285714285);
+  const double p = fma(r4, p45, fma(r2, p23, p01));
+  const double t = fma(-0.5, r2, lo);
+  return fma(r3, p, t) + hi;
 }
+ZM_HD double log_(double x) { return log_fixup(x, log1_t<false>(x)); }
 
 // log10, < 0.6 ulp
 ZM_HD double log10_(double x) {
@@ -173,10 +215,7 @@ ZM_HD double log10_(double x) {
 }
 
 // Hot variants: identical bits to log_/log10_ for positive normal finite x, no special-case selects.
-ZM_HD double log_hot(double x) {
-  double hi, lo; log_core_t<true>(x, hi, lo);
-  return hi;
-}
+ZM_HD double log_hot(double x) { return log1_t<true>(x); }
 ZM_HD double log10_hot(double x) {
   double hi, lo; log_core_t<true>(x, hi, lo);
   const double p  = hi * ZMM_INVLN10_HI;
@@ -234,6 +273,67 @@ ZM_HD double pow10_hot(double x) {
   const double yh = x * ZMM_LOG2_10_HI;
   const double yl = fma(x, ZMM_LOG2_10_HI, -yh) + x * ZMM_LOG2_10_LO;
   return exp2_dd_t<true>(yh, yl);
+}
+
+// ---- Goff-Gratch saturation vapour pressure over water, Pa ----------------------------------------------------
+// The formula as CAM's wv_sat_methods codes it (GoffGratch_svp_water; reached from zm_conv.F90:5423,5433 through
+// wv_saturation::qsat_water).  log10(1013.246) is a compile-time constant in the reference build.
+ZM_HD double svp_water_formula(double t) {
+  const double tboil = 373.16;
+  return pow10_(-7.90298 * (tboil / t - 1.0) + 5.02808 * log10_(tboil / t) -
+                1.3816e-7 * (pow10_(11.344 * (1.0 - t / tboil)) - 1.0) +
+                8.1328e-3 * (pow10_(-3.49149 * (tboil / t - 1.0)) - 1.0) + 3.0057148979490314) * 100.0;
+}
+#if defined(__CUDACC__)
+__device__ __noinline__ double svp_water_formula_cold(double t) { return svp_water_formula(t); }
+#endif
+// The same function from the per-kelvin polynomials of zm_svp_table.h (scripts/gen_svp_table.py): for
+// ZMM_SVP_T0 - 0.5 <= t < ZMM_SVP_T0 + ZMM_SVP_NCELL - 0.5 one table cell and 12 multiply-adds (the formula costs
+// three 10**x, one log10 and two divisions, and in double it carries +-2 ulp from the rounding of its exponent
+// alone, tens of ulp below 200 K); < 2 ulp against the formula in 300-bit arithmetic; outside the table the formula.
+// The cell is the integer nearest to t: t + 1.5*2^52 rounds t to that integer and leaves it in the low word of
+// the sum (no float<->int conversion on the dependency chain); x = t - centre is exact, |x| <= 0.5.
+// HOT = true reads the table from shared memory (hot_svp_load()).
+template <bool HOT> ZM_HD double svp_water(double t) {
+  if (!(t >= ZMM_SVP_T0 - 0.5 && t < ZMM_SVP_T0 + (ZMM_SVP_NCELL - 0.5))) {
+#if defined(__CUDA_ARCH__)
+    return svp_water_formula_cold(t);
+#else
+    return svp_water_formula(t);
+#endif
+  }
+  const double y = t + 6755399441055744.0;                 // 1.5 * 2^52
+  const int i = (int)(uint32_t)d2u(y) - (int)ZMM_SVP_T0;   // round(t) - T0
+  const double x = t - (y - 6755399441055744.0);
+  double c0, c1, c2, c3, c4, c5, c6, c7, c8, c9;
+#if defined(__CUDA_ARCH__)
+  if (HOT) {
+    const double2* cc = &s_svp[i * (ZMM_SVP_NCOEF / 2)];
+    const double2 a = cc[0], b = cc[1], c = cc[2], d = cc[3], e = cc[4];
+    c0 = a.x; c1 = a.y; c2 = b.x; c3 = b.y; c4 = c.x; c5 = c.y; c6 = d.x; c7 = d.y; c8 = e.x; c9 = e.y;
+  } else {
+    const double2* cc = reinterpret_cast<const double2*>(d_svp_tab) + i * (ZMM_SVP_NCOEF / 2);
+    const double2 a = __ldg(cc), b = __ldg(cc + 1), c = __ldg(cc + 2), d = __ldg(cc + 3), e = __ldg(cc + 4);
+    c0 = a.x; c1 = a.y; c2 = b.x; c3 = b.y; c4 = c.x; c5 = c.y; c6 = d.x; c7 = d.y; c8 = e.x; c9 = e.y;
+  }
+#else
+  const double* cc = h_svp_tab + i * ZMM_SVP_NCOEF;
+  c0 = cc[0]; c1 = cc[1]; c2 = cc[2]; c3 = cc[3]; c4 = cc[4]; c5 = cc[5]; c6 = cc[6]; c7 = cc[7]; c8 = cc[8]; c9 = cc[9];
+#endif
+  // es = c0 + x*(c1 + c2 x + ... + c9 x^8): the bracket by Estrin's scheme (depth 4), c0 added last so that
+  // the result carries one dominant rounding
+  const double x2 = x * x;
+  const double x4 = x2 * x2;
+  const double x8 = x4 * x4;
+  const double p12 = fma(c2, x, c1);
+  const double p34 = fma(c4, x, c3);
+  const double p56 = fma(c6, x, c5);
+  const double p78 = fma(c8, x, c7);
+  const double q0 = fma(p34, x2, p12);
+  const double q1 = fma(p78, x2, p56);
+  const double r0 = fma(q1, x4, q0);
+  const double tl = fma(c9, x8, r0);
+  return fma(x, tl, c0);
 }
 
 // a / b given rb = RN(1/b) (correctly rounded reciprocal of a fixed divisor): first quotient estimate plus

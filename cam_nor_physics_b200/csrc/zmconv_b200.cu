@@ -250,7 +250,7 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   auto k_plm = pl_ld == 34 ? k_plume_w<34> : (pl_ld == 66 ? k_plume_w<66> : k_plume_w<130>);
   CK(cudaFuncSetAttribute(k_cld1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
   CK(cudaFuncSetAttribute(k_plm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
-  if (smem > 48 * 1024) {
+  {   // static tables (22 KB) + the buoyancy rows exceed the 48 KB default: opt in (dynamic part)
     CK(cudaFuncSetAttribute(k_buoyan_dilute<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute((k_buoyan_dilute<1, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_buoyan_dilute<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -522,6 +522,7 @@ __global__ void k_dpdry_gather(int nchunks, const int* ideep, const int* lengath
 // ---- diagnostics kernels ----------------------------------------------------------------------
 __global__ void k_math_eval(int id, int n, const double* x, const double* y, double* o) {
   zmm::hot_tables_load();
+  zmm::hot_svp_load();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   switch (id) {
@@ -534,12 +535,16 @@ __global__ void k_math_eval(int id, int n, const double* x, const double* y, dou
     case 7: o[i] = zmm::pow10_hot(x[i]); break;
     case 8: o[i] = zmm::div_rcp(x[i], y[i], 1.0 / y[i]); break;
     case 9: o[i] = div_hot(x[i], y[i]); break;
+    case 10: o[i] = zmm::svp_water<false>(x[i]); break;
+    case 11: o[i] = zmm::svp_water_formula(x[i]); break;
+    case 12: o[i] = zmm::svp_water<true>(x[i]); break;
     default: o[i] = zmm::pow_(x[i], y[i]); break;
   }
 }
 __global__ void k_thermo_eval(int id, int n, const double* a, const double* b, const double* c,
                               const double* d, const double* e, double* o0, double* o1) {
   zmm::hot_tables_load();
+  zmm::hot_svp_load();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double r0 = 0.0, r1 = 0.0;
@@ -556,6 +561,7 @@ __global__ void k_thermo_eval(int id, int n, const double* a, const double* b, c
 // single-warp latency microbenchmark (cycles per dependent call), see zm_microbench
 __global__ void k_microbench(double* out, long long* cyc, int n) {
   zmm::hot_tables_load();
+  zmm::hot_svp_load();
   double x = 290.0 + threadIdx.x * 0.01, acc = 0.0, q;
   long long t0, t1;
   int j = 0;
@@ -571,13 +577,20 @@ __global__ void k_microbench(double* out, long long* cyc, int n) {
   MB(x = 300.0 + 1e-3 * zmm::pow10_(x * 1e-2));                          // 3 pow10
   MB(x = 300.0 + 1e-3 * zmm::exp_(x * 1e-2));                            // 4 exp
   MB(x = 300.0 + 1e-6 * gg_svp_water(x));                                // 5 goff-gratch
-  MB(x = 300.0 + 1e-9 * state_fn(1, x, 900.0, 0.015, 500.0, q));         // 6 enthalpy
-  MB(x = 300.0 + 1e-6 * state_fn(0, x, 900.0, 0.015, 0.0, q));           // 7 entropy
-  MB(invert_k<true>(1, 3.5e5 + x, 900.0, 500.0, 0.015, 295.0, acc, q); x = 290.0 + 1e-3 * acc);  // 8 ienthalpy
-  MB(invert_k<true>(0, 250.0 + 1e-3 * x, 900.0, 0.0, 0.015, 295.0, acc, q); x = 290.0 + 1e-3 * acc);  // 9 ientropy
+  MB(x = 300.0 + 1e-9 * enthalpy_q(x, 900.0, 0.015, 500.0, q));          // 6 enthalpy
+  MB(x = 300.0 + 1e-6 * entropy_q(x, 900.0, 0.015, q));                  // 7 entropy
+  MB(invert_k<1>(3.5e5 + x, 900.0, 500.0, 0.015, 295.0, acc, q); x = 290.0 + 1e-3 * acc);  // 8 ienthalpy
+  MB(invert_k<0>(250.0 + 1e-3 * x, 900.0, 0.0, 0.015, 295.0, acc, q); x = 290.0 + 1e-3 * acc);  // 9 ientropy
   MB(x = 300.0 + 1e-3 * zmm::pow_(x, 0.2857));                           // 10 pow
-  { double f1, f2, q1, q2;
-    MB(state_fn_dual(x, 900.0, 0.015, 500.0, x + 1.0, 900.0, 0.015, f1, q1, f2, q2); x = 300.0 + 1e-9 * f1 + 1e-6 * f2); }  // 11 dual
+  MB(x = 300.0 + 1e-6 * zmm::svp_water_formula(x));                      // 11 goff-gratch formula
+  MB(x = fma(x, 0.999999, 1e-4));                                        // 12 dependent DFMA
+  MB(x = x + 1e-9);                                                      // 13 dependent DADD
+  MB(x = x * 1.0000001);                                                 // 14 dependent DMUL
+  MB(x = 300.0 + 1e-3 * div_hot(373.16, x));                             // 15 div_hot
+  MB(x = 300.0 + 1e-3 * zmm::log_hot(x));                                // 16 log_hot
+  MB(x = 300.0 + 1e-6 * zmm::svp_water<true>(x));                        // 17 svp table (shared memory)
+  MB(x = (x > 300.5) ? x - 0.75 : x + 0.5);                              // 18 DSETP + select
+  MB(x = (double)((int)x) + 0.25);                                       // 19 F2I + I2F
   out[threadIdx.x] = x + acc;
 }
 __global__ void k_fp64_peak(double* out, int iters) {
@@ -641,12 +654,7 @@ int zm_init(const zm_params_t* p) {
   CK(cudaMemcpyToSymbol(P, &d, sizeof d));
   // CAM's estbl table (wv_saturation): svp_trans at 1-K steps from 127.16 K, ttrice = 20 K
   double tbl[ZM_ESTBL_LEN];
-  auto svp_w = [](double t) {
-    const double tb = 373.16;
-    return zmm::pow10_(-7.90298 * (tb / t - 1.0) + 5.02808 * zmm::log10_(tb / t) -
-                       1.3816e-7 * (zmm::pow10_(11.344 * (1.0 - t / tb)) - 1.0) +
-                       8.1328e-3 * (zmm::pow10_(-3.49149 * (tb / t - 1.0)) - 1.0) + 3.0057148979490314) * 100.0;
-  };
+  auto svp_w = [](double t) { return zmm::svp_water<false>(t); };
   auto svp_i = [](double t) {
     const double t3 = 273.16;
     return zmm::pow10_(-9.09718 * (t3 / t - 1.0) - 3.56654 * zmm::log10_(t3 / t) + 0.876793 * (1.0 - t / t3) +
@@ -1443,6 +1451,8 @@ int zm_math_eval_host(int id, int n, const double* x, const double* y, double* o
       case 7: o[i] = zmm::pow10_hot(x[i]); break;
       case 8: o[i] = zmm::div_rcp(x[i], y[i], 1.0 / y[i]); break;
       case 9: o[i] = x[i] / y[i]; break;
+      case 10: case 12: o[i] = zmm::svp_water<false>(x[i]); break;
+      case 11: o[i] = zmm::svp_water_formula(x[i]); break;
       default: o[i] = zmm::pow_(x[i], y[i]); break;
     }
   }
@@ -1472,17 +1482,22 @@ int zm_thermo_eval_dev(int id, int n, const double* a, const double* b, const do
   return S.flush();
 }
 
-// cycles per dependent call, one warp: 0 div,1 log,2 log10,3 pow10,4 exp,5 goff-gratch,
-// 6 enthalpy,7 entropy,8 ienthalpy,9 ientropy,10 pow
-int zm_microbench(long long* cycles11, int n) {
+// cycles per dependent call, one warp (ZM_MICROBENCH_N results): 0 div,1 log,2 log10,3 pow10,4 exp,5 es(T),
+// 6 enthalpy,7 entropy,8 ienthalpy,9 ientropy,10 pow,11 Goff-Gratch formula,12 DFMA,13 DADD,14 DMUL,15 div_hot,
+// 16 log_hot,17 es(T) from shared memory,18 compare+select,19 F2I+I2F.  Writes min(cap, ZM_MICROBENCH_N) values.
+int zm_microbench(long long* cycles, int cap, int n) {
   NEED_INIT();
-  double* d; long long* c;
-  CK(cudaMalloc(&d, 32 * sizeof(double))); CK(cudaMalloc(&c, 16 * sizeof(long long)));
-  CK(cudaMemset(c, 0, 16 * sizeof(long long)));
-  k_microbench<<<1, 32>>>(d, c, n); ++tls_launches;
-  CK(cudaMemcpy(cycles11, c, 12 * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (!cycles || cap <= 0) return 0;
+  double* d = nullptr; long long* c = nullptr;
+  cudaError_t e = cudaMalloc(&d, 32 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&c, ZM_MICROBENCH_N * sizeof(long long));
+  if (e == cudaSuccess) e = cudaMemset(c, 0, ZM_MICROBENCH_N * sizeof(long long));
+  if (e == cudaSuccess) { k_microbench<<<1, 32>>>(d, c, n); ++tls_launches; e = cudaGetLastError(); }
+  const int m = cap < ZM_MICROBENCH_N ? cap : ZM_MICROBENCH_N;
+  if (e == cudaSuccess) e = cudaMemcpy(cycles, c, m * sizeof(long long), cudaMemcpyDeviceToHost);
   cudaFree(d); cudaFree(c);
-  return 0;
+  if (e != cudaSuccess) { tls_err = std::string("zm_microbench: ") + cudaGetErrorString(e); return -100; }
+  return m;
 }
 
 double zm_fp64_peak_flops(int iters) {

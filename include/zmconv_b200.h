@@ -236,8 +236,11 @@ int zm_thermo_eval_dev(int id, int n, const double* a, const double* b, const do
 /* FP64 FMA-chain microbenchmark on the current device: returns achieved FLOP/s (FMA = 2). */
 double zm_fp64_peak_flops(int iters);
 /* single-warp latency microbenchmark: cycles per dependent call of
- * 0 div,1 log,2 log10,3 10**x,4 exp,5 Goff-Gratch es,6 enthalpy,7 entropy,8 ienthalpy,9 ientropy,10 pow */
-int zm_microbench(long long* cycles11, int n);
+ * 0 div,1 log,2 log10,3 10**x,4 exp,5 es(T),6 enthalpy,7 entropy,8 ienthalpy,9 ientropy,10 pow,
+ * 11 Goff-Gratch formula,12 DFMA,13 DADD,14 DMUL,15 div_hot,16 log_hot,17 es(T) shared-memory table,
+ * 18 compare+select,19 F2I+I2F.  Writes min(cap, ZM_MICROBENCH_N) values, returns that count. */
+#define ZM_MICROBENCH_N 20
+int zm_microbench(long long* cycles, int cap, int n);
 /* per-kernel device time (ms) of the last zm_convr_batch[_dev] call made with profiling on:
  * names/ms arrays of length *n (max 16). */
 int zm_set_profiling(int on);

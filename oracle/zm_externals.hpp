@@ -8,7 +8,9 @@
 //   cloud_fraction::cldfrc_fice    zm_conv.F90:18,1809
 // They are restated here from the published CAM algorithms (Goff & Gratch 1946 saturation
 // vapour pressure as coded in CAM's wv_sat_methods; CAM's estblf 1-K table 127.16..375.16 K
-// with a 20 K water/ice transition; cldfrc_fice linear ramps).  PARITY UNPINNED: nothing in
+// with a 20 K water/ice transition; cldfrc_fice linear ramps).  The glibc-libm flavour evaluates the Goff-Gratch
+// formula as written; the portable flavour takes it from the product's per-kelvin polynomial table of the same
+// formula (zm_math.h svp_water, < 1.3 ulp) so that it stays the bit-exact checker of the kernels.  PARITY UNPINNED: nothing in
 // /root/reference holds source, tests or golden values for these call sites, so this header
 // *defines* them for the oracle; the CUDA library restates the same formulas independently
 // (cam_nor_physics_b200/csrc/zm_device.cuh) and the Fortran stubs in fortran/ must mirror it.
@@ -24,6 +26,9 @@ static inline double m_log10(double x) { return zmm::log10_(x); }
 static inline double m_exp(double x)   { return zmm::exp_(x); }
 static inline double m_pow10(double x) { return zmm::pow10_(x); }
 static inline double m_pow(double x, double y) { return zmm::pow_(x, y); }
+// the saturation vapour pressure as the CUDA library evaluates it (per-kelvin polynomials of the Goff-Gratch
+// formula, the formula outside 140..350 K): this flavour is the bit-exact checker of the kernels
+static inline double m_svp_water(double t) { return zmm::svp_water<false>(t); }
 static const char* const math_backend = "portable(zm_math.h)";
 }
 #else
@@ -35,6 +40,7 @@ static inline double m_pow10(double x) { return std::pow(10.0, x); }   // Fortra
 static inline double m_pow(double x, double y) { return std::pow(x, y); }
 static const char* const math_backend = "glibc-libm";
 }
+#define ZMO_SVP_FORMULA 1
 #endif
 
 namespace zmo {
@@ -66,6 +72,9 @@ static inline PhysConst physconst_default() {
 // ---- wv_saturation --------------------------------------------------------------------
 // Goff-Gratch saturation vapour pressure over water (Pa), t in K.
 static inline double gg_svp_water(double t) {
+#ifndef ZMO_SVP_FORMULA
+  return m_svp_water(t);
+#endif
   const double tboil = 373.16;
   return m_pow10(-7.90298 * (tboil / t - 1.0) +
                  5.02808 * m_log10(tboil / t) -

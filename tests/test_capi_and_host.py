@@ -64,6 +64,40 @@ def test_portable_math_accuracy_host(built):
         assert worst < 1.0, (fid, worst)
 
 
+def test_saturation_vapour_pressure_table_host(built):
+    """es(T) over water comes from per-kelvin polynomials of the Goff-Gratch formula (zm_svp_table.h): against the
+    formula in 200-bit arithmetic the table is within 2 ulp over 139.5..349.5 K -- the formula evaluated in double
+    (what the reference runs) is itself tens of ulp off at the cold end -- and the two agree to 2e-14 relative;
+    outside the table the formula is used."""
+    import mpmath as mp
+    from cam_nor_physics_b200 import zm_conv as Z
+    mp.mp.prec = 200
+    c = {k: mp.mpf(float(v)) for k, v in dict(ts="373.16", a="7.90298", b="5.02808", c="1.3816e-7", d="11.344",
+                                               e="8.1328e-3", f="3.49149").items()}
+
+    def svp(t):
+        u = c["ts"] / t
+        ex = (-c["a"] * (u - 1) + c["b"] * mp.log10(u) - c["c"] * (mp.power(10, c["d"] * (1 - t / c["ts"])) - 1)
+              + c["e"] * (mp.power(10, -c["f"] * (u - 1)) - 1) + mp.mpf(3.0057148979490314))
+        return mp.power(10, ex) * 100
+
+    rng = np.random.default_rng(3)
+    T = np.concatenate([rng.uniform(139.5, 349.5, 1500), np.arange(140, 349) + 0.5 + 1e-13, np.arange(140, 349) + 0.5 - 1e-13,
+                        np.arange(140, 349) + 0.5, np.arange(140, 350).astype(float)])      # incl. the cell edges
+    tab, frm = Z.math_eval(10, T, device=False), Z.math_eval(11, T, device=False)
+    worst = 0.0
+    for t, a in zip(T, tab):
+        e = svp(mp.mpf(float(t)))
+        worst = max(worst, float(abs(mp.mpf(float(a)) - e)) / math.ulp(float(e)))
+    assert worst < 2.0, worst
+    assert np.max(np.abs(tab - frm) / frm) < 2e-14
+    warm = T > 200.0
+    assert np.max(np.abs(tab - frm)[warm] / frm[warm]) < 8e-15
+    out = np.array([100.0, 139.499, 349.5, 360.0, 420.0])
+    assert np.array_equal(Z.math_eval(10, out, device=False), Z.math_eval(11, out, device=False))
+    assert np.all(np.diff(Z.math_eval(10, np.linspace(139.0, 350.5, 40001), device=False)) > 0)   # monotone across cells
+
+
 def test_hot_math_variants_equal_general_ones_host(built):
     """The state function uses trimmed transcendentals (no special-case selects) and constant-reciprocal
     divisions; inside their stated domains they must return the same bits as the general ones."""

@@ -10,7 +10,8 @@ import pytest
 
 from cam_nor_physics_b200 import soundings as S
 from helpers import (get_oracle, init_cuda, state_of, assert_same, cuda_convr, dpdry_gathered, CONVR_KEYS,
-                     TEND_KEYS, near_threshold_columns, REFTEXT_CASES, REFTEXT_CONVR, reftext_overrides, RTOL, ATOL)
+                     TEND_KEYS, near_threshold_columns, REFTEXT_CASES, REFTEXT_CONVR, reftext_overrides, RTOL, ATOL,
+                     GATHERED_2D, GATHERED_1D, INT_KEYS)
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -36,6 +37,13 @@ def test_portable_math_device_equals_host(built):
         assert np.array_equal(Z.math_eval(8, a, np.full_like(a, b), device=True), a / b), b
     b = np.exp(rng.uniform(-50, 50, a.size))
     assert np.array_equal(Z.math_eval(9, a, b, device=True), a / b)          # div_hot == IEEE quotient
+    # saturation vapour pressure: global-memory and shared-memory table paths, cell edges, formula fallback
+    ts = np.concatenate([rng.uniform(100, 400, n), np.arange(139, 352) + 0.5, np.arange(139, 352) + 0.5 - 1e-13,
+                         np.arange(139, 352) + 0.5 + 1e-13, np.arange(139, 352) + 0.0])
+    host = Z.math_eval(10, ts, device=False)
+    assert np.array_equal(Z.math_eval(10, ts, device=True), host)
+    assert np.array_equal(Z.math_eval(12, ts, device=True), host)
+    assert np.array_equal(Z.math_eval(11, ts, device=True), Z.math_eval(11, ts, device=False))
 
 
 def test_thermo_scalars_match_oracle(built):
@@ -198,9 +206,20 @@ def test_f09_full_step_vs_oracle(built):
     o2, _, _ = get_oracle("libm", 16, 32)
     ref2 = o2.conv_tend_batch(ch)
     near = near_threshold_columns(ref2["cape"])
-    print("near-threshold columns (reported):", near.tolist())
-    if len(near) == 0:
-        assert_same(out, ref2, TEND_KEYS, 16, exact=False, what="f09 zm_conv_tend vs libm oracle")
+    print("near-threshold columns (reported, left out of the comparison):", near.tolist())
+    # ptend_s / ptend_q are sums of zm_convr's and zm_conv_evap's tendencies that largely cancel below cloud base:
+    # the tolerance is taken against the magnitude of the terms (which are themselves compared against it)
+    cv = o2.convr_batch(ch)
+    cvo = cuda_convr(Z, ch)
+    assert_same(cvo, cv, CONVR_KEYS, 16, exact=False, what="f09 zm_convr vs libm oracle", skip_cols=near)
+    scales = {"ptend_s": np.abs(cv["heat"]) + np.abs(ref2["ptend_s"] - cv["heat"]),
+              "ptend_q": np.abs(cv["qtnd"]) + np.abs(ref2["evapcdp"])}
+    if not len(near):          # gathered outputs shift when a column enters or leaves ideep
+        assert_same(out, ref2, TEND_KEYS, 16, exact=False, what="f09 zm_conv_tend vs libm oracle", scales=scales)
+    else:
+        keys = [k for k in TEND_KEYS if k not in GATHERED_2D + GATHERED_1D + INT_KEYS]
+        assert_same(out, ref2, keys, 16, exact=False, what="f09 zm_conv_tend vs libm oracle", scales=scales,
+                    skip_cols=near)
 
 
 def test_sharding_invariance_and_properties_L58_large(built):
