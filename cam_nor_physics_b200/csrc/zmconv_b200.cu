@@ -79,8 +79,10 @@ struct Workspace {
   }
 };
 // Device-resident copy of the pbuf fields zm_conv_tend hands to zm_conv_tend_2 (ZM_MU..ZM_IDEEP,
-// zm_conv_intr.F90:113-132, 994-1004): they live in the calling thread's staging arena until its next
-// zm_conv_tend_batch call, so convtran2 needs no second H2D of them.
+// zm_conv_intr.F90:113-132, 994-1004): they live in an arena of their own (tls_mirror_ws, touched by nothing but
+// zm_conv_tend_batch) until the calling thread's next zm_conv_tend_batch call, so convtran2 needs no second H2D
+// of them and the calls the model makes in between (geopotential_t, convect_diagnostics_calc, physpkg.F90:2820-2885)
+// cannot disturb them.  Set only when zm_conv_tend_batch succeeded; cleared on entry and on failure.
 struct PbufMirror {
   int nchunks = 0;
   const double *mu = nullptr, *md = nullptr, *du = nullptr, *eu = nullptr, *ed = nullptr, *dp = nullptr, *dsubcld = nullptr;
@@ -91,9 +93,16 @@ thread_local PbufMirror tls_mirror;
 // with zm_org_fields (host pointers for the host-pointer entry points, device pointers for *_dev)
 struct OrgFields { const double* org = nullptr; double* orgt = nullptr; double* org2d = nullptr; };
 thread_local OrgFields tls_org;
+// convtran1 of zm_conv_tend (zm_conv_intr.F90:865-880), attached per call with zm_convtran1_fields: state%q,
+// fracis and ptend_loc%q, (pcols,pver,pcnst) per chunk (host or device pointers like zm_org_fields)
+struct Tran1Fields { int pcnst = 0; const double* q = nullptr; const double* fracis = nullptr; double* ptend_q = nullptr; };
+thread_local Tran1Fields tls_tran1;
+struct Tran1Dev { int ncnst, nactive; const int* active; const int* is_dry; bool any_dry;
+                  const double* q; const double* fracis; double* dqdt; };
 thread_local Workspace tls_work;     // kernel work arrays
 thread_local Workspace tls_stage;    // device staging of user arrays for the host-pointer API
-thread_local Workspace tls_stage2;   // staging for zm_conv_tend_2_batch (must not disturb tls_stage: the mirror lives there)
+thread_local Workspace tls_stage2;   // staging for zm_conv_tend_2_batch
+thread_local Workspace tls_mirror_ws; // the device pbuf mirror (see PbufMirror)
 
 // Streams, events and per-sub-batch work arenas of the pipelined host-pointer zm_conv_tend_batch.
 struct TendPipe {
@@ -121,14 +130,18 @@ struct TendPipe {
     const char* e = getenv("ZM_TEND_SCHEDULE");
     const bool ramp = !(e && !strcmp(e, "uniform")) && !getenv("ZM_TEND_SUBBATCHES") && nchunks >= 16 * 64;
     if (e && strchr(e, ',')) {                 // explicit sizes in sixteenths, e.g. "1,2,3,4,6"
+      // every entry >= 1, at most MAXB entries, sum 16; anything else falls back to the default schedule
       int sizes[MAXB], n = 0, tot = 0;
-      for (const char* p = e; *p && n < MAXB;) {
-        sizes[n] = atoi(p); tot += sizes[n++];
+      bool ok = true;
+      for (const char* p = e; *p;) {
+        const int v = atoi(p);
+        if (v < 1 || n >= MAXB) { ok = false; break; }
+        sizes[n++] = v; tot += v;
         p = strchr(p, ',');
         if (!p) break;
         ++p;
       }
-      if (tot == 16 && nchunks >= 16 * 64) {
+      if (ok && tot == 16 && nchunks >= 16 * 64) {
         sched_nb = n;
         int acc = 0;
         for (int b = 0; b <= n; ++b) { sched_first[b] = (int)((long long)nchunks * acc / 16); if (b < n) acc += sizes[b]; }
@@ -372,16 +385,32 @@ int evap_launch(cudaStream_t s, const EvapArgs& a) {
   return 0;
 }
 
-int momtran_launch(Workspace& ws, cudaStream_t s, MomArgs a, bool own_arena = true) {
+// ktm / kbm of momtran and convtran (zm_conv.F90:2076-2081, 2449-2454) + the compact list of convective slots
+struct ChunkBounds { int *ktm = nullptr, *kbm = nullptr, *slots = nullptr, *count = nullptr; };
+size_t chunk_bounds_bytes(int nchunks, int ncolpad) { return 2 * al(nchunks, 4) + al(ncolpad, 4) + 2048; }
+int chunk_bounds_enqueue(Workspace& ws, cudaStream_t s, int nchunks, const int* jt, const int* mx, const int* lengath,
+                         ChunkBounds& cb) {
+  const int ncolpad = nchunks * g_params.pcols;
+  cb.ktm = ws.take<int>(nchunks); cb.kbm = ws.take<int>(nchunks);
+  cb.slots = ws.take<int>(ncolpad); cb.count = ws.take<int>(1);
+  CK(cudaMemsetAsync(cb.count, 0, sizeof(int), s));
+  k_chunk_bounds<<<(nchunks * 32 + 127) / 128, 128, 0, s>>>(nchunks, jt, mx, lengath, cb.ktm, cb.kbm, cb.slots, cb.count);
+  ++tls_launches;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// own_arena: the bounds come from this call's own arena; otherwise `cb` holds them already
+int momtran_launch(Workspace& ws, cudaStream_t s, MomArgs a, bool own_arena = true, const ChunkBounds* cb = nullptr) {
   const int pcols = g_params.pcols, pver = g_params.pver;
   const int ncolpad = a.nchunks * pcols;
-  if (own_arena && ws.ensure(2 * al(a.nchunks, 4) + al(ncolpad, 4) + 2048)) return -100;
-  int* ktm = ws.take<int>(a.nchunks); int* kbm = ws.take<int>(a.nchunks);
-  int* slots = ws.take<int>(ncolpad); int* count = ws.take<int>(1);
-  a.ktm = ktm; a.kbm = kbm; a.slots = slots; a.count = count;
-  CK(cudaMemsetAsync(count, 0, sizeof(int), s));
-  k_chunk_bounds<<<(a.nchunks * 32 + 127) / 128, 128, 0, s>>>(a.nchunks, a.jt, a.mx, a.lengath, ktm, kbm, slots, count);
-  ++tls_launches;
+  ChunkBounds own;
+  if (!cb) {
+    if (own_arena && ws.ensure(chunk_bounds_bytes(a.nchunks, ncolpad))) return -100;
+    if (chunk_bounds_enqueue(ws, s, a.nchunks, a.jt, a.mx, a.lengath, own)) return -100;
+    cb = &own;
+  }
+  a.ktm = cb->ktm; a.kbm = cb->kbm; a.slots = cb->slots; a.count = cb->count;
   k_momtran_init<<<592, 256, 0, s>>>(a); ++tls_launches;
   const size_t smem_mom = momtran_smem_bytes(pver);
   if (smem_mom > 48 * 1024)
@@ -392,27 +421,58 @@ int momtran_launch(Workspace& ws, cudaStream_t s, MomArgs a, bool own_arena = tr
   return 0;
 }
 
-int convtran_launch(Workspace& ws, cudaStream_t s, TranArgs a, const int* doconvtran_h,
-                    const int* is_dry_h) {
+// Constituent flags of a convtran call on the device: [0, nactive) the 0-based indices m >= 1 with doconvtran(m),
+// then ncnst dry flags.  Kept per thread and re-uploaded (synchronously) only when the flags change, so that a
+// step that repeats -- every model time step -- enqueues no host->device copy and can be captured in a CUDA graph.
+struct TranMeta {
+  int* d = nullptr; int cap = 0;
+  std::vector<int> host;
+  int ncnst = 0, nactive = 0, version = 0; bool any_dry = false;
+  const int* active() const { return d; }
+  const int* dry() const { return d + nactive; }
+  int set(const int* doconvtran, const int* is_dry, int n) {
+    std::vector<int> h;
+    for (int m = 1; m < n; ++m)            // reference loops m = 2, ncnst (1-based)
+      if (doconvtran[m]) h.push_back(m);
+    const int na = (int)h.size();
+    bool dry_any = false;
+    for (int m = 0; m < n; ++m) { h.push_back(is_dry ? is_dry[m] : 0); }
+    for (int j = 0; j < na; ++j) dry_any = dry_any || (is_dry && is_dry[h[j]]);
+    return upload(h, n, na, dry_any);
+  }
+  // compact form: `na` constituents 0..na-1, all active, with their dry flags
+  int set_compact(const std::vector<int>& dry_of_active) {
+    const int na = (int)dry_of_active.size();
+    std::vector<int> h;
+    bool dry_any = false;
+    for (int j = 0; j < na; ++j) h.push_back(j);
+    for (int j = 0; j < na; ++j) { h.push_back(dry_of_active[j]); dry_any = dry_any || dry_of_active[j]; }
+    return upload(h, na, na, dry_any);
+  }
+  int upload(const std::vector<int>& h, int n, int na, bool dry_any) {
+    if (h == host && n == ncnst && d) return 0;
+    if ((int)h.size() > cap) {
+      if (d) { CK(cudaDeviceSynchronize()); CK(cudaFree(d)); d = nullptr; }
+      cap = (int)h.size() + 64;
+      CK(cudaMalloc((void**)&d, cap * sizeof(int)));
+    }
+    CK(cudaMemcpy(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+    host = h; ncnst = n; nactive = na; any_dry = dry_any; ++version;
+    return 0;
+  }
+  void release() { if (d) { cudaFree(d); d = nullptr; } cap = 0; host.clear(); ncnst = nactive = 0; }
+};
+thread_local TranMeta tls_tmeta;      // zm_convtran_batch[_dev] / zm_conv_tend_2_batch
+thread_local TranMeta tls_tmeta1;     // convtran1 attached to zm_conv_tend_batch_dev (caller's constituent layout)
+thread_local TranMeta tls_tmeta1c;    // convtran1 of the host-pointer zm_conv_tend_batch (compact: active slices only)
+thread_local std::vector<int> tls_tran1_flags;   // host copy of (doconvtran, cnst_is_dry) given to zm_convtran1_fields
+
+// a.active / a.is_dry / a.nactive and the chunk bounds are set: zero the active slices, transport
+int convtran_enqueue(cudaStream_t s, TranArgs a, const ChunkBounds& cb) {
   const int pcols = g_params.pcols, pver = g_params.pver;
   const int ncolpad = a.nchunks * pcols;
-  std::vector<int> active;
-  for (int m = 1; m < a.ncnst; ++m)          // reference loops m = 2, ncnst (1-based)
-    if (doconvtran_h[m]) active.push_back(m);
-  a.nactive = (int)active.size();
   if (a.nactive == 0) return 0;
-  if (ws.ensure(2 * al(a.nchunks, 4) + al(a.nactive, 4) + al(a.ncnst, 4) + al(ncolpad, 4) + 2048)) return -100;
-  int* ktm = ws.take<int>(a.nchunks); int* kbm = ws.take<int>(a.nchunks);
-  int* slots = ws.take<int>(ncolpad); int* count = ws.take<int>(1);
-  a.slots = slots; a.count = count;
-  CK(cudaMemsetAsync(count, 0, sizeof(int), s));
-  int* act_d = ws.take<int>(a.nactive); int* dry_d = ws.take<int>(a.ncnst);
-  CK(cudaMemcpyAsync(act_d, active.data(), a.nactive * sizeof(int), cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(dry_d, is_dry_h, a.ncnst * sizeof(int), cudaMemcpyHostToDevice, s));
-  CK(cudaStreamSynchronize(s));            // `active` is a stack vector: copy must finish first
-  a.ktm = ktm; a.kbm = kbm; a.active = act_d; a.is_dry = dry_d;
-  k_chunk_bounds<<<(a.nchunks * 32 + 127) / 128, 128, 0, s>>>(a.nchunks, a.jt, a.mx, a.lengath, ktm, kbm, slots, count);
-  ++tls_launches;
+  a.ktm = cb.ktm; a.kbm = cb.kbm; a.slots = cb.slots; a.count = cb.count;
   k_convtran_zero<<<a.nchunks * a.nactive, 128, 0, s>>>(a); ++tls_launches;
   const int cpb = convtran_cnst_per_block(pver);
   dim3 blk(32, cpb);
@@ -421,6 +481,19 @@ int convtran_launch(Workspace& ws, cudaStream_t s, TranArgs a, const int* doconv
   ++tls_launches;
   CK(cudaGetLastError());
   return 0;
+}
+
+int convtran_launch(Workspace& ws, cudaStream_t s, TranArgs a, const int* doconvtran_h,
+                    const int* is_dry_h) {
+  const int ncolpad = a.nchunks * g_params.pcols;
+  if (tls_tmeta.set(doconvtran_h, is_dry_h, a.ncnst)) return -100;
+  a.nactive = tls_tmeta.nactive;
+  if (a.nactive == 0) return 0;
+  a.active = tls_tmeta.active(); a.is_dry = tls_tmeta.dry();
+  if (ws.ensure(chunk_bounds_bytes(a.nchunks, ncolpad))) return -100;
+  ChunkBounds cb;
+  if (chunk_bounds_enqueue(ws, s, a.nchunks, a.jt, a.mx, a.lengath, cb)) return -100;
+  return convtran_enqueue(s, a, cb);
 }
 
 // ---- zm_conv_tend glue (zm_conv_intr.F90:662-836) ------------------------------------------------
@@ -447,6 +520,7 @@ __global__ void k_state_update(int n2, int nper, const double* t, const double* 
 }
 // ptend_all = sum of the three ptend_loc (physics_ptend_sum, physics_types.F90:698-844) and the
 // mcon unit conversion mb/s -> kg/m2/s (zm_conv_intr.F90:693)
+template <bool MOM>
 __global__ void k_tend_finalize(int n2, int n2p, int nper, const double* heat, const double* qtnd,
                                 const double* ev_s, const double* ev_q, const double* seten,
                                 const double* wtend, double* ps, double* pq, double* pu, double* pv,
@@ -454,11 +528,16 @@ __global__ void k_tend_finalize(int n2, int n2p, int nper, const double* heat, c
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n2p; e += gridDim.x * blockDim.x) {
     mcon[e] = mcon[e] * 100.0 / P.gravit;
     if (e < n2) {
-      ps[e] = (heat[e] + ev_s[e]) + seten[e];
       pq[e] = qtnd[e] + ev_q[e];
-      int c = e / nper, r = e - c * nper;
-      pu[e] = wtend[(size_t)c * 2 * nper + r];
-      pv[e] = wtend[(size_t)c * 2 * nper + nper + r];
+      if (MOM) {
+        ps[e] = (heat[e] + ev_s[e]) + seten[e];
+        int c = e / nper, r = e - c * nper;
+        pu[e] = wtend[(size_t)c * 2 * nper + r];
+        pv[e] = wtend[(size_t)c * 2 * nper + nper + r];
+      } else {                      // cam3: no momentum transport (zm_conv_intr.F90:808)
+        ps[e] = heat[e] + ev_s[e];
+        pu[e] = 0.0; pv[e] = 0.0;
+      }
       evapcdp[e] = ev_q[e];
     }
   }
@@ -502,6 +581,42 @@ __global__ void k_conservation_final(int nblocks, const double* partial, double*
     double s = 0.0;
     for (int b = 0; b < nblocks; ++b) s += partial[b * 6 + threadIdx.x];
     out6[threadIdx.x] = s;
+  }
+}
+
+// freqzm, mu_out / md_out, pcont / pconb of zm_conv_tend (zm_conv_intr.F90:685-688, 575-576 + 700-706, 721-729):
+// one warp per chunk.  pcont / pconb are assigned for i <= ncol only (:721-722); the rest of the row is zero-filled.
+__global__ void k_tend_diag(int nchunks, const int* ncol, const double* ps, const double* pmid, const double* mu,
+                            const double* md, const int* jt, const int* maxg, const int* ideep, const int* lengath,
+                            double* freqzm, double* mu_out, double* md_out, double* pcont, double* pconb) {
+  const int pcols = P.pcols, pver = P.pver;
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= nchunks) return;
+  const int n = ncol[c], len = lengath[c];
+  const size_t c1 = (size_t)c * pcols;
+  for (int i = lane; i < pcols; i += 32) {
+    freqzm[c1 + i] = 0.0;
+    pcont[c1 + i] = (i < n) ? ps[c1 + i] : 0.0;
+    pconb[c1 + i] = (i < n) ? ps[c1 + i] : 0.0;
+  }
+  for (int e = lane; e < pcols * pver; e += 32) {
+    mu_out[(size_t)c * pcols * pver + e] = 0.0;
+    md_out[(size_t)c * pcols * pver + e] = 0.0;
+  }
+  __syncwarp();
+  for (int i = lane; i < len; i += 32) {
+    const int ii = ideep[c1 + i] - 1;
+    freqzm[c1 + ii] = 1.0;
+    const int j = jt[c1 + i], mx = maxg[c1 + i];
+    if (mx > j) {
+      pcont[c1 + ii] = pmid[cidx(c, j - 1, ii, pver)];
+      pconb[c1 + ii] = pmid[cidx(c, mx - 1, ii, pver)];
+    }
+    for (int k = 0; k < pver; ++k) {
+      mu_out[cidx(c, k, ii, pver)] = mu[cidx(c, k, i, pver)] * 100.0 / P.gravit;
+      md_out[cidx(c, k, ii, pver)] = md[cidx(c, k, i, pver)] * 100.0 / P.gravit;
+    }
   }
 }
 
@@ -686,7 +801,8 @@ int zm_finalize(void) {
   g_inited = false;
   cudaDeviceSynchronize();
   tls_graph.clear();
-  tls_work.release(); tls_stage.release(); tls_stage2.release(); tls_pipe.release();
+  tls_work.release(); tls_stage.release(); tls_stage2.release(); tls_mirror_ws.release(); tls_pipe.release();
+  tls_tmeta.release(); tls_tmeta1.release(); tls_tmeta1c.release(); tls_tran1 = Tran1Fields{};
   tls_mirror = PbufMirror{};
   return 0;
 }
@@ -709,6 +825,34 @@ int zm_get_kernel_times(int* n, const char** names, float* ms) {
       names[cnt] = ws.tnames[i];
     }
   }
+  *n = cnt;
+  return 0;
+}
+
+// The same per-kernel times folded into the reference's GPTL timer names (t_startf / t_stopf in
+// zm_conv_intr.F90:654-711 'zm_convr', :763-798 'zm_conv_evap', :821-827 'momtran', :874-880 'convtran1',
+// :1019-1025 'convtran2'); the glue kernels of physics_update / physics_ptend_sum are reported beside them.
+int zm_get_timers(int* n, const char** names, float* ms) {
+  static const char* const gptl[] = {"zm_convr", "zm_conv_evap", "momtran", "convtran1", "convtran2", "physics_update"};
+  float acc[6] = {0, 0, 0, 0, 0, 0};
+  auto bucket = [](const char* k) {
+    if (!strcmp(k, "zm_conv_evap")) return 1;
+    if (!strcmp(k, "momtran")) return 2;
+    if (!strcmp(k, "convtran1")) return 3;
+    if (!strcmp(k, "convtran2")) return 4;
+    if (!strcmp(k, "state_update") || !strcmp(k, "tend_finalize")) return 5;
+    return 0;                                        // every kernel of zm_convr
+  };
+  for (Workspace* ws : {&tls_work, &tls_stage2}) {
+    if (ws->tev.size() < 2) continue;
+    cudaEventSynchronize(ws->tev.back());
+    for (size_t i = 1; i < ws->tev.size(); ++i) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, ws->tev[i - 1], ws->tev[i]) == cudaSuccess) acc[bucket(ws->tnames[i])] += t;
+    }
+  }
+  int cnt = 0;
+  for (int j = 0; j < 6 && cnt < *n; ++j, ++cnt) { names[cnt] = gptl[j]; ms[cnt] = acc[j]; }
   *n = cnt;
   return 0;
 }
@@ -958,12 +1102,12 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
                            double* md, double* du, double* eu, double* ed, double* dp, double* dsubcld,
                            int* jt, int* maxg, int* ideep, int* lengath, double* cape, void* stream,
                            const TendHooks* hooks, const double* org = nullptr, double* orgt = nullptr,
-                           double* org2d = nullptr) {
+                           double* org2d = nullptr, const Tran1Dev* tr1 = nullptr) {
   NEED_INIT();
   if (nchunks <= 0) return 0;
   const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc;
   const size_t n2 = nc * L, n2p = nc * (L + 1);
-  if (ws.ensure(convr_work_bytes(nc, (int)L) + 18 * al(n2, 8) + 6 * al(2 * n2, 8) + 2 * al(nchunks, 4) + al(nc, 4) + 8192))
+  if (ws.ensure(convr_work_bytes(nc, (int)L) + 19 * al(n2, 8) + 6 * al(2 * n2, 8) + chunk_bounds_bytes(nchunks, (int)nc) + 8192))
     return -100;
   cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
   double *heat = ws.take<double>(n2), *qtnd = ws.take<double>(n2), *eurt = ws.take<double>(n2),
@@ -999,8 +1143,11 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
     CK(cudaEventRecord(ws.ev_fork, s));
     CK(cudaStreamWaitEvent(ws.side, ws.ev_fork, 0));
     k_state_update<1><<<1184, 256, 0, ws.side>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
-    k_state_update<2><<<1184, 256, 0, s>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
-    tls_launches += 2;
+    if (!g_params.cam3) {       // winds feed momtran only
+      k_state_update<2><<<1184, 256, 0, s>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
+      ++tls_launches;
+    }
+    ++tls_launches;
   } else {
     k_state_update<0><<<1184, 256, 0, s>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
     ++tls_launches;
@@ -1013,18 +1160,45 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
   }
   if (fork) CK(cudaEventRecord(ws.ev_join, ws.side));
   tick(ws, s, "zm_conv_evap");
-  MomArgs ma;
-  ma.nchunks = nchunks; ma.ncnst = 2; ma.ncol = ncol; ma.jt = jt; ma.mx = maxg; ma.ideep = ideep;
-  ma.lengath = lengath; ma.ktm = nullptr; ma.kbm = nullptr; ma.domom[0] = 1; ma.domom[1] = 1;
-  ma.q = winds; ma.mu = mu; ma.md = md; ma.du = du; ma.eu = eu; ma.ed = ed; ma.dp = dp;
-  ma.dqdt = wtend; ma.pguall = pgu; ma.pgdall = pgd; ma.icwu = icwu; ma.icwd = icwd; ma.seten = seten;
-  ma.dt = ztodt;
-  rc = momtran_launch(ws, s, ma, false);
-  if (rc) return rc;
+  const bool do_mom = !g_params.cam3;          // zm_conv_intr.F90:808: momentum transport is non-cam3 physics
+  const bool do_tran1 = tr1 && tr1->nactive > 0;
+  ChunkBounds cb;
+  if (do_mom || do_tran1) {
+    rc = chunk_bounds_enqueue(ws, s, nchunks, jt, maxg, lengath, cb);
+    if (rc) return rc;
+  }
+  if (do_mom) {
+    MomArgs ma;
+    ma.nchunks = nchunks; ma.ncnst = 2; ma.ncol = ncol; ma.jt = jt; ma.mx = maxg; ma.ideep = ideep;
+    ma.lengath = lengath; ma.ktm = nullptr; ma.kbm = nullptr; ma.domom[0] = 1; ma.domom[1] = 1;
+    ma.q = winds; ma.mu = mu; ma.md = md; ma.du = du; ma.eu = eu; ma.ed = ed; ma.dp = dp;
+    ma.dqdt = wtend; ma.pguall = pgu; ma.pgdall = pgd; ma.icwu = icwu; ma.icwd = icwd; ma.seten = seten;
+    ma.dt = ztodt;
+    rc = momtran_launch(ws, s, ma, false, &cb);
+    if (rc) return rc;
+  }
   tick(ws, s, "momtran");
+  if (do_tran1) {
+    // convtran1 (zm_conv_intr.F90:865-880) on state1%q: its constituents m >= 2 are the caller's (only q(:,:,1)
+    // was updated); fake_dpdry = 0 (the transported species are moist; a zeroed array stands in if one is 'dry')
+    double* fake_dpdry = ws.take<double>(n2);
+    if (tr1->any_dry) CK(cudaMemsetAsync(fake_dpdry, 0, n2 * sizeof(double), s));
+    TranArgs ta;
+    ta.nchunks = nchunks; ta.ncnst = tr1->ncnst; ta.nactive = tr1->nactive; ta.jt = jt; ta.mx = maxg; ta.ideep = ideep;
+    ta.lengath = lengath; ta.active = tr1->active; ta.is_dry = tr1->is_dry;
+    ta.q = tr1->q; ta.fracis = tr1->fracis; ta.mu = mu; ta.md = md; ta.du = du; ta.eu = eu; ta.ed = ed; ta.dp = dp;
+    ta.dpdry = fake_dpdry; ta.dqdt = tr1->dqdt;
+    rc = convtran_enqueue(s, ta, cb);
+    if (rc) return rc;
+    tick(ws, s, "convtran1");
+  }
   if (fork) CK(cudaStreamWaitEvent(s, ws.ev_join, 0));
-  k_tend_finalize<<<1184, 256, 0, s>>>((int)n2, (int)n2p, nper, heat, qtnd, ev_s, ev_q, seten, wtend, ptend_s,
-                                       ptend_q, ptend_u, ptend_v, evapcdp, mcon);
+  if (do_mom)
+    k_tend_finalize<true><<<1184, 256, 0, s>>>((int)n2, (int)n2p, nper, heat, qtnd, ev_s, ev_q, seten, wtend, ptend_s,
+                                               ptend_q, ptend_u, ptend_v, evapcdp, mcon);
+  else
+    k_tend_finalize<false><<<1184, 256, 0, s>>>((int)n2, (int)n2p, nper, heat, qtnd, ev_s, ev_q, seten, wtend, ptend_s,
+                                                ptend_q, ptend_u, ptend_v, evapcdp, mcon);
   ++tls_launches;
   tick(ws, s, "tend_finalize");
   CK(cudaGetLastError());
@@ -1055,12 +1229,21 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
   while (NB > 1 && nchunks / NB < 128) --NB;
   tp.dev_nb = 0;
   const OrgFields of = tls_org; tls_org = OrgFields{};       // one-shot
+  const Tran1Fields tf = tls_tran1; tls_tran1 = Tran1Fields{};   // one-shot
+  Tran1Dev td{};
+  const Tran1Dev* tdp = nullptr;
+  if (tf.pcnst > 0) {
+    const int n = tf.pcnst;
+    if (tls_tmeta1.set(tls_tran1_flags.data(), tls_tran1_flags.data() + n, n)) return -100;
+    td = Tran1Dev{n, tls_tmeta1.nactive, tls_tmeta1.active(), tls_tmeta1.dry(), tls_tmeta1.any_dry, tf.q, tf.fracis, tf.ptend_q};
+    tdp = &td;
+  }
   if (NB == 1 || g_profile) {
     auto direct = [&](Workspace& ws, void* on) {
       return conv_tend_impl(ws, nchunks, ncol, t, q, u, v, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac,
                             cld, ztodt, ptend_s, ptend_q, ptend_u, ptend_v, mcon, cme, pflx, zdu, rliq, rice, jctop,
                             jcbot, prec, snow, ql, rprd, evapcdp, flxprec, flxsnow, dlf, mu, md, du, eu, ed, dp,
-                            dsubcld, jt, maxg, ideep, lengath, cape, on, nullptr, of.org, of.orgt, of.org2d);
+                            dsubcld, jt, maxg, ideep, lengath, cape, on, nullptr, of.org, of.orgt, of.org2d, tdp);
     };
     static const bool use_graph = !(getenv("ZM_DEV_GRAPH") && atoi(getenv("ZM_DEV_GRAPH")) == 0);
     if (g_profile || !use_graph) { tls_graph.clear(); return direct(tls_work, stream); }
@@ -1071,6 +1254,8 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
         ptend_s, ptend_q, ptend_u, ptend_v, mcon, cme, pflx, zdu, rliq, rice, jctop, jcbot, prec, snow, ql, rprd,
         evapcdp, flxprec, flxsnow, dlf, mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, lengath, cape,
         of.org, of.orgt, of.org2d, ztbits, (const void*)(size_t)nchunks, (const void*)(size_t)g_epoch,
+        tf.q, tf.fracis, tf.ptend_q, (const void*)(size_t)tf.pcnst, (const void*)tls_tmeta1.d,
+        (const void*)(size_t)(tdp ? tls_tmeta1.version : 0),
         (const void*)ws.dbuf, (const void*)ws.dcap};
     cudaStream_t s = (cudaStream_t)stream;
     if (key == G.key) {
@@ -1110,6 +1295,11 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
     Workspace& ws = tp.work[b];
     ws.chunk0 = c0;
     CK(cudaStreamWaitEvent(ws.stream, tp.in_ready[0], 0));
+    Tran1Dev tb = td;            // this sub-batch's slice of the constituent arrays
+    if (tdp) {
+      const size_t o3 = (size_t)c0 * s2 * td.ncnst;
+      tb.q = td.q + o3; tb.fracis = td.fracis + o3; tb.dqdt = td.dqdt + o3;
+    }
 #define O2(x)  ((x) + (size_t)c0 * s2)
 #define O2P(x) ((x) + (size_t)c0 * s2p)
 #define O1(x)  ((x) + (size_t)c0 * s1)
@@ -1120,7 +1310,7 @@ int zm_conv_tend_batch_dev(int nchunks, const int* ncol, const double* t, const 
                             O2P(flxprec), O2P(flxsnow), O2(dlf), O2(mu), O2(md), O2(du), O2(eu), O2(ed), O2(dp),
                             O1(dsubcld), O1(jt), O1(maxg), O1(ideep), lengath + c0, O1(cape), (void*)ws.stream, nullptr,
                             of.org ? O2(of.org) : nullptr, of.orgt ? O2(of.orgt) : nullptr,
-                            of.org2d ? O2(of.org2d) : nullptr);
+                            of.org2d ? O2(of.org2d) : nullptr, tdp ? &tb : nullptr);
 #undef O2
 #undef O2P
 #undef O1
@@ -1147,8 +1337,11 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc;
   const size_t n2 = nc * L, n2p = nc * (L + 1);
   Workspace& st = tls_stage;
+  tls_mirror = PbufMirror{};                 // whatever happens below, the previous step's mirror is gone
   if (st.ensure(al(nchunks, 4) + 27 * al(n2, 8) + 6 * al(n2p, 8) + 14 * al(nc, 8) + 4 * al(nc, 4) + 8192))
     return -100;
+  Workspace& mw = tls_mirror_ws;
+  if (mw.ensure(6 * al(n2, 8) + al(nc, 8) + 3 * al(nc, 4) + al(nchunks, 4) + 4096)) return -100;
   // The batch is cut into NB sub-batches of whole chunks (columns are independent).  Sub-batch b's inputs
   // travel host->device while sub-batch b-1 computes, and its outputs travel back while sub-batch b+1
   // computes: PCIe (both directions) and the SMs are busy at the same time.  Every array keeps ONE
@@ -1165,8 +1358,9 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   // whole batch (4: in, before the first sub-batch; 5: out, after the last) instead of once per sub-batch
   struct Arr { const void* h; void* d; size_t stride, esz; int kind; };
   std::vector<Arr> arrs; arrs.reserve(64);
+  bool to_mirror = false;                    // the pbuf fields go to the mirror arena
   auto dev = [&](const void* h, size_t stride, size_t esz, int kind, bool always = true) -> void* {
-    void* d = (void*)st.take<char>((size_t)nchunks * stride * esz);
+    void* d = (void*)(to_mirror ? mw : st).take<char>((size_t)nchunks * stride * esz);
     if (stride <= pc) kind = (kind <= 1) ? 4 : 5;
     if (h || always) arrs.push_back({h, d, stride, esz, h ? kind : -1});
     return d;
@@ -1180,11 +1374,13 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
                *d_pdel = DIN(pdel, s2), *d_zm = DIN(zm, s2), *d_zi = DIN(zi, s2p), *d_phis = DIN(phis, s1),
                *d_pblh = DIN(pblh, s1), *d_tpert = DIN(tpert, s1), *d_lf = DIN(landfrac, s1);
   const double *d_u = DLATE(u, s2), *d_v = DLATE(v, s2), *d_cld = DLATE(cld, s2);
+  to_mirror = true;
   double *d_mu = DOUTE(mu, s2), *d_md = DOUTE(md, s2), *d_du = DOUTE(du, s2), *d_eu = DOUTE(eu, s2),
          *d_ed = DOUTE(ed, s2), *d_dp = DOUTE(dp, s2), *d_dsub = DOUTE(dsubcld, s1);
   int *d_jt = (int*)dev(jt, s1, 4, 2), *d_maxg = (int*)dev(maxg, s1, 4, 2), *d_ideep = (int*)dev(ideep, s1, 4, 2),
       *d_len = (int*)dev(lengath, 1, 4, 2);
-  tls_mirror = PbufMirror{nchunks, d_mu, d_md, d_du, d_eu, d_ed, d_dp, d_dsub, d_jt, d_maxg, d_ideep, d_len};
+  to_mirror = false;
+  const PbufMirror new_mirror{nchunks, d_mu, d_md, d_du, d_eu, d_ed, d_dp, d_dsub, d_jt, d_maxg, d_ideep, d_len};
   double *d_ps = DOUTF(ptend_s, s2), *d_pq = DOUTF(ptend_q, s2), *d_pu = DOUTF(ptend_u, s2), *d_pv = DOUTF(ptend_v, s2),
          *d_mcon = DOUTF(mcon, s2p), *d_cme = DOUTE(cme, s2), *d_pflx = DOUTE(pflx, s2p), *d_zdu = DOUTE(zdu, s2),
          *d_rliq = DOUTE(rliq, s1), *d_rice = DOUTE(rice, s1), *d_jctop = DOUTE(jctop, s1), *d_jcbot = DOUTE(jcbot, s1),
@@ -1204,7 +1400,51 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
 #undef DLATE
 #undef DOUTE
 #undef DOUTF
+  // convtran1 (zm_conv_intr.F90:865-880): only the slices of the transported constituents travel; on the device
+  // they are stored compactly, (pcols,pver,nactive) per chunk
+  const Tran1Fields tf = tls_tran1; tls_tran1 = Tran1Fields{};   // one-shot
+  struct SArr { const char* h; char* d; size_t hpitch, dpitch, width; int kind; };   // one constituent slice, all chunks
+  std::vector<SArr> sarrs;
+  Tran1Dev td{};
+  const Tran1Dev* tdp = nullptr;
+  if (tf.pcnst > 0) {
+    const int n = tf.pcnst;
+    std::vector<int> act, dryc;
+    for (int m = 1; m < n; ++m)
+      if (tls_tran1_flags[m]) { act.push_back(m); dryc.push_back(tls_tran1_flags[n + m]); }
+    const int na = (int)act.size();
+    if (na > 0) {
+      if (tls_tmeta1c.set_compact(dryc)) return -100;
+      Workspace& s3 = tls_stage2;                  // constituent slices: their own staging arena
+      if (s3.ensure(3 * al((size_t)nchunks * na * s2, 8) + 4096)) return -100;
+      double* d_q3 = s3.take<double>((size_t)nchunks * na * s2);
+      double* d_f3 = s3.take<double>((size_t)nchunks * na * s2);
+      double* d_t3 = s3.take<double>((size_t)nchunks * na * s2);
+      for (int j = 0; j < na; ++j) {
+        const size_t ho = (size_t)act[j] * s2 * 8, dof = (size_t)j * s2 * 8;
+        sarrs.push_back({(const char*)tf.q + ho, (char*)d_q3 + dof, (size_t)n * s2 * 8, (size_t)na * s2 * 8, s2 * 8, 1});
+        sarrs.push_back({(const char*)tf.fracis + ho, (char*)d_f3 + dof, (size_t)n * s2 * 8, (size_t)na * s2 * 8, s2 * 8, 1});
+        sarrs.push_back({(const char*)tf.ptend_q + ho, (char*)d_t3 + dof, (size_t)n * s2 * 8, (size_t)na * s2 * 8, s2 * 8, 3});
+      }
+      td = Tran1Dev{na, na, tls_tmeta1c.active(), tls_tmeta1c.dry(), tls_tmeta1c.any_dry, d_q3, d_f3, d_t3};
+      tdp = &td;
+    }
+  }
   int rc = 0;
+  // error paths: no copy into or out of the caller's buffers may still be in flight when the call returns
+  auto drain = [&]() {
+    cudaStreamSynchronize(tp.h2d); cudaStreamSynchronize(tp.d2h_early); cudaStreamSynchronize(tp.d2h_final);
+    for (int b = 0; b < TendPipe::MAXB; ++b) if (tp.work[b].stream) cudaStreamSynchronize(tp.work[b].stream);
+  };
+#define CKP(call)                                                                                   \
+  do {                                                                                              \
+    cudaError_t _e = (call);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      tls_err = std::string("CUDA error ") + cudaGetErrorString(_e) + " in zm_conv_tend_batch (" #call ")"; \
+      drain();                                                                                      \
+      return -100;                                                                                  \
+    }                                                                                               \
+  } while (0)
   auto copy_kind = [&](int kind, int c0, int nb, cudaStream_t on) {
     for (auto& a : arrs) {
       if (a.kind != kind) continue;
@@ -1213,28 +1453,40 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
                                   : cudaMemcpyAsync((char*)a.h + off, (char*)a.d + off, bytes, cudaMemcpyDeviceToHost, on);
       if (e != cudaSuccess) rc = -100;
     }
+    for (auto& a : sarrs) {
+      if (a.kind != kind) continue;
+      const cudaError_t e = (kind == 1)
+          ? cudaMemcpy2DAsync(a.d + (size_t)c0 * a.dpitch, a.dpitch, a.h + (size_t)c0 * a.hpitch, a.hpitch, a.width, nb, cudaMemcpyHostToDevice, on)
+          : cudaMemcpy2DAsync((char*)a.h + (size_t)c0 * a.hpitch, a.hpitch, a.d + (size_t)c0 * a.dpitch, a.dpitch, a.width, nb, cudaMemcpyDeviceToHost, on);
+      if (e != cudaSuccess) rc = -100;
+    }
   };
   // Enqueue order on the host thread: inputs of sub-batch b+1 go out right after the kernels of sub-batch b
   // were launched, so neither the copy engine nor the SMs wait for the host to finish enqueueing.
   auto send_inputs = [&](int b) -> int {
     const int c0 = tp.sched_first[b], nb = tp.sched_first[b + 1] - c0;
     copy_kind(0, c0, nb, tp.h2d);
-    CK(cudaEventRecord(tp.in_ready[b], tp.h2d));
+    CKP(cudaEventRecord(tp.in_ready[b], tp.h2d));
     copy_kind(1, c0, nb, tp.h2d);
-    CK(cudaEventRecord(tp.late_ready[b], tp.h2d));
+    CKP(cudaEventRecord(tp.late_ready[b], tp.h2d));
     return 0;
   };
-  CK(cudaEventRecord(tp.t0, tp.h2d));
+  CKP(cudaEventRecord(tp.t0, tp.h2d));
   const double w_t0 = wall_ms();
   copy_kind(4, 0, nchunks, tp.h2d);
-  if (send_inputs(0)) return -100;
+  if (send_inputs(0)) { drain(); return -100; }
   for (int b = 0; b < NB && rc == 0; ++b) {
     const int c0 = tp.sched_first[b], nb = tp.sched_first[b + 1] - c0;
     Workspace& ws = tp.work[b];
     ws.chunk0 = c0;
-    if (!ws.stream && ws.ensure(0)) return -100;
-    CK(cudaStreamWaitEvent(ws.stream, tp.in_ready[b], 0));
+    if (!ws.stream && ws.ensure(0)) { drain(); return -100; }
+    CKP(cudaStreamWaitEvent(ws.stream, tp.in_ready[b], 0));
     TendHooks hooks{tp.late_ready[b], tp.convr_done[b]};
+    Tran1Dev tb = td;
+    if (tdp) {
+      const size_t o3 = (size_t)c0 * s2 * td.ncnst;
+      tb.q = td.q + o3; tb.fracis = td.fracis + o3; tb.dqdt = td.dqdt + o3;
+    }
 #define O2(x)  ((x) + (size_t)c0 * s2)
 #define O2P(x) ((x) + (size_t)c0 * s2p)
 #define O1(x)  ((x) + (size_t)c0 * s1)
@@ -1245,24 +1497,24 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
                         O2(d_rprd), O2(d_evap), O2P(d_fp), O2P(d_fs), O2(d_dlf), O2(d_mu), O2(d_md), O2(d_du),
                         O2(d_eu), O2(d_ed), O2(d_dp), O1(d_dsub), O1(d_jt), O1(d_maxg), O1(d_ideep), d_len + c0,
                         O1(d_cape), (void*)ws.stream, &hooks, d_org ? O2(d_org) : nullptr,
-                        d_orgt ? O2(d_orgt) : nullptr, d_org2d ? O2(d_org2d) : nullptr);
+                        d_orgt ? O2(d_orgt) : nullptr, d_org2d ? O2(d_org2d) : nullptr, tdp ? &tb : nullptr);
 #undef O2
 #undef O2P
 #undef O1
     if (rc) break;
     const double w_k = wall_ms();
-    CK(cudaEventRecord(tp.done[b], ws.stream));
-    if (b + 1 < NB && send_inputs(b + 1)) return -100;
+    CKP(cudaEventRecord(tp.done[b], ws.stream));
+    if (b + 1 < NB && send_inputs(b + 1)) { drain(); return -100; }
     const double w_in = wall_ms();
     // device->host: zm_convr's outputs as soon as they are final, the rest when the sub-batch ends
     // one return stream, in the order results become final: by the time sub-batch b's zm_convr outputs are
     // across, its evap/momtran kernels have finished too
-    CK(cudaStreamWaitEvent(tp.d2h_early, tp.convr_done[b], 0));
+    CKP(cudaStreamWaitEvent(tp.d2h_early, tp.convr_done[b], 0));
     copy_kind(2, c0, nb, tp.d2h_early);
-    CK(cudaEventRecord(tp.early_back[b], tp.d2h_early));
-    CK(cudaStreamWaitEvent(tp.d2h_early, tp.done[b], 0));
+    CKP(cudaEventRecord(tp.early_back[b], tp.d2h_early));
+    CKP(cudaStreamWaitEvent(tp.d2h_early, tp.done[b], 0));
     copy_kind(3, c0, nb, tp.d2h_early);
-    CK(cudaEventRecord(tp.final_back[b], tp.d2h_early));
+    CKP(cudaEventRecord(tp.final_back[b], tp.d2h_early));
     if (dbg) fprintf(stderr, "  sub-batch %d: kernels enqueued %.3f, next inputs enqueued %.3f, returns enqueued %.3f ms\n",
                      b, w_k, w_in, wall_ms());
   }
@@ -1285,6 +1537,7 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) rc = -100;
   if (rc) {
     if (rc == -100 && tls_err.empty()) tls_err = std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError());
+    drain();
     return rc;
   }
   int fails = 0;
@@ -1294,7 +1547,9 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
     if (f < 0) return f;
     fails += f;
   }
+  if (fails == 0) tls_mirror = new_mirror;   // a failed step (the reference stops in endrun) leaves no mirror
   return fails;
+#undef CKP
 }
 
 // zm_org = 1: attach org (in), orgt and org2d (out), shapes (pcols,pver) per chunk, for the NEXT zm_convr_batch /
@@ -1303,6 +1558,65 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
 int zm_org_fields(const double* org, double* orgt, double* org2d) {
   tls_org = OrgFields{org, orgt, org2d};
   return 0;
+}
+
+// convtran1 of zm_conv_tend (zm_conv_intr.F90:865-880): attaches state%q, fracis and ptend_loc%q, all
+// (pcols,pver,pcnst) per chunk, and the constituent flags (lq(2:) = cnst_is_convtran1(2:); cnst_get_type_byind)
+// for the NEXT zm_conv_tend_batch[_dev] call of this thread.  pcnst <= 0 detaches.
+int zm_convtran1_fields(int pcnst, const int* doconvtran, const int* cnst_is_dry, const double* q,
+                        const double* fracis, double* ptend_q) {
+  if (pcnst <= 0 || !doconvtran || !q || !fracis || !ptend_q) { tls_tran1 = Tran1Fields{}; return 0; }
+  tls_tran1_flags.assign(2 * (size_t)pcnst, 0);
+  for (int m = 0; m < pcnst; ++m) {
+    tls_tran1_flags[m] = doconvtran[m] != 0;
+    tls_tran1_flags[pcnst + m] = cnst_is_dry ? (cnst_is_dry[m] != 0) : 0;
+  }
+  tls_tran1 = Tran1Fields{pcnst, q, fracis, ptend_q};
+  return 0;
+}
+
+// zm_conv_tend's history fields that involve arithmetic (zm_conv_intr.F90:685-688, 700-706, 721-729)
+int zm_conv_tend_diag_batch_dev(int nchunks, const int* ncol, const double* ps, const double* pmid, const double* mu,
+                                const double* md, const int* jt, const int* maxg, const int* ideep, const int* lengath,
+                                double* freqzm, double* mu_out, double* md_out, double* pcont, double* pconb,
+                                void* stream) {
+  NEED_INIT();
+  if (nchunks <= 0) return 0;
+  k_tend_diag<<<(nchunks * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nchunks, ncol, ps, pmid, mu, md, jt, maxg,
+                                                                            ideep, lengath, freqzm, mu_out, md_out,
+                                                                            pcont, pconb);
+  ++tls_launches;
+  CK(cudaGetLastError());
+  return 0;
+}
+// host pointers; mu, md, jt, maxg, ideep, lengath may be NULL: taken from the device pbuf mirror of this thread's
+// last zm_conv_tend_batch
+int zm_conv_tend_diag_batch(int nchunks, const int* ncol, const double* ps, const double* pmid, const double* mu,
+                            const double* md, const int* jt, const int* maxg, const int* ideep, const int* lengath,
+                            double* freqzm, double* mu_out, double* md_out, double* pcont, double* pconb) {
+  NEED_INIT();
+  if (nchunks <= 0) return 0;
+  const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc, n2 = nc * L;
+  const bool from_mirror = !(mu && md && jt && maxg && ideep && lengath);
+  const PbufMirror M = tls_mirror;
+  if (from_mirror && (M.nchunks != nchunks || !M.mu)) {
+    tls_err = "zm_conv_tend_diag_batch: no device mirror from a zm_conv_tend_batch call with the same nchunks on this thread";
+    return -7;
+  }
+  Workspace& st = tls_stage2;
+  if (st.ensure(al(nchunks, 4) * 2 + 5 * al(n2, 8) + 3 * al(nc, 4) + 4 * al(nc, 8) + 4096)) return -100;
+  Stager S(st);
+  const int* d_ncol = S.in(ncol, nchunks);
+  const double *d_ps = S.in(ps, nc), *d_pmid = S.in(pmid, n2);
+  const double *d_mu = from_mirror ? M.mu : S.in(mu, n2), *d_md = from_mirror ? M.md : S.in(md, n2);
+  const int *d_jt = from_mirror ? M.jt : S.in(jt, nc), *d_mx = from_mirror ? M.maxg : S.in(maxg, nc),
+            *d_id = from_mirror ? M.ideep : S.in(ideep, nc), *d_len = from_mirror ? M.lengath : S.in(lengath, nchunks);
+  double *d_f = S.out(freqzm, nc), *d_muo = S.out(mu_out, n2), *d_mdo = S.out(md_out, n2), *d_pt = S.out(pcont, nc),
+         *d_pb = S.out(pconb, nc);
+  int rc = zm_conv_tend_diag_batch_dev(nchunks, d_ncol, d_ps, d_pmid, d_mu, d_md, d_jt, d_mx, d_id, d_len, d_f, d_muo,
+                                       d_mdo, d_pt, d_pb, (void*)st.stream);
+  if (rc) return rc;
+  return S.flush();
 }
 
 // Timeline of this thread's last zm_conv_tend_batch call: for each sub-batch 6 times in ms since the first
@@ -1361,10 +1675,14 @@ int zm_conv_tend_2_batch(int nchunks, const int* doconvtran, const double* q, in
   double* d_dqdt = S.inout(ptend_q, n3);
   // dpdry(i,:) = pdeldry(ideep(i),:)/100 for i <= lengath, else 0 (zm_conv_intr.F90:1014-1017)
   k_dpdry_gather<<<592, 256, 0, st.stream>>>(nchunks, M.ideep, M.lengath, d_pdd, d_dpdry); ++tls_launches;
+  for (auto e : st.tev) cudaEventDestroy(e);
+  st.tev.clear(); st.tnames.clear();
+  tick(st, st.stream, "start");
   int rc = zm_convtran_batch_dev(nchunks, doconvtran, d_q, pcnst, M.mu, M.md, M.du, M.eu, M.ed, M.dp, M.dsubcld,
                                  M.jt, M.maxg, M.ideep, M.lengath, d_fr, d_dqdt, d_dpdry, ztodt, cnst_is_dry,
                                  (void*)st.stream);
   if (rc) return rc;
+  tick(st, st.stream, "convtran2");
   return S.flush();
 }
 

@@ -75,6 +75,7 @@ EXPORTS = [
     "zm_convect_diagnostics_batch_dev",
     "zm_math_eval_dev", "zm_math_eval_host", "zm_thermo_eval_dev", "zm_fp64_peak_flops",
     "zm_set_profiling", "zm_get_kernel_times", "zm_launch_count",
+    "zm_convtran1_fields", "zm_conv_tend_diag_batch", "zm_conv_tend_diag_batch_dev", "zm_get_timers",
 ]
 
 
@@ -268,10 +269,14 @@ def zm_conv_tend_2(doconvtran, q, pdeldry, fracis, ztodt, cnst_is_dry, ptend_q=N
     return dq
 
 
-def zm_conv_tend(ncol, state: dict, ztodt: float, out: dict | None = None, keep_pbuf_on_device: bool = False):
+def zm_conv_tend(ncol, state: dict, ztodt: float, out: dict | None = None, keep_pbuf_on_device: bool = False,
+                 convtran1: dict | None = None):
     """zm_conv_tend (zm_conv_intr.F90:390) over host arrays: zm_convr -> physics_update ->
-    zm_conv_evap -> momtran with everything resident on the device in between.
-    `state` holds t,q,u,v,pmid,pint,pdel,zm,zi,phis,pblh,tpert,landfrac,cld in chunk layout."""
+    zm_conv_evap -> momtran [-> convtran1] with everything resident on the device in between.
+    `state` holds t,q,u,v,pmid,pint,pdel,zm,zi,phis,pblh,tpert,landfrac,cld in chunk layout.
+    convtran1 = dict(doconvtran=cnst_is_convtran1 flags [pcnst], cnst_is_dry=[pcnst] or None,
+    q=state%q [nchunks,pcnst,pver,pcols], fracis=same shape[, ptend_q=initial ptend_all%q]) adds the transport of
+    cloud liquid / ice (zm_conv_intr.F90:865-880); the result comes back as out["ptend_qc"]."""
     pc, L = _grid()
     ncol = _i(ncol)
     nch = ncol.shape[0]
@@ -293,6 +298,14 @@ def zm_conv_tend(ncol, state: dict, ztodt: float, out: dict | None = None, keep_
         if "orgt" not in out:
             out["orgt"], out["org2d"] = np.zeros_like(org), np.zeros_like(org)
         zm_org_fields(org, out["orgt"], out["org2d"])
+    if convtran1 is not None:
+        q3, f3 = _f(convtran1["q"]), _f(convtran1["fracis"])
+        pcnst = q3.shape[1]
+        out["ptend_qc"] = np.zeros_like(q3) if convtran1.get("ptend_q") is None else _f(convtran1["ptend_q"]).copy()
+        dry = convtran1.get("cnst_is_dry")
+        keep = (q3, f3)                                                    # noqa: F841 (alive during the call)
+        lib().zm_convtran1_fields(C.c_int(pcnst), _ip(_i(convtran1["doconvtran"])),
+                                  _ip(_i(dry)) if dry is not None else None, _dp(q3), _dp(f3), _dp(out["ptend_qc"]))
     mirror_only = {"mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg"} if keep_pbuf_on_device else set()
     for k in TEND_ARG_ORDER:
         a = out[k]
@@ -303,6 +316,32 @@ def zm_conv_tend(ncol, state: dict, ztodt: float, out: dict | None = None, keep_
     rc = lib().zm_conv_tend_batch(*args)
     _check(rc, "zm_conv_tend")
     return out
+
+
+def zm_conv_tend_diag(ncol, ps, pmid, mu=None, md=None, jt=None, maxg=None, ideep=None, lengath=None):
+    """freqzm, mu_out, md_out, pcont, pconb of zm_conv_tend (zm_conv_intr.F90:685-688, 700-706, 721-729).  With the
+    mass-flux fields left out they come from the device mirror of this thread's last zm_conv_tend call."""
+    pc, L = _grid()
+    ncol = _i(ncol)
+    nch = ncol.shape[0]
+    o = dict(freqzm=np.zeros((nch, pc)), mu_out=np.zeros((nch, L, pc)), md_out=np.zeros((nch, L, pc)),
+             pcont=np.zeros((nch, pc)), pconb=np.zeros((nch, pc)))
+    given = mu is not None
+    a = [(_dp(_f(x)) if given else None) for x in (mu, md)] + [(_ip(_i(x)) if given else None) for x in (jt, maxg, ideep, lengath)]
+    rc = lib().zm_conv_tend_diag_batch(C.c_int(nch), _ip(ncol), _dp(_f(ps)), _dp(_f(pmid)), *a, _dp(o["freqzm"]),
+                                       _dp(o["mu_out"]), _dp(o["md_out"]), _dp(o["pcont"]), _dp(o["pconb"]))
+    _check(rc, "zm_conv_tend_diag")
+    return o
+
+
+def timers():
+    """Device times (ms) of the last profiled zm_conv_tend / zm_conv_tend_2 call under the reference's GPTL timer
+    names (zm_conv_intr.F90:654-880, 1019-1025): zm_convr, zm_conv_evap, momtran, convtran1, convtran2."""
+    n = C.c_int(8)
+    names = (C.c_char_p * 8)()
+    ms = (C.c_float * 8)()
+    lib().zm_get_timers(C.byref(n), names, ms)
+    return {names[i].decode(): float(ms[i]) for i in range(n.value)}
 
 
 def geopotential_t(ncol, piln, pmln, pint, pmid, pdel, rpdel, t, q, rair, gravit, zvir, dycore_lr=True):
@@ -373,8 +412,8 @@ def fp64_peak_flops(iters: int = 20000) -> float:
 
 
 def kernel_times():
-    n = C.c_int(16)
-    names = (C.c_char_p * 16)()
-    ms = (C.c_float * 16)()
+    n = C.c_int(24)
+    names = (C.c_char_p * 24)()
+    ms = (C.c_float * 24)()
     lib().zm_get_kernel_times(C.byref(n), names, ms)
     return [(names[i].decode(), float(ms[i])) for i in range(n.value)]

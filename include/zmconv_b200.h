@@ -124,8 +124,10 @@ int zm_convtran_batch_dev(int nchunks, const int* doconvtran, const double* q, i
 /* The reference's driver for this path, zm_conv_tend (zm_conv_intr.F90:390-951), batched and kept on
  * the device end to end: zm_convr (delt = 0.5*ztodt, :666) -> physics_update of state1 (t += s*dt/cpair,
  * q(:,:,1) += qtnd*dt clipped at qmin=1e-12; physics_types.F90:322-329,427) -> zm_conv_evap (:764) ->
- * momtran on (u,v) (:822) -> ptend_all = sum of the three ptend_loc (:736,803,833).  mcon is returned
- * in kg/m2/s (:693).  convtran1 (:875) is separate; zm_org goes through zm_org_fields; zmconv_microp is out of scope.
+ * momtran on (u,v) (:822; skipped when cam3 = 1, :808 -- ptend_u, ptend_v are then 0 and ptend_s carries no KE
+ * dissipation term) -> convtran1 (:865-880) when zm_convtran1_fields attached the constituent arrays ->
+ * ptend_all = sum of the ptend_loc (:736,803,833,886).  mcon is returned in kg/m2/s (:693).  zm_org goes through
+ * zm_org_fields; zmconv_microp is out of scope.
  * State in: t,q(wv),u,v,pmid,pint,pdel,zm,zi,phis + pblh,tpert,landfrac,cld(pbuf 'CLD').
  * Out: ptend_all%s,q(:,:,1),u,v; the dummy outputs mcon,cme,pflx,zdu,rliq,rice,jctop,jcbot; and the
  * pbuf fields the reference fills (prec_dp, snow_dp, icwmrdp=ql, rprddp=rprd, nevapr_dpcu=evapcdp,
@@ -214,6 +216,32 @@ int zm_conv_tend_2_batch(int nchunks, const int* doconvtran, const double* q, in
  * zm_conv_evap uses ke over ocean / ke_lnd over land (zm_conv.F90:1860-1864).  Calls without attached fields fail (-8). */
 int zm_org_fields(const double* org, double* orgt, double* org2d);
 
+/* convtran1 inside zm_conv_tend (zm_conv_intr.F90:865-880: `lq(2:) = cnst_is_convtran1(2:)`, convtran on state1%q with
+ * fake_dpdry = 0, result summed into ptend_all%q): attach for the NEXT zm_conv_tend_batch[_dev] call of the calling
+ * thread (host pointers for the host-pointer entry point, device pointers for _dev) the constituent arrays
+ * q = state%q, fracis (pbuf 'FRACIS') and ptend_q = ptend_all%q, all (pcols,pver,pcnst) per chunk, and the HOST flag
+ * arrays doconvtran[pcnst] (= cnst_is_convtran1; entry 0, water vapour, is ignored like the reference's m = 2..pcnst
+ * loop, zm_conv.F90:2084) and cnst_is_dry[pcnst] (may be NULL = all moist).  ptend_q(:,:,m) is written (zero + scatter,
+ * zm_conv.F90:2298-2304) for the flagged m only; ptend_all%q(:,:,1) stays the separate ptend_q argument of
+ * zm_conv_tend_batch.  state1%q(:,:,m >= 2) equals state%q(:,:,m) at that point of zm_conv_tend (only q(:,:,1) -- and the
+ * org tracer under zm_org, which is not a convtran1 species -- was updated), so the caller's array is transported
+ * as is.  The host-pointer variant moves only the flagged slices over PCIe.  pcnst <= 0 or a NULL pointer detaches. */
+int zm_convtran1_fields(int pcnst, const int* doconvtran, const int* cnst_is_dry, const double* q,
+                        const double* fracis, double* ptend_q);
+
+/* zm_conv_tend's history diagnostics that involve arithmetic (zm_conv_intr.F90): freqzm (:685-688, 1 where the
+ * column convects), mu_out / md_out (:575-576, 700-706: ungathered mass fluxes in kg/m2/s), pcont / pconb (:721-729:
+ * pressure at cloud top / base, ps elsewhere).  ps, freqzm, pcont, pconb are (pcols); pmid, mu, md, mu_out, md_out
+ * (pcols,pver).  In the host-pointer variant mu, md, jt, maxg, ideep, lengath may all be NULL: they are then taken
+ * from the device pbuf mirror of the calling thread's last zm_conv_tend_batch. */
+int zm_conv_tend_diag_batch(int nchunks, const int* ncol, const double* ps, const double* pmid, const double* mu,
+                            const double* md, const int* jt, const int* maxg, const int* ideep, const int* lengath,
+                            double* freqzm, double* mu_out, double* md_out, double* pcont, double* pconb);
+int zm_conv_tend_diag_batch_dev(int nchunks, const int* ncol, const double* ps, const double* pmid, const double* mu,
+                            const double* md, const int* jt, const int* maxg, const int* ideep, const int* lengath,
+                            double* freqzm, double* mu_out, double* md_out, double* pcont, double* pconb,
+                            void* stream);
+
 /* Pipeline timeline of the calling thread's last zm_conv_tend_batch (diagnostics): per sub-batch six times in
  * ms (inputs on device, late inputs on device, zm_convr done, all kernels done, zm_convr outputs on host,
  * remaining outputs on host).  Returns the number of sub-batches; fills at most cap doubles. */
@@ -242,9 +270,13 @@ double zm_fp64_peak_flops(int iters);
 #define ZM_MICROBENCH_N 20
 int zm_microbench(long long* cycles, int cap, int n);
 /* per-kernel device time (ms) of the last zm_convr_batch[_dev] call made with profiling on:
- * names/ms arrays of length *n (max 16). */
+ * names/ms arrays of length *n (max 24). */
 int zm_set_profiling(int on);
 int zm_get_kernel_times(int* n, const char** names, float* ms);
+/* the same device times under the reference's GPTL timer names (zm_conv_intr.F90:654-880, 1019-1025):
+ * zm_convr, zm_conv_evap, momtran, convtran1, convtran2 (+ physics_update for the glue kernels); *n in = capacity
+ * (>= 6), out = count.  Covers the calling thread's last profiled zm_conv_tend_batch_dev and zm_conv_tend_2_batch. */
+int zm_get_timers(int* n, const char** names, float* ms);
 /* number of kernel launches issued by this thread since the last call (bench's gpu_launches) */
 long long zm_launch_count(int reset);
 

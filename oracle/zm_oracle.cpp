@@ -69,6 +69,11 @@ thread_local int brent_fail;
 // tl_* point at the chunk being processed; the batch drivers set them from the batch-wide base pointers.
 thread_local const double* tl_org = nullptr; thread_local double* tl_orgt = nullptr; thread_local double* tl_org2d = nullptr;
 const double* batch_org = nullptr; double* batch_orgt = nullptr; double* batch_org2d = nullptr;
+// convtran1 of zm_conv_tend (zm_conv_intr.F90:865-880), attached with zmo_convtran1_fields for the next
+// zmo_conv_tend_batch: state%q / fracis / ptend_loc%q, (pcols,pver,pcnst) per chunk
+struct Tran1 { int pcnst = 0; const int* doconv = nullptr; const int* dry = nullptr; const double* q = nullptr;
+               const double* fracis = nullptr; double* ptend_q = nullptr; };
+Tran1 batch_tran1;
 thread_local int* trace_buf = nullptr; thread_local int trace_n = 0, trace_cap = 0;
 
 inline double fmax2(double a, double b) { return (a > b) ? a : b; }
@@ -2069,17 +2074,61 @@ static int conv_tend_chunk(int lchnk, int ncol, const double* t, const double* q
         tl_orgt[e] = tl_orgt[e] + x;
       }
   }
-  const int domom[2] = {1, 1};
-  zmo_momtran(lchnk, ncol, domom, winds.data(), 2, mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, 1,
-              *lengath, 0, wtend.data(), pgu.data(), pgd.data(), icwu.data(), icwd.data(), ztodt, seten.data());
+  // momentum transport is skipped by the cam3 physics package (zm_conv_intr.F90:808-859): ptend_all then carries
+  // no wind tendency and no KE-dissipation heating
+  if (!g.cam3) {
+    const int domom[2] = {1, 1};
+    zmo_momtran(lchnk, ncol, domom, winds.data(), 2, mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, 1,
+                *lengath, 0, wtend.data(), pgu.data(), pgd.data(), icwu.data(), icwd.data(), ztodt, seten.data());
+  }
   for (size_t e = 0; e < n2; ++e) {
-    ptend_s[e] = (heat[e] + ev_s[e]) + seten[e];
+    ptend_s[e] = g.cam3 ? (heat[e] + ev_s[e]) : (heat[e] + ev_s[e]) + seten[e];
     ptend_q[e] = qtnd[e] + ev_q[e];
-    ptend_u[e] = wtend[e];
-    ptend_v[e] = wtend[n2 + e];
+    ptend_u[e] = g.cam3 ? 0.0 : wtend[e];
+    ptend_v[e] = g.cam3 ? 0.0 : wtend[n2 + e];
     evapcdp[e] = ev_q[e];
   }
+  // convtran1 (zm_conv_intr.F90:865-880): cloud liquid / ice (cnst_is_convtran1) on state1%q -- constituents
+  // m >= 2 of state1 are those of state (only q(:,:,1), and the org tracer under zm_org, were updated) --
+  // with the mass fluxes of this step and fake_dpdry = 0
+  if (batch_tran1.pcnst > 0) {
+    const size_t n3 = n2 * batch_tran1.pcnst, off = (size_t)(lchnk - 1) * n3;
+    std::vector<double> fake_dpdry(n2, 0.0);
+    zmo_convtran(lchnk, batch_tran1.doconv, batch_tran1.q + off, batch_tran1.pcnst, mu, md, du, eu, ed, dp, dsubcld,
+                 jt, maxg, ideep, 1, *lengath, 0, batch_tran1.fracis + off, batch_tran1.ptend_q + off,
+                 fake_dpdry.data(), ztodt, batch_tran1.dry);
+  }
   return fails;
+}
+
+void zmo_convtran1_fields(int pcnst, const int* doconvtran, const int* cnst_is_dry, const double* q,
+                          const double* fracis, double* ptend_q) {
+  batch_tran1 = Tran1{pcnst, doconvtran, cnst_is_dry, q, fracis, ptend_q};
+}
+
+// zm_conv_tend's history diagnostics that involve arithmetic (zm_conv_intr.F90:685-688, 700-706, 721-729), one chunk:
+// freqzm, the ungathered mass fluxes mu_out / md_out in kg/m2/s, and the cloud top / base pressures pcont / pconb
+void zmo_conv_tend_diag(int ncol, const double* ps, const double* pmid_, const double* mu_, const double* md_,
+                        const int* jt, const int* maxg, const int* ideep, int lengath, double* freqzm,
+                        double* mu_out_, double* md_out_, double* pcont, double* pconb) {
+  const int pcols = g.pcols, pver = g.pver;
+  C2 pmid{pmid_, pcols}, mu{mu_, pcols}, md{md_, pcols};
+  A2 mu_out{mu_out_, pcols}, md_out{md_out_, pcols};
+  for (int i = 1; i <= pcols; ++i) freqzm[i - 1] = 0.0;
+  for (int i = 1; i <= lengath; ++i) freqzm[ideep[i - 1] - 1] = 1.0;
+  for (int k = 1; k <= pver; ++k) for (int i = 1; i <= pcols; ++i) { mu_out(i, k) = 0.0; md_out(i, k) = 0.0; }  // :575-576
+  for (int i = 1; i <= lengath; ++i)
+    for (int k = 1; k <= pver; ++k) {
+      const int ii = ideep[i - 1];
+      mu_out(ii, k) = mu(i, k) * 100.0 / g.gravit;
+      md_out(ii, k) = md(i, k) * 100.0 / g.gravit;
+    }
+  for (int i = 1; i <= ncol; ++i) { pcont[i - 1] = ps[i - 1]; pconb[i - 1] = ps[i - 1]; }
+  for (int i = 1; i <= lengath; ++i)
+    if (maxg[i - 1] > jt[i - 1]) {
+      pcont[ideep[i - 1] - 1] = pmid(ideep[i - 1], jt[i - 1]);
+      pconb[ideep[i - 1] - 1] = pmid(ideep[i - 1], maxg[i - 1]);
+    }
 }
 
 int zmo_conv_tend_batch(int nchunks, const int* ncol, const double* t, const double* q, const double* u,
@@ -2111,6 +2160,7 @@ int zmo_conv_tend_batch(int nchunks, const int* ncol, const double* t, const dou
         dlf + c * L, mu + c * L, md + c * L, du + c * L, eu + c * L, ed + c * L, dp + c * L, dsubcld + c * pc,
         jt + c * pc, maxg + c * pc, ideep + c * pc, lengath + c, cape + c * pc);
   }
+  batch_tran1 = Tran1{};        // one-shot, like the attached org fields
   return fails;
 }
 

@@ -130,6 +130,15 @@ int zmo_conv_tend_batch(int nchunks, const int* ncol, const double* t, const dou
                         double* eu, double* ed, double* dp, double* dsubcld, int* jt, int* maxg, int* ideep,
                         int* lengath, double* cape, int nthreads);
 
+/* convtran1 inside zm_conv_tend (zm_conv_intr.F90:865-880): attach state%q, fracis and ptend_loc%q
+ * ((pcols,pver,pcnst) per chunk, chunks back to back) and the constituent flags for the NEXT zmo_conv_tend_batch. */
+void zmo_convtran1_fields(int pcnst, const int* doconvtran, const int* cnst_is_dry, const double* q,
+                          const double* fracis, double* ptend_q);
+/* zm_conv_tend's diagnostics with arithmetic (zm_conv_intr.F90:685-688, 700-706, 721-729), one chunk */
+void zmo_conv_tend_diag(int ncol, const double* ps, const double* pmid, const double* mu, const double* md,
+                        const int* jt, const int* maxg, const int* ideep, int lengath, double* freqzm,
+                        double* mu_out, double* md_out, double* pcont, double* pconb);
+
 /* N4 neighbours: geopotential_t (geopotential.F90:153-247; dycore_lr selects the FV 'LR'
  * branch, else EUL/SE) and convect_diagnostics_calc for shallow_scheme='CLUBB_SGS'
  * (convect_diagnostics.F90:115-249).  Single chunk, Fortran layout. */

@@ -199,11 +199,33 @@ class Oracle:
                              _dp(o["icwd"]), C.c_double(dt), _dp(o["seten"]))
         return o
 
-    def conv_tend_batch(self, ch, nthreads=0, org=None):
-        """zm_conv_tend sequence on soundings.Chunks; same output names as zm_conv.zm_conv_tend."""
+    def conv_tend_diag(self, ncol, ps, pmid, mu, md, jt, maxg, ideep, lengath):
+        """freqzm, mu_out, md_out, pcont, pconb of zm_conv_tend (zm_conv_intr.F90:685-729), one chunk."""
+        P = self.params
+        L, pc = P.pver, P.pcols
+        o = dict(freqzm=np.zeros(pc), mu_out=np.zeros((L, pc)), md_out=np.zeros((L, pc)), pcont=np.zeros(pc),
+                 pconb=np.zeros(pc))
+        self.lib.zmo_conv_tend_diag(C.c_int(int(ncol)), _dp(_f(ps)), _dp(_f(pmid)), _dp(_f(mu)), _dp(_f(md)),
+                                    _ip(np.ascontiguousarray(jt, np.int32)), _ip(np.ascontiguousarray(maxg, np.int32)),
+                                    _ip(np.ascontiguousarray(ideep, np.int32)), C.c_int(int(lengath)),
+                                    _dp(o["freqzm"]), _dp(o["mu_out"]), _dp(o["md_out"]), _dp(o["pcont"]),
+                                    _dp(o["pconb"]))
+        return o
+
+    def conv_tend_batch(self, ch, nthreads=0, org=None, convtran1=None):
+        """zm_conv_tend sequence on soundings.Chunks; same output names as zm_conv.zm_conv_tend.
+        convtran1 = dict(doconvtran, cnst_is_dry, q, fracis[, ptend_q]) adds zm_conv_intr.F90:865-880 -> out["ptend_qc"]."""
         P = self.params
         nch, L, pc = ch.nchunks, P.pver, P.pcols
         out = {}
+        if convtran1 is not None:
+            q3, f3 = _f(convtran1["q"]), _f(convtran1["fracis"])
+            out["ptend_qc"] = np.zeros_like(q3) if convtran1.get("ptend_q") is None else _f(convtran1["ptend_q"]).copy()
+            do = np.ascontiguousarray(convtran1["doconvtran"], np.int32)
+            dry = np.ascontiguousarray(convtran1["cnst_is_dry"] if convtran1.get("cnst_is_dry") is not None
+                                       else np.zeros(q3.shape[1]), np.int32)
+            self._tran1_keep = (q3, f3, do, dry)
+            self.lib.zmo_convtran1_fields(C.c_int(q3.shape[1]), _ip(do), _ip(dry), _dp(q3), _dp(f3), _dp(out["ptend_qc"]))
         if org is not None:
             org = _f(org)
             out["orgt"], out["org2d"] = np.full_like(org, 7.0), np.zeros_like(org)

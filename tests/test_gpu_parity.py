@@ -375,6 +375,84 @@ def test_conv_tend_2_uses_device_mirror(built):
         Z.zm_conv_tend_2(do, q, pdeldry, fracis, ch.ztodt, dry)
 
 
+def test_pbuf_mirror_survives_the_calls_between_tend_and_tend_2(built):
+    """The model runs geopotential_t / convect_diagnostics_calc (and anything else that stages host arrays) between
+    zm_conv_tend and zm_conv_tend_2 (physpkg.F90:2820, 2885, 1988): the device pbuf mirror must survive them, whatever
+    their sizes.  A failed tend call leaves no mirror."""
+    Z = init_cuda(16, 32)
+    o, _, _ = get_oracle("pm", 16, 32)
+    ch = S.make_chunks(640, 32, 16, p_conv=0.6)
+    ref = o.conv_tend_batch(ch)
+    Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt, keep_pbuf_on_device=True)
+    # same-size and larger host-pointer calls in between: each restages the thread's staging arena
+    big = S.make_chunks(4000, 32, 16, p_conv=0.5)
+    for cc in (ch, big):
+        piln, pmln, rpdel = np.log(cc.pint), np.log(cc.pmid), 1.0 / cc.pdel
+        rair = np.full_like(cc.t, 287.04); zvir = np.full_like(cc.t, 0.608)
+        Z.geopotential_t(cc.ncol, piln, pmln, cc.pint, cc.pmid, cc.pdel, rpdel, cc.t, cc.q, rair, 9.80616, zvir)
+        cuda_convr(Z, cc)
+        n = cc.nchunks
+        Z.convect_diagnostics_calc(cc.ncol, np.zeros((n, 33, 16)), np.zeros((n, 32, 16)), np.zeros((n, 16)), cc.pmid,
+                                   np.zeros((n, 32, 16)), np.full((n, 16), 20.0), np.full((n, 16), 30.0))
+    pcnst = 6
+    q, fracis, pdeldry = S.make_tracers(ch, pcnst)
+    do, dry = [0, 1, 1, 0, 1, 1], [0, 0, 1, 0, 1, 0]
+    dq = Z.zm_conv_tend_2(do, q, pdeldry, fracis, ch.ztodt, dry)
+    dpdry = dpdry_gathered(ch, ref, pdeldry)
+    for c in range(ch.nchunks):
+        r = o.convtran(do, q[c], ref["mu"][c], ref["md"][c], ref["du"][c], ref["eu"][c], ref["ed"][c], ref["dp"][c],
+                       ref["dsubcld"][c], ref["jt"][c], ref["maxg"][c], ref["ideep"][c], ref["lengath"][c], fracis[c],
+                       dpdry[c], ch.ztodt, dry)
+        for m in range(pcnst):
+            assert np.array_equal(dq[c, m], r[m] if do[m] else np.zeros_like(r[m])), (c, m)
+    assert np.count_nonzero(dq) > 0
+    # the diagnostics of zm_conv_tend from the same mirror (zm_conv_intr.F90:685-729)
+    ps = ch.pint[:, -1, :]
+    dg = Z.zm_conv_tend_diag(ch.ncol, ps, ch.pmid)
+    dg2 = Z.zm_conv_tend_diag(ch.ncol, ps, ch.pmid, ref["mu"], ref["md"], ref["jt"], ref["maxg"], ref["ideep"], ref["lengath"])
+    for c in range(ch.nchunks):
+        r = o.conv_tend_diag(ch.ncol[c], ps[c], ch.pmid[c], ref["mu"][c], ref["md"][c], ref["jt"][c], ref["maxg"][c],
+                             ref["ideep"][c], ref["lengath"][c])
+        for k in r:
+            assert np.array_equal(dg[k][c], r[k]) and np.array_equal(dg2[k][c], r[k]), (c, k)
+    assert dg["freqzm"].sum() == ref["lengath"].sum() and np.any(dg["pcont"] < ps)
+    # a tend call that fails (zm_org without attached fields) leaves no mirror behind
+    Z2 = init_cuda(16, 32, zm_org=1)
+    with pytest.raises(Z2.ZmError):
+        Z2.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt, keep_pbuf_on_device=True)
+    with pytest.raises(Z2.ZmError):
+        Z2.zm_conv_tend_2(do, q, pdeldry, fracis, ch.ztodt, dry)
+
+
+@pytest.mark.parametrize("ncols,cam3", [(1600, False), (16 * 1100, False), (900, True)])
+def test_conv_tend_with_convtran1_and_cam3(built, ncols, cam3):
+    """zm_conv_tend including convtran1 (zm_conv_intr.F90:865-880: cloud liquid / ice on state1%q, fake_dpdry = 0),
+    unpipelined and pipelined (sub-batches move only the flagged constituent slices), and the cam3 package, which
+    skips momtran (zm_conv_intr.F90:808): every output bit for bit against the oracle."""
+    over = dict(cam3=1, num_cin=5) if cam3 else {}
+    Z = init_cuda(16, 32, **over)
+    o, _, _ = get_oracle("pm", 16, 32, **over)
+    ch = S.make_chunks(ncols, 32, 16, p_conv=0.55)
+    pcnst = 7
+    q, fracis, _ = S.make_tracers(ch, pcnst)
+    q[:, 0] = ch.q
+    t1 = dict(doconvtran=[1, 1, 1, 0, 0, 1, 0], cnst_is_dry=[0] * pcnst, q=q, fracis=fracis,
+              ptend_q=np.full_like(q, 3.0))
+    ref = o.conv_tend_batch(ch, convtran1=t1)
+    out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt, convtran1=t1)
+    assert_same(out, ref, TEND_KEYS, 16, exact=True, what="zm_conv_tend + convtran1")
+    assert np.array_equal(out["ptend_qc"], ref["ptend_qc"])
+    assert np.all(out["ptend_qc"][:, [0, 3, 4, 6]] == 3.0)          # water vapour and unflagged slices untouched
+    assert np.count_nonzero(out["ptend_qc"][:, [1, 2, 5]]) > 0 and not np.any(out["ptend_qc"][:, [1, 2, 5]] == 3.0)
+    if cam3:
+        assert np.all(out["ptend_u"] == 0.0) and np.all(out["ptend_v"] == 0.0)
+    else:
+        assert np.count_nonzero(out["ptend_u"]) > 0
+    # the attachment is one-shot
+    out2 = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
+    assert "ptend_qc" not in out2 and np.array_equal(out2["ptend_s"], out["ptend_s"])
+
+
 def test_finalize_releases_and_reinit_reproduces(built):
     """zm_finalize frees the thread's arenas/streams; a fresh zm_init + step gives the same bits, and the
     pipelined host API (ramp schedule: 6 sub-batches of 1,1,2,4,4,4 sixteenths; then 8 equal ones) equals the
