@@ -1655,6 +1655,40 @@ int zm_conservation_dev(int nchunks, const int* ncol, const double* pdel, const 
   return 0;
 }
 
+// zm_conv_tend_2 (zm_conv_intr.F90:955-1028) on device arrays: dpdry gather (:1014-1017) + convtran (:1020-1024)
+// with the pbuf fields zm_conv_tend_batch_dev left in the caller's device arrays.  Enqueue on the stream the tend
+// step ran on (the scratch arena is shared and reused in stream order).
+int zm_conv_tend_2_batch_dev(int nchunks, const int* doconvtran, const double* q, int pcnst, const double* pdeldry,
+                             const double* fracis, double* ptend_q, double ztodt, const int* cnst_is_dry,
+                             const double* mu, const double* md, const double* du, const double* eu,
+                             const double* ed, const double* dp, const double* dsubcld, const int* jt,
+                             const int* maxg, const int* ideep, const int* lengath, void* stream) {
+  NEED_INIT();
+  (void)dsubcld; (void)ztodt;
+  if (nchunks <= 0) return 0;
+  const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc, n2 = nc * L;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (tls_tmeta.set(doconvtran, cnst_is_dry, pcnst)) return -100;
+  if (tls_tmeta.nactive == 0) return 0;
+  Workspace& ws = tls_work;
+  if (ws.ensure(chunk_bounds_bytes(nchunks, (int)nc) + al(n2, 8) + 1024)) return -100;
+  double* dpdry = ws.take<double>(n2);
+  for (auto e : ws.tev) cudaEventDestroy(e);
+  ws.tev.clear(); ws.tnames.clear();
+  tick(ws, s, "start");
+  k_dpdry_gather<<<592, 256, 0, s>>>(nchunks, ideep, lengath, pdeldry, dpdry); ++tls_launches;
+  TranArgs a;
+  a.nchunks = nchunks; a.ncnst = pcnst; a.nactive = tls_tmeta.nactive; a.jt = jt; a.mx = maxg; a.ideep = ideep;
+  a.lengath = lengath; a.active = tls_tmeta.active(); a.is_dry = tls_tmeta.dry();
+  a.q = q; a.fracis = fracis; a.mu = mu; a.md = md; a.du = du; a.eu = eu; a.ed = ed; a.dp = dp;
+  a.dpdry = dpdry; a.dqdt = ptend_q;
+  ChunkBounds cb;
+  if (chunk_bounds_enqueue(ws, s, nchunks, jt, maxg, lengath, cb)) return -100;
+  const int rc = convtran_enqueue(s, a, cb);
+  tick(ws, s, "convtran2");
+  return rc;
+}
+
 // zm_conv_tend_2 (zm_conv_intr.F90:955-1028): convtran over the constituents flagged convtran2, with the
 // mass-flux fields of this thread's last zm_conv_tend_batch taken from the device mirror.
 int zm_conv_tend_2_batch(int nchunks, const int* doconvtran, const double* q, int pcnst, const double* pdeldry,

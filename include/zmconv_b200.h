@@ -205,6 +205,13 @@ int zm_convect_diagnostics_batch_dev(int nchunks, const int* ncol, double* cmfmc
  * q, fracis, ptend_q are (pcols,pver,pcnst); pdeldry is (pcols,pver). */
 int zm_conv_tend_2_batch(int nchunks, const int* doconvtran, const double* q, int pcnst, const double* pdeldry,
                          const double* fracis, double* ptend_q, double ztodt, const int* cnst_is_dry);
+/* the same on DEVICE arrays, the pbuf fields being the caller's own device arrays (as zm_conv_tend_batch_dev filled
+ * them); doconvtran / cnst_is_dry stay HOST flags.  Enqueue on the stream the tend step ran on. */
+int zm_conv_tend_2_batch_dev(int nchunks, const int* doconvtran, const double* q, int pcnst, const double* pdeldry,
+                         const double* fracis, double* ptend_q, double ztodt, const int* cnst_is_dry,
+                         const double* mu, const double* md, const double* du, const double* eu,
+                         const double* ed, const double* dp, const double* dsubcld, const int* jt,
+                         const int* maxg, const int* ideep, const int* lengath, void* stream);
 
 /* zm_org = 1 (zmconv_org): attach the pointer dummies org / orgt / org2d of zm_convr
  * (zm_conv.F90:242, 421-423; zm_conv_intr.F90:656-659) for the NEXT zm_convr_batch / zm_conv_tend_batch [_dev] call

@@ -2101,6 +2101,32 @@ static int conv_tend_chunk(int lchnk, int ncol, const double* t, const double* q
   return fails;
 }
 
+// zm_conv_tend_2 (zm_conv_intr.F90:955-1028) chunk by chunk under OpenMP: dpdry(i,:) = pdeldry(ideep(i),:)/100 for
+// i <= lengath, 0 beyond (:1014-1017), then convtran (:1020-1024)
+int zmo_conv_tend_2_batch(int nchunks, const int* doconvtran, const double* q, int pcnst, const double* pdeldry,
+                          const double* fracis, double* ptend_q, double ztodt, const int* cnst_is_dry,
+                          const double* mu, const double* md, const double* du, const double* eu, const double* ed,
+                          const double* dp, const double* dsubcld, const int* jt, const int* maxg, const int* ideep,
+                          const int* lengath, int nthreads) {
+  const size_t pc = g.pcols, L = (size_t)g.pcols * g.pver, n3 = L * pcnst;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+  (void)nthreads;
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int c = 0; c < nchunks; ++c) {
+    std::vector<double> dpdry(L, 0.0);
+    for (int i = 0; i < lengath[c]; ++i)
+      for (int k = 0; k < g.pver; ++k)
+        dpdry[(size_t)k * pc + i] = pdeldry[c * L + (size_t)k * pc + (ideep[c * pc + i] - 1)] / 100.0;
+    zmo_convtran(c + 1, doconvtran, q + c * n3, pcnst, mu + c * L, md + c * L, du + c * L, eu + c * L, ed + c * L,
+                 dp + c * L, dsubcld + c * pc, jt + c * pc, maxg + c * pc, ideep + c * pc, 1, lengath[c], 0,
+                 fracis + c * n3, ptend_q + c * n3, dpdry.data(), ztodt, cnst_is_dry);
+  }
+  return 0;
+}
+
 void zmo_convtran1_fields(int pcnst, const int* doconvtran, const int* cnst_is_dry, const double* q,
                           const double* fracis, double* ptend_q) {
   batch_tran1 = Tran1{pcnst, doconvtran, cnst_is_dry, q, fracis, ptend_q};

@@ -130,6 +130,12 @@ int zmo_conv_tend_batch(int nchunks, const int* ncol, const double* t, const dou
                         double* eu, double* ed, double* dp, double* dsubcld, int* jt, int* maxg, int* ideep,
                         int* lengath, double* cape, int nthreads);
 
+/* zm_conv_tend_2 (zm_conv_intr.F90:955-1028): dpdry gather + convtran2, OpenMP over chunks */
+int zmo_conv_tend_2_batch(int nchunks, const int* doconvtran, const double* q, int pcnst, const double* pdeldry,
+                          const double* fracis, double* ptend_q, double ztodt, const int* cnst_is_dry,
+                          const double* mu, const double* md, const double* du, const double* eu, const double* ed,
+                          const double* dp, const double* dsubcld, const int* jt, const int* maxg, const int* ideep,
+                          const int* lengath, int nthreads);
 /* convtran1 inside zm_conv_tend (zm_conv_intr.F90:865-880): attach state%q, fracis and ptend_loc%q
  * ((pcols,pver,pcnst) per chunk, chunks back to back) and the constituent flags for the NEXT zmo_conv_tend_batch. */
 void zmo_convtran1_fields(int pcnst, const int* doconvtran, const int* cnst_is_dry, const double* q,

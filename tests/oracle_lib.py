@@ -199,6 +199,19 @@ class Oracle:
                              _dp(o["icwd"]), C.c_double(dt), _dp(o["seten"]))
         return o
 
+    def conv_tend_2_batch(self, doconvtran, q, pdeldry, fracis, ztodt, cnst_is_dry, tend, ptend_q=None, nthreads=0):
+        """zm_conv_tend_2 (zm_conv_intr.F90:955-1028) over all chunks with the pbuf fields of `tend`
+        (a conv_tend_batch result)."""
+        q = _f(q)
+        nch, pcnst = q.shape[0], q.shape[1]
+        dq = np.zeros_like(q) if ptend_q is None else _f(ptend_q).copy()
+        i32 = lambda a: _ip(np.ascontiguousarray(a, np.int32))
+        self.lib.zmo_conv_tend_2_batch(C.c_int(nch), i32(doconvtran), _dp(q), C.c_int(pcnst), _dp(_f(pdeldry)),
+                                       _dp(_f(fracis)), _dp(dq), C.c_double(ztodt), i32(cnst_is_dry),
+                                       *[_dp(_f(tend[k])) for k in ("mu", "md", "du", "eu", "ed", "dp", "dsubcld")],
+                                       *[i32(tend[k]) for k in ("jt", "maxg", "ideep", "lengath")], C.c_int(nthreads))
+        return dq
+
     def conv_tend_diag(self, ncol, ps, pmid, mu, md, jt, maxg, ideep, lengath):
         """freqzm, mu_out, md_out, pcont, pconb of zm_conv_tend (zm_conv_intr.F90:685-729), one chunk."""
         P = self.params

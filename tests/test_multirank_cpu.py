@@ -33,8 +33,9 @@ def _worker(rank, world, port, ncols, q):
     from cam_nor_physics_b200 import soundings as S
     from helpers import get_oracle
     o, _, _ = get_oracle("libm", 16, 32)
-    per = ncols // world
-    ch = S.make_chunks(per, 32, 16, p_conv=0.5, col0=rank * per)
+    import bench                                     # the product's host-side partition of the grid (bench.shard_of)
+    col0, per = bench.shard_of(rank, world, ncols, "strong")
+    ch = S.make_chunks(per, 32, 16, p_conv=0.5, col0=col0)
     r = o.conv_tend_batch(ch, nthreads=2)
     w = torch.from_numpy(_budget(o, ch, r))
     dist.all_reduce(w)
@@ -47,7 +48,7 @@ def test_two_rank_sharding_matches_single_rank(built):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from cam_nor_physics_b200 import soundings as S
     from helpers import get_oracle
-    ncols, world = 16 * 12, 2
+    ncols, world = 16 * 13 + 5, 2            # 14 chunks, the last one ragged: ranks get 7 chunks each
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
@@ -67,3 +68,20 @@ def test_two_rank_sharding_matches_single_rank(built):
     for rk in range(world):
         assert np.allclose(res[rk][1], w1, rtol=1e-13, atol=1e-300)
     assert w1[4] > 0 and w1[5] == ncols
+
+
+def test_shard_partition_covers_the_grid_in_whole_chunks():
+    """bench.shard_of: strong scaling cuts ONE grid into contiguous blocks of whole pcols=16 chunks (chunk c -> rank
+    floor(c*world/nchunks)); weak scaling gives every rank its own grid."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for ncols in (55296, 13824, 16 * 13 + 5, 17):
+        for world in (1, 2, 3, 4, 8):
+            parts = [bench.shard_of(r, world, ncols, "strong") for r in range(world)]
+            assert parts[0][0] == 0 and sum(n for _, n in parts) == ncols
+            for (c0, n), (c1, _) in zip(parts, parts[1:]):
+                assert c0 + n == c1 and c1 % 16 == 0
+            assert all(n >= 0 for _, n in parts)
+            if ncols % (16 * world) == 0:
+                assert len({n for _, n in parts}) == 1
+    assert bench.shard_of(3, 8, 55296, "weak") == (3 * 55296, 55296)
