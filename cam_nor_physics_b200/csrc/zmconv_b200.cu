@@ -14,6 +14,11 @@
 #include <string>
 #include <mutex>
 #include <chrono>
+#include <thread>
+#include <condition_variable>
+#include <functional>
+#include <atomic>
+#include <deque>
 
 namespace {
 
@@ -104,6 +109,106 @@ thread_local Workspace tls_stage;    // device staging of user arrays for the ho
 thread_local Workspace tls_stage2;   // staging for zm_conv_tend_2_batch
 thread_local Workspace tls_mirror_ws; // the device pbuf mirror (see PbufMirror)
 
+// Host worker threads of the sparse return path (zero-fill of the caller's dense output arrays while the GPU works,
+// then the scatter of the convective columns' records): ZM_HOST_THREADS, default min(8, hardware threads).
+class HostPool {
+ public:
+  explicit HostPool(int n) {
+    for (int i = 0; i < n; ++i) th_.emplace_back([this] { run(); });
+  }
+  ~HostPool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int size() const { return (int)th_.size(); }
+  void submit(std::function<void()> f) {
+    { std::lock_guard<std::mutex> lk(mu_); q_.push_back(std::move(f)); ++pending_; }
+    cv_.notify_one();
+  }
+  void wait_all() {
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+ private:
+  void run() {
+    for (;;) {
+      std::function<void()> f;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+        if (stop_ && q_.empty()) return;
+        f = std::move(q_.front()); q_.pop_front();
+      }
+      f();
+      { std::lock_guard<std::mutex> lk(mu_); if (--pending_ == 0) done_.notify_all(); }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::deque<std::function<void()>> q_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+HostPool& host_pool() {
+  static HostPool* pool = [] {
+    int n = 0;
+    if (const char* e = getenv("ZM_HOST_THREADS")) n = atoi(e);
+    if (n <= 0) { n = (int)std::thread::hardware_concurrency(); n = n > 8 ? 8 : (n < 1 ? 1 : n); }
+    return new HostPool(n > 64 ? 64 : n);
+  }();
+  return *pool;
+}
+
+// Sparse return of zm_conv_tend_batch: the 2-D outputs are zero outside the convective columns (zm_conv.F90:559-563,
+// 625-650; zm_conv_evap and momtran add nothing where zm_convr produced no rain and no mass flux), so only the
+// convective columns' levels travel device -> host, as one record per column, and worker threads scatter them into
+// the caller's arrays, which they zero-filled while the GPU was busy.  Field order of a record:
+enum { SF_PS, SF_PQ, SF_PU, SF_PV, SF_CME, SF_ZDU, SF_QL, SF_RPRD, SF_EVAP, SF_DLF,     // (pcols,pver), by column
+       SF_MCON, SF_PFLX, SF_FP, SF_FS,                                                   // (pcols,pverp), by column
+       SF_MU, SF_MD, SF_DU, SF_EU, SF_ED, SF_DP,                                         // (pcols,pver), by gathered slot
+       SF_N };
+struct SparseFields {
+  const double* d[SF_N];     // device arrays (sub-batch slice), NULL = not packed
+  int off[SF_N];             // offset of the field inside a record (doubles), -1 = absent
+  int rec_len;               // doubles per record
+};
+// exclusive prefix of lengath over the chunks of a sub-batch (one block): base[c], total in base[nchunks]
+__global__ void k_lengath_scan(int nchunks, const int* lengath, int* base) {
+  __shared__ int part[1024];
+  const int t = threadIdx.x, per = (nchunks + blockDim.x - 1) / blockDim.x;
+  const int lo = min(t * per, nchunks), hi = min(lo + per, nchunks);
+  int sum = 0;
+  for (int c = lo; c < hi; ++c) sum += lengath[c];
+  part[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    int acc = 0;
+    for (int i = 0; i < blockDim.x; ++i) { const int v = part[i]; part[i] = acc; acc += v; }
+    base[nchunks] = acc;
+  }
+  __syncthreads();
+  int acc = part[t];
+  for (int c = lo; c < hi; ++c) { base[c] = acc; acc += lengath[c]; }
+}
+// one block per (chunk, gathered slot): the column's record
+__global__ void __launch_bounds__(64) k_pack_records(int nchunks, const int* lengath, const int* ideep, const int* base,
+                                                     SparseFields f, double* rec) {
+  const int pcols = P.pcols, pver = P.pver;
+  const int c = blockIdx.x / pcols, slot = blockIdx.x - c * pcols;
+  if (c >= nchunks || slot >= lengath[c]) return;
+  const int i = ideep[(size_t)c * pcols + slot] - 1;
+  double* r = rec + (size_t)(base[c] + slot) * f.rec_len;
+#pragma unroll
+  for (int q = 0; q < SF_N; ++q) {
+    if (f.off[q] < 0) continue;
+    const int nlev = (q >= SF_MCON && q <= SF_FS) ? pver + 1 : pver;
+    for (int k = threadIdx.x; k < nlev; k += blockDim.x)
+      r[f.off[q] + k] = f.d[q][cidx(c, k, q >= SF_MU ? slot : i, nlev)];
+  }
+}
+
 // Streams, events and per-sub-batch work arenas of the pipelined host-pointer zm_conv_tend_batch.
 struct TendPipe {
   static const int MAXB = 8;
@@ -112,6 +217,24 @@ struct TendPipe {
   cudaEvent_t in_ready[MAXB] = {}, late_ready[MAXB] = {}, convr_done[MAXB] = {}, done[MAXB] = {};
   cudaEvent_t early_back[MAXB] = {}, final_back[MAXB] = {}, t0 = nullptr;   // timeline of the last call (zm_tend_trace)
   int ninit = 0, last_nb = 0, dev_nb = 0;
+  // sparse return: pinned host staging of the records and of the per-sub-batch (lengath, ideep, count) triple
+  cudaEvent_t small_back[MAXB] = {}, rec_back[MAXB] = {};
+  double* h_rec = nullptr; size_t h_rec_cap = 0;       // doubles
+  int* h_small = nullptr; size_t h_small_cap = 0;      // ints
+  long long last_h2d = 0, last_d2h = 0;                // bytes moved by the last call (zm_tend_transfer_bytes)
+  int ensure_pinned(size_t rec_doubles, size_t small_ints) {
+    if (rec_doubles > h_rec_cap) {
+      if (h_rec) { CK(cudaDeviceSynchronize()); CK(cudaFreeHost(h_rec)); h_rec = nullptr; }
+      h_rec_cap = rec_doubles + (rec_doubles >> 2) + 1024;
+      CK(cudaHostAlloc((void**)&h_rec, h_rec_cap * sizeof(double), cudaHostAllocDefault));
+    }
+    if (small_ints > h_small_cap) {
+      if (h_small) { CK(cudaDeviceSynchronize()); CK(cudaFreeHost(h_small)); h_small = nullptr; }
+      h_small_cap = small_ints + 1024;
+      CK(cudaHostAlloc((void**)&h_small, h_small_cap * sizeof(int), cudaHostAllocDefault));
+    }
+    return 0;
+  }
   // ZM_TEND_SUBBATCHES (1..8, default 8); a sub-batch is never smaller than 128 chunks
   int subbatches(int nchunks) const {
     int nb = 8;
@@ -163,7 +286,10 @@ struct TendPipe {
     for (int b = 0; b < ninit; ++b) {
       cudaEventDestroy(in_ready[b]); cudaEventDestroy(late_ready[b]); cudaEventDestroy(convr_done[b]);
       cudaEventDestroy(done[b]); cudaEventDestroy(early_back[b]); cudaEventDestroy(final_back[b]);
+      cudaEventDestroy(small_back[b]); cudaEventDestroy(rec_back[b]);
     }
+    if (h_rec) { cudaFreeHost(h_rec); h_rec = nullptr; h_rec_cap = 0; }
+    if (h_small) { cudaFreeHost(h_small); h_small = nullptr; h_small_cap = 0; }
     ninit = 0; last_nb = 0; dev_nb = 0;
     if (t0) { cudaEventDestroy(t0); t0 = nullptr; }
     if (h2d) { cudaStreamDestroy(h2d); cudaStreamDestroy(d2h_early); cudaStreamDestroy(d2h_final); h2d = d2h_early = d2h_final = nullptr; }
@@ -182,6 +308,8 @@ struct TendPipe {
       CK(cudaEventCreate(&done[ninit]));
       CK(cudaEventCreate(&early_back[ninit]));
       CK(cudaEventCreate(&final_back[ninit]));
+      CK(cudaEventCreateWithFlags(&small_back[ninit], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&rec_back[ninit], cudaEventDisableTiming));
       // earlier sub-batches get higher stream priority: the first results reach the return stream sooner
       int lo = 0, hi = 0;
       CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // hi = greatest priority (numerically lowest)
@@ -1338,7 +1466,8 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   const size_t n2 = nc * L, n2p = nc * (L + 1);
   Workspace& st = tls_stage;
   tls_mirror = PbufMirror{};                 // whatever happens below, the previous step's mirror is gone
-  if (st.ensure(al(nchunks, 4) + 27 * al(n2, 8) + 6 * al(n2p, 8) + 14 * al(nc, 8) + 4 * al(nc, 4) + 8192))
+  if (st.ensure(al(nchunks, 4) + 27 * al(n2, 8) + 6 * al(n2p, 8) + 14 * al(nc, 8) + 4 * al(nc, 4) + 8192 +
+                al(nc * (20 * L + 4), 8) + al((size_t)nchunks + 16, 4)))
     return -100;
   Workspace& mw = tls_mirror_ws;
   if (mw.ensure(6 * al(n2, 8) + al(nc, 8) + 3 * al(nc, 4) + al(nchunks, 4) + 4096)) return -100;
@@ -1358,10 +1487,25 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   // whole batch (4: in, before the first sub-batch; 5: out, after the last) instead of once per sub-batch
   struct Arr { const void* h; void* d; size_t stride, esz; int kind; };
   std::vector<Arr> arrs; arrs.reserve(64);
+  // Return path of the 2-D outputs: "sparse" (default from 64 chunks on) moves only the convective columns' records
+  // and scatters them on the host into the arrays worker threads zero-filled meanwhile; ZM_TEND_RETURN=dense copies
+  // the arrays whole.  ZM_TEND_OUTPUTS_PREZEROED=1: the caller's arrays are all-zero on entry (as after
+  // physics_ptend_init), the zero-fill is skipped.
+  const char* ret_env = getenv("ZM_TEND_RETURN");
+  const bool sparse = ret_env ? !strcmp(ret_env, "sparse") : nchunks >= 64;
+  const bool prezeroed = getenv("ZM_TEND_OUTPUTS_PREZEROED") && atoi(getenv("ZM_TEND_OUTPUTS_PREZEROED")) != 0;
+  double* sf_host[SF_N] = {};               // caller's arrays of the sparse fields (NULL: not wanted)
+  double* sf_dev[SF_N] = {};
+  int sf_next = -1;                          // id of the sparse field the next dev() call stages
   bool to_mirror = false;                    // the pbuf fields go to the mirror arena
   auto dev = [&](const void* h, size_t stride, size_t esz, int kind, bool always = true) -> void* {
     void* d = (void*)(to_mirror ? mw : st).take<char>((size_t)nchunks * stride * esz);
     if (stride <= pc) kind = (kind <= 1) ? 4 : 5;
+    if (sf_next >= 0) {
+      sf_host[sf_next] = (double*)h; sf_dev[sf_next] = (double*)d;
+      if (sparse && h) kind = 6;             // no dense copy: travels in the records
+      sf_next = -1;
+    }
     if (h || always) arrs.push_back({h, d, stride, esz, h ? kind : -1});
     return d;
   };
@@ -1369,24 +1513,27 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
 #define DLATE(x, str) (const double*)dev(x, str, 8, 1)
 #define DOUTE(x, str) (double*)dev(x, str, 8, 2)
 #define DOUTF(x, str) (double*)dev(x, str, 8, 3)
+#define SPE(id, x, str) (sf_next = id, DOUTE(x, str))
+#define SPF(id, x, str) (sf_next = id, DOUTF(x, str))
   const int* d_ncol = (const int*)dev(ncol, 1, 4, 0);
   const double *d_t = DIN(t, s2), *d_q = DIN(q, s2), *d_pmid = DIN(pmid, s2), *d_pint = DIN(pint, s2p),
                *d_pdel = DIN(pdel, s2), *d_zm = DIN(zm, s2), *d_zi = DIN(zi, s2p), *d_phis = DIN(phis, s1),
                *d_pblh = DIN(pblh, s1), *d_tpert = DIN(tpert, s1), *d_lf = DIN(landfrac, s1);
   const double *d_u = DLATE(u, s2), *d_v = DLATE(v, s2), *d_cld = DLATE(cld, s2);
   to_mirror = true;
-  double *d_mu = DOUTE(mu, s2), *d_md = DOUTE(md, s2), *d_du = DOUTE(du, s2), *d_eu = DOUTE(eu, s2),
-         *d_ed = DOUTE(ed, s2), *d_dp = DOUTE(dp, s2), *d_dsub = DOUTE(dsubcld, s1);
+  double *d_mu = SPE(SF_MU, mu, s2), *d_md = SPE(SF_MD, md, s2), *d_du = SPE(SF_DU, du, s2), *d_eu = SPE(SF_EU, eu, s2),
+         *d_ed = SPE(SF_ED, ed, s2), *d_dp = SPE(SF_DP, dp, s2), *d_dsub = DOUTE(dsubcld, s1);
   int *d_jt = (int*)dev(jt, s1, 4, 2), *d_maxg = (int*)dev(maxg, s1, 4, 2), *d_ideep = (int*)dev(ideep, s1, 4, 2),
       *d_len = (int*)dev(lengath, 1, 4, 2);
   to_mirror = false;
   const PbufMirror new_mirror{nchunks, d_mu, d_md, d_du, d_eu, d_ed, d_dp, d_dsub, d_jt, d_maxg, d_ideep, d_len};
-  double *d_ps = DOUTF(ptend_s, s2), *d_pq = DOUTF(ptend_q, s2), *d_pu = DOUTF(ptend_u, s2), *d_pv = DOUTF(ptend_v, s2),
-         *d_mcon = DOUTF(mcon, s2p), *d_cme = DOUTE(cme, s2), *d_pflx = DOUTE(pflx, s2p), *d_zdu = DOUTE(zdu, s2),
+  double *d_ps = SPF(SF_PS, ptend_s, s2), *d_pq = SPF(SF_PQ, ptend_q, s2), *d_pu = SPF(SF_PU, ptend_u, s2),
+         *d_pv = SPF(SF_PV, ptend_v, s2), *d_mcon = SPF(SF_MCON, mcon, s2p), *d_cme = SPE(SF_CME, cme, s2),
+         *d_pflx = SPE(SF_PFLX, pflx, s2p), *d_zdu = SPE(SF_ZDU, zdu, s2),
          *d_rliq = DOUTE(rliq, s1), *d_rice = DOUTE(rice, s1), *d_jctop = DOUTE(jctop, s1), *d_jcbot = DOUTE(jcbot, s1),
-         *d_prec = DOUTF(prec, s1), *d_snow = DOUTF(snow, s1), *d_ql = DOUTE(ql, s2), *d_rprd = DOUTE(rprd, s2),
-         *d_evap = DOUTF(evapcdp, s2), *d_fp = DOUTF(flxprec, s2p), *d_fs = DOUTF(flxsnow, s2p), *d_dlf = DOUTE(dlf, s2),
-         *d_cape = DOUTE(cape, s1);
+         *d_prec = DOUTF(prec, s1), *d_snow = DOUTF(snow, s1), *d_ql = SPE(SF_QL, ql, s2), *d_rprd = SPE(SF_RPRD, rprd, s2),
+         *d_evap = SPF(SF_EVAP, evapcdp, s2), *d_fp = SPF(SF_FP, flxprec, s2p), *d_fs = SPF(SF_FS, flxsnow, s2p),
+         *d_dlf = SPE(SF_DLF, dlf, s2), *d_cape = DOUTE(cape, s1);
   const OrgFields of = tls_org; tls_org = OrgFields{};       // one-shot
   const double* d_org = nullptr; double *d_orgt = nullptr, *d_org2d = nullptr;
   if (g_params.zm_org) {
@@ -1400,6 +1547,21 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
 #undef DLATE
 #undef DOUTE
 #undef DOUTF
+#undef SPE
+#undef SPF
+  // sparse return: record layout (fields the caller asked for), device record buffer sized for the worst case so
+  // that a sub-batch's region does not depend on the counts of the others
+  int sf_off[SF_N], rec_len = 0;
+  for (int qf = 0; qf < SF_N; ++qf) {
+    const int nlev = (qf >= SF_MCON && qf <= SF_FS) ? (int)L + 1 : (int)L;
+    if (sparse && sf_host[qf]) { sf_off[qf] = rec_len; rec_len += nlev; } else sf_off[qf] = -1;
+  }
+  double* d_rec = nullptr; int* d_base = nullptr;
+  if (sparse && rec_len > 0) {
+    d_rec = st.take<double>(nc * rec_len);
+    d_base = st.take<int>((size_t)nchunks + TendPipe::MAXB + 1);
+    if (tp.ensure_pinned(0, 2 * (nc + nchunks + 2 * TendPipe::MAXB))) return -100;
+  }
   // convtran1 (zm_conv_intr.F90:865-880): only the slices of the transported constituents travel; on the device
   // they are stored compactly, (pcols,pver,nactive) per chunk
   const Tran1Fields tf = tls_tran1; tls_tran1 = Tran1Fields{};   // one-shot
@@ -1445,16 +1607,25 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
       return -100;                                                                                  \
     }                                                                                               \
   } while (0)
+  long long moved_h2d = 0, moved_d2h = 0;
+  // zero-fill of the caller's arrays of the sparse fields by the worker threads, one counter per sub-batch
+  HostPool* pool = (sparse && rec_len > 0) ? &host_pool() : nullptr;
+  std::atomic<int> zero_left[TendPipe::MAXB];
+  for (auto& z : zero_left) z.store(0);
+  // anything that returns early must not leave worker tasks (which write the caller's arrays) behind
+  struct PoolGuard { HostPool* p; ~PoolGuard() { if (p) p->wait_all(); } } pool_guard{pool};
   auto copy_kind = [&](int kind, int c0, int nb, cudaStream_t on) {
     for (auto& a : arrs) {
       if (a.kind != kind) continue;
       const size_t off = (size_t)c0 * a.stride * a.esz, bytes = (size_t)nb * a.stride * a.esz;
+      ((kind <= 1 || kind == 4) ? moved_h2d : moved_d2h) += (long long)bytes;
       cudaError_t e = (kind <= 1 || kind == 4) ? cudaMemcpyAsync((char*)a.d + off, (const char*)a.h + off, bytes, cudaMemcpyHostToDevice, on)
                                   : cudaMemcpyAsync((char*)a.h + off, (char*)a.d + off, bytes, cudaMemcpyDeviceToHost, on);
       if (e != cudaSuccess) rc = -100;
     }
     for (auto& a : sarrs) {
       if (a.kind != kind) continue;
+      (kind == 1 ? moved_h2d : moved_d2h) += (long long)(a.width * nb);
       const cudaError_t e = (kind == 1)
           ? cudaMemcpy2DAsync(a.d + (size_t)c0 * a.dpitch, a.dpitch, a.h + (size_t)c0 * a.hpitch, a.hpitch, a.width, nb, cudaMemcpyHostToDevice, on)
           : cudaMemcpy2DAsync((char*)a.h + (size_t)c0 * a.hpitch, a.hpitch, a.d + (size_t)c0 * a.dpitch, a.dpitch, a.width, nb, cudaMemcpyDeviceToHost, on);
@@ -1471,6 +1642,23 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
     CKP(cudaEventRecord(tp.late_ready[b], tp.h2d));
     return 0;
   };
+  if (pool && !prezeroed) {
+    for (int b = 0; b < NB; ++b) {
+      const int c0 = tp.sched_first[b], nb = tp.sched_first[b + 1] - c0;
+      for (int qf = 0; qf < SF_N; ++qf) {
+        if (sf_off[qf] < 0) continue;
+        const size_t str = ((qf >= SF_MCON && qf <= SF_FS) ? s2p : s2);
+        char* base = (char*)(sf_host[qf] + (size_t)c0 * str);
+        const size_t bytes = (size_t)nb * str * 8, piece = 2u << 20;
+        for (size_t o = 0; o < bytes; o += piece) {
+          zero_left[b].fetch_add(1);
+          const size_t n = bytes - o < piece ? bytes - o : piece;
+          std::atomic<int>* cnt = &zero_left[b];
+          pool->submit([base, o, n, cnt] { std::memset(base + o, 0, n); cnt->fetch_sub(1); });
+        }
+      }
+    }
+  }
   CKP(cudaEventRecord(tp.t0, tp.h2d));
   const double w_t0 = wall_ms();
   copy_kind(4, 0, nchunks, tp.h2d);
@@ -1503,7 +1691,29 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
 #undef O1
     if (rc) break;
     const double w_k = wall_ms();
+    if (pool) {         // the convective columns' records of this sub-batch
+      SparseFields sf;
+      sf.rec_len = rec_len;
+      for (int qf = 0; qf < SF_N; ++qf) {
+        sf.off[qf] = sf_off[qf];
+        sf.d[qf] = sf_off[qf] < 0 ? nullptr : sf_dev[qf] + (size_t)c0 * ((qf >= SF_MCON && qf <= SF_FS) ? s2p : s2);
+      }
+      int* base_b = d_base + c0 + b;                       // nb + 1 entries
+      k_lengath_scan<<<1, 256, 0, ws.stream>>>(nb, d_len + c0, base_b);
+      k_pack_records<<<nb * (int)pc, 64, 0, ws.stream>>>(nb, d_len + c0, d_ideep + (size_t)c0 * s1, base_b, sf,
+                                                         d_rec + (size_t)c0 * pc * rec_len);
+      tls_launches += 2;
+    }
     CKP(cudaEventRecord(tp.done[b], ws.stream));
+    if (pool) {         // (count, lengath, ideep) of the sub-batch: what the host needs to size and scatter the records
+      int* hs = tp.h_small + 2 * ((size_t)c0 * pc + c0 + 2 * b);
+      CKP(cudaStreamWaitEvent(tp.d2h_final, tp.done[b], 0));
+      CKP(cudaMemcpyAsync(hs, d_base + c0 + b + nb, sizeof(int), cudaMemcpyDeviceToHost, tp.d2h_final));
+      CKP(cudaMemcpyAsync(hs + 2, d_len + c0, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, tp.d2h_final));
+      CKP(cudaMemcpyAsync(hs + 2 + nb, d_ideep + (size_t)c0 * s1, (size_t)nb * pc * sizeof(int), cudaMemcpyDeviceToHost, tp.d2h_final));
+      CKP(cudaEventRecord(tp.small_back[b], tp.d2h_final));
+      moved_d2h += (long long)(1 + nb + nb * pc) * 4;
+    }
     if (b + 1 < NB && send_inputs(b + 1)) { drain(); return -100; }
     const double w_in = wall_ms();
     // device->host: zm_convr's outputs as soon as they are final, the rest when the sub-batch ends
@@ -1517,6 +1727,70 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
     CKP(cudaEventRecord(tp.final_back[b], tp.d2h_early));
     if (dbg) fprintf(stderr, "  sub-batch %d: kernels enqueued %.3f, next inputs enqueued %.3f, returns enqueued %.3f ms\n",
                      b, w_k, w_in, wall_ms());
+  }
+  if (rc == 0 && pool) {
+    // records: as soon as a sub-batch's count is known its records are fetched (exact size) while the worker threads
+    // scatter the previous sub-batch's
+    size_t hoff = 0;                       // doubles into the pinned record staging
+    size_t rec_off[TendPipe::MAXB]; int rec_cnt[TendPipe::MAXB];
+    auto scatter = [&](int b) {
+      const int c0 = tp.sched_first[b], nb = tp.sched_first[b + 1] - c0;
+      const int* hs = tp.h_small + 2 * ((size_t)c0 * pc + c0 + 2 * b);
+      const int* len = hs + 2; const int* idp = hs + 2 + nb;
+      while (zero_left[b].load() > 0) std::this_thread::yield();
+      const int ntask = pool->size() * 2, total = rec_cnt[b];
+      const double* recs = tp.h_rec + rec_off[b];
+      int ca = 0, j0 = 0;
+      for (int tsk = 0; tsk < ntask && ca < nb; ++tsk) {
+        const int want = (int)(((long long)total * (tsk + 1)) / ntask);
+        int cb = ca, j1 = j0;
+        while (cb < nb && (j1 < want || tsk == ntask - 1)) j1 += len[cb++];
+        if (cb == ca) continue;
+        double* const* hostp = sf_host; const int* offp = sf_off;
+        const int pcl = (int)pc, Ll = (int)L, rl = rec_len;
+        pool->submit([=] {
+          int j = j0;
+          for (int c = ca; c < cb; ++c)
+            for (int slot = 0; slot < len[c]; ++slot, ++j) {
+              const int i = idp[(size_t)c * pcl + slot] - 1;
+              const double* r = recs + (size_t)j * rl;
+              for (int qf = 0; qf < SF_N; ++qf) {
+                if (offp[qf] < 0) continue;
+                const int nlev = (qf >= SF_MCON && qf <= SF_FS) ? Ll + 1 : Ll;
+                double* dst = hostp[qf] + ((size_t)(c0 + c) * nlev) * pcl + (qf >= SF_MU ? slot : i);
+                const double* src = r + offp[qf];
+                for (int k = 0; k < nlev; ++k) dst[(size_t)k * pcl] = src[k];
+              }
+            }
+        });
+        ca = cb; j0 = j1;
+      }
+    };
+    for (int b = 0; b < NB && rc == 0; ++b) {
+      const int c0 = tp.sched_first[b];
+      if (cudaEventSynchronize(tp.small_back[b]) != cudaSuccess) { rc = -100; break; }
+      rec_cnt[b] = tp.h_small[2 * ((size_t)c0 * pc + c0 + 2 * b)];
+      rec_off[b] = hoff;
+      const size_t n = (size_t)rec_cnt[b] * rec_len;
+      if (hoff + n > tp.h_rec_cap) {       // grow the pinned staging: earlier records must be scattered first
+        for (int p2 = 0; p2 < b; ++p2) cudaEventSynchronize(tp.rec_back[p2]);
+        pool->wait_all();
+        if (tp.ensure_pinned(nc * rec_len, 0)) { rc = -100; break; }
+      }
+      if (n && cudaMemcpyAsync(tp.h_rec + hoff, d_rec + (size_t)c0 * pc * rec_len, n * sizeof(double),
+                               cudaMemcpyDeviceToHost, tp.d2h_early) != cudaSuccess) rc = -100;
+      if (cudaEventRecord(tp.rec_back[b], tp.d2h_early) != cudaSuccess) rc = -100;
+      moved_d2h += (long long)n * 8;
+      hoff += n;
+      if (b > 0) {
+        if (cudaEventSynchronize(tp.rec_back[b - 1]) != cudaSuccess) { rc = -100; break; }
+        scatter(b - 1);
+      }
+    }
+    if (rc == 0) {
+      if (cudaEventSynchronize(tp.rec_back[NB - 1]) != cudaSuccess) rc = -100;
+      else scatter(NB - 1);
+    }
   }
   if (rc == 0) copy_kind(5, 0, nchunks, tp.d2h_early);
   // the Brent failure counters of all sub-batches ride back on the return stream (it has waited for every
@@ -1548,8 +1822,17 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
     fails += f;
   }
   if (fails == 0) tls_mirror = new_mirror;   // a failed step (the reference stops in endrun) leaves no mirror
+  if (pool) pool->wait_all();
+  tp.last_h2d = moved_h2d; tp.last_d2h = moved_d2h;
   return fails;
 #undef CKP
+}
+
+// bytes the calling thread's last zm_conv_tend_batch moved over PCIe (host->device, device->host)
+int zm_tend_transfer_bytes(long long* h2d, long long* d2h) {
+  if (h2d) *h2d = tls_pipe.last_h2d;
+  if (d2h) *d2h = tls_pipe.last_d2h;
+  return 0;
 }
 
 // zm_org = 1: attach org (in), orgt and org2d (out), shapes (pcols,pver) per chunk, for the NEXT zm_convr_batch /

@@ -76,7 +76,7 @@ EXPORTS = [
     "zm_math_eval_dev", "zm_math_eval_host", "zm_thermo_eval_dev", "zm_fp64_peak_flops",
     "zm_set_profiling", "zm_get_kernel_times", "zm_launch_count",
     "zm_convtran1_fields", "zm_conv_tend_diag_batch", "zm_conv_tend_diag_batch_dev", "zm_get_timers",
-    "zm_conv_tend_2_batch_dev",
+    "zm_conv_tend_2_batch_dev", "zm_tend_transfer_bytes",
 ]
 
 
@@ -406,6 +406,13 @@ def tend_trace():
     buf = (C.c_double * 48)()
     nb = lib().zm_tend_trace(buf, C.c_int(48))
     return np.array(buf[:6 * nb]).reshape(nb, 6)
+
+
+def last_transfer_bytes():
+    """(host->device, device->host) bytes the last zm_conv_tend call of this thread moved over PCIe."""
+    a, b = C.c_longlong(0), C.c_longlong(0)
+    lib().zm_tend_transfer_bytes(C.byref(a), C.byref(b))
+    return {"h2d": int(a.value), "d2h": int(b.value)}
 
 
 def fp64_peak_flops(iters: int = 20000) -> float:

@@ -139,6 +139,12 @@ int zm_convtran_batch_dev(int nchunks, const int* doconvtran, const double* q, i
  *     sub-batches of 1,1,2,4,4,4 sixteenths (early first results, then large PCIe copies); ZM_TEND_SUBBATCHES=n
  *     (1..8) or ZM_TEND_SCHEDULE=uniform selects equal parts (default 8, never below 128 chunks each);
  *     ZM_TEND_SCHEDULE="1,2,3,4,6" gives explicit sizes in sixteenths; ZM_TEND_DEBUG prints the host-side timing.
+ *     Return path of the (pcols,pver[p]) outputs: they are zero outside the convective columns, so by default (from 64
+ *     chunks on) only the convective columns' levels travel device->host, one record per column, and ZM_HOST_THREADS
+ *     worker threads (default min(8, hardware threads)) scatter them into the caller's arrays, which they zero-filled
+ *     while the GPU worked; every element of every output is defined on return exactly as with ZM_TEND_RETURN=dense,
+ *     which copies the arrays whole.  ZM_TEND_OUTPUTS_PREZEROED=1 tells the library the arrays are all-zero on entry
+ *     (as after physics_ptend_init) and skips the zero-fill.  Per-column outputs always travel whole.
  *   _dev variant: from the third call with an identical argument list on, the step is replayed as a CUDA graph on
  *     `stream` (ZM_DEV_GRAPH=0 disables); ZM_DEV_SUBBATCHES (default 1) optionally splits the step over the
  *     library's own prioritised streams, joined back into `stream`. */
@@ -253,6 +259,8 @@ int zm_conv_tend_diag_batch_dev(int nchunks, const int* ncol, const double* ps, 
  * ms (inputs on device, late inputs on device, zm_convr done, all kernels done, zm_convr outputs on host,
  * remaining outputs on host).  Returns the number of sub-batches; fills at most cap doubles. */
 int zm_tend_trace(double* ms, int cap);
+/* bytes the calling thread's last zm_conv_tend_batch moved over PCIe in each direction */
+int zm_tend_transfer_bytes(long long* h2d, long long* d2h);
 
 /* Synchronises `stream` (NULL = the CUDA default stream) and returns the number of
  * Brent non-convergence events of this thread's last zm_convr_batch_dev call (0 = clean). */

@@ -453,6 +453,48 @@ def test_conv_tend_with_convtran1_and_cam3(built, ncols, cam3):
     assert "ptend_qc" not in out2 and np.array_equal(out2["ptend_s"], out["ptend_s"])
 
 
+@pytest.mark.parametrize("ncols", [16 * 70, 16 * 1100 + 5])
+def test_sparse_return_equals_dense_return(built, ncols, monkeypatch):
+    """zm_conv_tend_batch moves only the convective columns' records device->host and scatters them into arrays its
+    worker threads zero-fill (default); ZM_TEND_RETURN=dense copies the arrays whole.  Both must define every element
+    identically, whatever the arrays held before, with and without the pbuf fields kept on the device."""
+    Z = init_cuda(16, 32)
+    ch = S.make_chunks(ncols, 32, 16, p_conv=0.45)
+    res = {}
+    for mode in ("dense", "sparse", "sparse-prezeroed"):
+        monkeypatch.setenv("ZM_TEND_RETURN", mode.split("-")[0])
+        monkeypatch.setenv("ZM_TEND_OUTPUTS_PREZEROED", "1" if mode.endswith("prezeroed") else "0")
+        out = None
+        for rep in range(2):                   # the second call finds the first call's values (or garbage) in the arrays
+            if out is not None and not mode.endswith("prezeroed"):
+                for k, a in out.items():
+                    a[...] = 7 if a.dtype.kind == "i" else 1.25
+            elif out is not None:
+                for a in out.values():
+                    a[...] = 0
+            out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt, out)
+        res[mode] = {k: v.copy() for k, v in out.items()}
+        moved = Z.last_transfer_bytes()
+        dense_bytes = sum(v.nbytes for v in out.values())
+        if mode == "dense":
+            assert moved["d2h"] >= dense_bytes
+        else:
+            assert moved["d2h"] < 0.75 * dense_bytes
+    for mode in ("sparse", "sparse-prezeroed"):
+        for k in res["dense"]:
+            assert np.array_equal(res[mode][k], res["dense"][k]), (mode, k)
+    monkeypatch.setenv("ZM_TEND_RETURN", "sparse")
+    monkeypatch.setenv("ZM_TEND_OUTPUTS_PREZEROED", "0")
+    out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt, keep_pbuf_on_device=True)
+    for k in res["dense"]:
+        if k in ("mu", "md", "du", "eu", "ed", "dp", "dsubcld", "jt", "maxg"):
+            assert not out[k].any()
+        else:
+            assert np.array_equal(out[k], res["dense"][k]), k
+    o, _, _ = get_oracle("pm", 16, 32)
+    assert_same(res["sparse"], o.conv_tend_batch(ch), TEND_KEYS, 16, exact=True, what="sparse return vs oracle")
+
+
 def test_finalize_releases_and_reinit_reproduces(built):
     """zm_finalize frees the thread's arenas/streams; a fresh zm_init + step gives the same bits, and the
     pipelined host API (ramp schedule: 6 sub-batches of 1,1,2,4,4,4 sixteenths; then 8 equal ones) equals the
