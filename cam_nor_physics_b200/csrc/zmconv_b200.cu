@@ -244,10 +244,11 @@ struct TendPipe {
     return nb;
   }
   static int first(int b, int nchunks, int nb) { return (int)((long long)nchunks * b / nb); }
-  // Host-pointer pipeline: sub-batch boundaries in sixteenths of the batch.  "ramp" (default for large batches)
-  // starts with two small sub-batches so that the first results reach the return stream early, then grows them
-  // (1,1,2,4,4,4 sixteenths): fewer and larger PCIe copies, while every sub-batch is still computed before the
-  // return stream gets to it.  ZM_TEND_SCHEDULE=uniform keeps ZM_TEND_SUBBATCHES equal parts.
+  // Host-pointer pipeline: sub-batch boundaries in sixteenths of the batch.  Default for large batches: four equal
+  // sub-batches (with the round-2 kernels a sub-batch's chain of kernels is ~1.5 ms whatever its size, and the return
+  // stream -- 289 MB at 47-56 GB/s -- is the long pole from the moment the first results exist; fewer, larger copies
+  // serve it best: 7.84 ms against 8.11 ms for the earlier 1,1,2,4,4,4 ramp, scripts/e2e_schedule_sweep.py).
+  // ZM_TEND_SCHEDULE=uniform keeps ZM_TEND_SUBBATCHES equal parts, ZM_TEND_SCHEDULE="1,1,2,4,4,4" sets explicit sizes.
   int sched_nb = 0, sched_first[MAXB + 1] = {};
   int plan(int nchunks) {
     const char* e = getenv("ZM_TEND_SCHEDULE");
@@ -272,9 +273,9 @@ struct TendPipe {
       }
     }
     if (ramp) {
-      static const int sixteenths[7] = {0, 1, 2, 4, 8, 12, 16};
-      sched_nb = 6;
-      for (int b = 0; b <= 6; ++b) sched_first[b] = (int)((long long)nchunks * sixteenths[b] / 16);
+      static const int sixteenths[5] = {0, 4, 8, 12, 16};
+      sched_nb = 4;
+      for (int b = 0; b <= 4; ++b) sched_first[b] = (int)((long long)nchunks * sixteenths[b] / 16);
     } else {
       sched_nb = subbatches(nchunks);
       for (int b = 0; b <= sched_nb; ++b) sched_first[b] = first(b, nchunks, sched_nb);
@@ -1487,12 +1488,16 @@ int zm_conv_tend_batch(int nchunks, const int* ncol, const double* t, const doub
   // whole batch (4: in, before the first sub-batch; 5: out, after the last) instead of once per sub-batch
   struct Arr { const void* h; void* d; size_t stride, esz; int kind; };
   std::vector<Arr> arrs; arrs.reserve(64);
-  // Return path of the 2-D outputs: "sparse" (default from 64 chunks on) moves only the convective columns' records
-  // and scatters them on the host into the arrays worker threads zero-filled meanwhile; ZM_TEND_RETURN=dense copies
-  // the arrays whole.  ZM_TEND_OUTPUTS_PREZEROED=1: the caller's arrays are all-zero on entry (as after
-  // physics_ptend_init), the zero-fill is skipped.
+  // Return path of the 2-D outputs: dense (default) copies the arrays whole; ZM_TEND_RETURN=sparse moves only the
+  // convective columns' records and scatters them on the host into the arrays worker threads zero-filled meanwhile.
+  // The sparse path moves a third of the bytes over PCIe but writes the caller's arrays with CPU stores, and on a
+  // host whose memory bandwidth is of the order of the PCIe rate (the B200 boxes of this project: 70-78 GB/s for a
+  // parallel memset against 56 GB/s D2H) that costs more than it saves -- measured 11.7 against 8.2 ms per f09 step
+  //  -- so it is opt-in, for hosts with memory bandwidth to spare.
+  // ZM_TEND_OUTPUTS_PREZEROED=1: the caller's arrays are all-zero on entry (as after physics_ptend_init), the
+  // zero-fill is skipped.
   const char* ret_env = getenv("ZM_TEND_RETURN");
-  const bool sparse = ret_env ? !strcmp(ret_env, "sparse") : nchunks >= 64;
+  const bool sparse = ret_env && !strcmp(ret_env, "sparse");
   const bool prezeroed = getenv("ZM_TEND_OUTPUTS_PREZEROED") && atoi(getenv("ZM_TEND_OUTPUTS_PREZEROED")) != 0;
   double* sf_host[SF_N] = {};               // caller's arrays of the sparse fields (NULL: not wanted)
   double* sf_dev[SF_N] = {};

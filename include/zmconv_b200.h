@@ -135,16 +135,18 @@ int zm_convtran_batch_dev(int nchunks, const int* doconvtran, const double* q, i
  *
  * Execution (environment variables, read per call):
  *   host-pointer variant: the batch is pipelined over sub-batches of whole chunks so that host->device copies,
- *     kernels and device->host copies overlap; results do not depend on it.  Default for >= 1024 chunks: six
- *     sub-batches of 1,1,2,4,4,4 sixteenths (early first results, then large PCIe copies); ZM_TEND_SUBBATCHES=n
+ *     kernels and device->host copies overlap; results do not depend on it.  Default for >= 1024 chunks: four
+ *     equal sub-batches; ZM_TEND_SUBBATCHES=n
  *     (1..8) or ZM_TEND_SCHEDULE=uniform selects equal parts (default 8, never below 128 chunks each);
  *     ZM_TEND_SCHEDULE="1,2,3,4,6" gives explicit sizes in sixteenths; ZM_TEND_DEBUG prints the host-side timing.
- *     Return path of the (pcols,pver[p]) outputs: they are zero outside the convective columns, so by default (from 64
- *     chunks on) only the convective columns' levels travel device->host, one record per column, and ZM_HOST_THREADS
- *     worker threads (default min(8, hardware threads)) scatter them into the caller's arrays, which they zero-filled
- *     while the GPU worked; every element of every output is defined on return exactly as with ZM_TEND_RETURN=dense,
- *     which copies the arrays whole.  ZM_TEND_OUTPUTS_PREZEROED=1 tells the library the arrays are all-zero on entry
- *     (as after physics_ptend_init) and skips the zero-fill.  Per-column outputs always travel whole.
+ *     Return path of the (pcols,pver[p]) outputs: whole arrays by default.  They are zero outside the convective
+ *     columns, so ZM_TEND_RETURN=sparse sends only the convective columns' levels device->host, one record per column,
+ *     and ZM_HOST_THREADS worker threads (default min(8, hardware threads)) scatter them into the caller's arrays,
+ *     which they zero-filled while the GPU worked; every element of every output is defined on return exactly as in
+ *     the dense mode.  A third of the PCIe bytes, three times the host-memory traffic: it pays only on hosts whose
+ *     memory bandwidth is well above the PCIe rate (not the case on this project's B200 boxes, where it is slower).
+ *     ZM_TEND_OUTPUTS_PREZEROED=1 tells the library the arrays are all-zero on entry (as after physics_ptend_init)
+ *     and skips the zero-fill.  Per-column outputs always travel whole.
  *   _dev variant: from the third call with an identical argument list on, the step is replayed as a CUDA graph on
  *     `stream` (ZM_DEV_GRAPH=0 disables); ZM_DEV_SUBBATCHES (default 1) optionally splits the step over the
  *     library's own prioritised streams, joined back into `stream`. */

@@ -497,27 +497,29 @@ def test_sparse_return_equals_dense_return(built, ncols, monkeypatch):
 
 def test_finalize_releases_and_reinit_reproduces(built):
     """zm_finalize frees the thread's arenas/streams; a fresh zm_init + step gives the same bits, and the
-    pipelined host API (ramp schedule: 6 sub-batches of 1,1,2,4,4,4 sixteenths; then 8 equal ones) equals the
-    unpipelined one."""
+    pipelined host API (default: 4 equal sub-batches; an explicit 1,1,2,4,4,4-sixteenths ramp; 8 equal ones) equals
+    the unpipelined one."""
     Z = init_cuda(16, 32)
-    ch = S.make_chunks(16 * 1100, 32, 16, p_conv=0.5)         # 1100 chunks: enough for the ramp schedule
+    ch = S.make_chunks(16 * 1100, 32, 16, p_conv=0.5)         # 1100 chunks: enough for the default schedule
     out1 = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
     tr = Z.tend_trace()
-    assert tr.shape == (6, 6) and np.all(tr >= 0.0)
+    assert tr.shape == (4, 6) and np.all(tr >= 0.0)
     assert np.all(tr[:, 5] >= tr[:, 2])                        # outputs leave after zm_convr finished
     assert Z.lib().zm_finalize() == 0
     with pytest.raises(Z.ZmError):
         Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
     Z = init_cuda(16, 32)
-    for nsub, shape in (("1", (1, 6)), ("8", (8, 6))):
-        os.environ["ZM_TEND_SUBBATCHES"] = nsub
+    for var, val, shape in (("ZM_TEND_SUBBATCHES", "1", (1, 6)), ("ZM_TEND_SUBBATCHES", "8", (8, 6)),
+                            ("ZM_TEND_SCHEDULE", "1,1,2,4,4,4", (6, 6)), ("ZM_TEND_SCHEDULE", "-4,20", (4, 6)),
+                            ("ZM_TEND_SCHEDULE", "1,1,1,1,1,1,1,1,8", (4, 6))):
+        os.environ[var] = val                      # invalid lists (non-positive entries, too many) fall back to the default
         try:
             out2 = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
-            assert Z.tend_trace().shape == shape
+            assert Z.tend_trace().shape == shape, (var, val)
         finally:
-            del os.environ["ZM_TEND_SUBBATCHES"]
+            del os.environ[var]
         for k in out1:
-            assert np.array_equal(out1[k], out2[k]), (nsub, k)
+            assert np.array_equal(out1[k], out2[k]), (var, val, k)
     assert out1["lengath"].sum() > 0
 
 
