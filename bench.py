@@ -376,6 +376,11 @@ def main():
         alg_fpc = exe_fpc
     achieved = alg_fpc * ncols_rank / t_dom / 1e12
     alg_bytes = (6 * L + 2 + 2 * L + 6) * 8 + 12      # inputs t,q,pap,zm (L) + paph,zi (L+1) + 3; outputs tp,qstp + 6 scalars
+    import hashlib
+    hsh = hashlib.sha256()
+    for fn in ("zm_kernels.cuh", "zm_device.cuh", "zm_math.h", "zm_svp_table.h"):
+        hsh.update(open(os.path.join(ROOT, "cam_nor_physics_b200", "csrc", fn), "rb").read())
+    executed_stale = fl.get("executed_kernel_hash") != hsh.hexdigest()[:16]
     roofline = {"kernel": "k_buoyan_dilute<1> (dilute CAPE trigger, pass 1, all columns)",
                 "bound": "fp64", "achieved": achieved if flops_valid else None, "peak": fp64_peak / 1e12,
                 "unit": "TFLOP/s", "frac": achieved / (fp64_peak / 1e12) if flops_valid else None,
@@ -389,6 +394,8 @@ def main():
                 "executed_tflops": exe_fpc * ncols_rank / t_dom / 1e12 if flops_valid else None,
                 "executed_frac": exe_fpc * ncols_rank / t_dom / fp64_peak if flops_valid else None,
                 "executed_flops_source": fl.get("executed_source"),
+                "executed_flops_stale": bool(executed_stale) if flops_valid else None,   # kernel sources changed since the capture
+                "algorithmic_calls_per_column": fl.get("algorithmic_calls_per_column") if flops_valid else None,
                 "ms_per_launch": t_dom * 1e3,
                 "traffic": fl.get("dram_bytes_per_launch") if flops_valid and ncols_rank == int(fl.get("ncols", -1)) else None,
                 "hbm": {"achieved_gbs": alg_bytes * ncols_rank / t_dom / 1e9, "peak_gbs": peaks.get("hbm_gbs"),

@@ -64,6 +64,14 @@ Module g;
 
 thread_local long long cnt[10];
 thread_local int brent_fail;
+// FP64 operation count of the calling thread (+, -, *, /, compare, abs-compare = 1 each; log / log10 /
+// 10**x / exp / x**y counted as calls), per phase of zm_convr: 0 = everything else, 1 = first buoyan_dilute call (the
+// dominant kernel's algorithmic work), 2 = second buoyan_dilute call.  Columns: 0 basic operations, 1 log, 2 log10,
+// 3 10**x, 4 exp, 5 x**y, 6 state-function evaluations, 7 Brent iterations.  Only buoyan_dilute / parcel_dilute and
+// what they call are instrumented with basic-operation counts (FL(n) next to the statements they count).
+thread_local int fl_phase = 0;
+thread_local long long fl[3][8];
+#define FL(n) (fl[fl_phase][0] += (n))
 // optional trace of Brent inversions (rcall, icol, lchnk, state-function evaluations) for divergence studies
 // zm_org (organisation tracer): the pointer dummies org/orgt/org2d of zm_convr (zm_conv.F90:421-423).
 // tl_* point at the chunk being processed; the batch drivers set them from the batch-wide base pointers.
@@ -78,9 +86,9 @@ thread_local int* trace_buf = nullptr; thread_local int trace_n = 0, trace_cap =
 
 inline double fmax2(double a, double b) { return (a > b) ? a : b; }
 inline double fmin2(double a, double b) { return (a < b) ? a : b; }
-inline double c_log(double x)   { ++cnt[5]; return m_log(x); }
-inline double c_exp(double x)   { ++cnt[8]; return m_exp(x); }
-inline double c_pow(double x, double y) { ++cnt[9]; return m_pow(x, y); }
+inline double c_log(double x)   { ++cnt[5]; ++fl[fl_phase][1]; return m_log(x); }
+inline double c_exp(double x)   { ++cnt[8]; ++fl[fl_phase][4]; return m_exp(x); }
+inline double c_pow(double x, double y) { ++cnt[9]; ++fl[fl_phase][5]; return m_pow(x, y); }
 
 // 1-based column-major views -------------------------------------------------------------
 struct A2 {
@@ -128,13 +136,18 @@ inline int nint_(double x) { return (int)std::lround(x); }
 // ---- qsat_hPa  zm_conv.F90:5421-5437 ----------------------------------------------------
 inline void qsat_hPa(double t, double p, double& es, double& qm) {
   ++cnt[0]; cnt[6] += 1; cnt[7] += 3;
+  fl[fl_phase][2] += 1; fl[fl_phase][3] += 3;
+  // p*100 (1); Goff-Gratch (zm_externals.hpp): 3 divisions, 3 subtractions of 1, 6 products with the coefficients,
+  // 2 (10**x - 1), 4 additions of the terms, *100 (19); svp_to_qsat: p-es, <=, 2 products, -, / (6); min (1); *0.01 (1)
+  FL(28);
   zmo::qsat_water(t, p * 100.0, g.epsilo, es, qm);
   es = es * 0.01;
 }
 
 // ---- entropy  zm_conv.F90:5280-5300 -----------------------------------------------------
 double entropy(double TK, double p, double qtot) {
-  ++cnt[1];
+  ++cnt[1]; ++fl[fl_phase][6];
+  FL(23);        // L (3), min (1), e (3), the four terms: 2 + 2 | 2 + 1 | 2 | 3, their 3 sums (16)
   const double pref = 1000.0;
   double qv, qst, e, est, L;
   L = g.rl - (g.cpliq - g.cpwv) * (TK - g.tfreez);
@@ -147,7 +160,8 @@ double entropy(double TK, double p, double qtot) {
 
 // ---- enthalpy  zm_conv.F90:5440-5457 ----------------------------------------------------
 double enthalpy(double TK, double p, double qtot, double z) {
-  ++cnt[2];
+  ++cnt[2]; ++fl[fl_phase][6];
+  FL(13);        // L (3), min (1), (cpres + qtot*cpliq)*TK (3), L*qv (1), (1+qtot)*grav*z (3), 2 sums
   double qv, qst, est, L;
   L = g.rl - (g.cpliq - g.cpwv) * (TK - g.tfreez);
   qsat_hPa(TK, p, est, qst);
@@ -174,16 +188,20 @@ void invert(int rcall, int icol, int lchnk, double s, double p, double z, double
   b = Tfg + 10;
   fa = F(a) - s;
   fb = F(b) - s;
+  FL(4);
   c = b;
   fc = fb;
   tol = 0.001;
 
   for (int i = 0; i <= LOOPMAX; ++i) {
+    ++fl[fl_phase][7];
+    FL(4 + 1 + 4 + 2 + 2);     // sign tests, |fc| < |fb|, tol1, xm, convergence test
     if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) {
       c = a;
       fc = fa;
       d = b - a;
       ebr = d;
+      FL(1);
     }
     if (std::fabs(fc) < std::fabs(fb)) {
       a = b;
@@ -198,22 +216,28 @@ void invert(int rcall, int icol, int lchnk, double s, double p, double z, double
     converged = (std::fabs(xm) <= tol1 || fb == 0.0);
     if (converged) break;
 
+    FL(2);                     // the two comparisons that admit an interpolation step
     if (std::fabs(ebr) >= tol1 && std::fabs(fa) > std::fabs(fb)) {
       sbr = fb / fa;
+      FL(2);                   // fb/fa, a == c
       if (a == c) {
         pbr = 2.0 * xm * sbr;
         qbr = 1.0 - sbr;
+        FL(3);
       } else {
         qbr = fa / fc;
         rbr = fb / fc;
         pbr = sbr * (2.0 * xm * qbr * (qbr - rbr) - (b - a) * (rbr - 1.0));
         qbr = (qbr - 1.0) * (rbr - 1.0) * (sbr - 1.0);
+        FL(2 + 9 + 5);
       }
       if (pbr > 0.0) qbr = -qbr;
       pbr = std::fabs(pbr);
+      FL(1 + 8);               // pbr > 0; 2 pbr < min(3 xm qbr - |tol1 qbr|, |ebr qbr|)
       if (2.0 * pbr < fmin2(3.0 * xm * qbr - std::fabs(tol1 * qbr), std::fabs(ebr * qbr))) {
         ebr = d;
         d = pbr / qbr;
+        FL(1);
       } else {
         d = xm;
         ebr = d;
@@ -226,6 +250,7 @@ void invert(int rcall, int icol, int lchnk, double s, double p, double z, double
     fa = fb;
     b = b + ((std::fabs(d) > tol1) ? d : std::copysign(tol1, xm));
     fb = F(b) - s;
+    FL(3);                     // |d| > tol1, b + step, F - s
   }
   T = b;
   if (trace_buf && trace_n + 4 <= trace_cap) {
@@ -278,6 +303,8 @@ void parcel_dilute(int lchnk, int ncol, int msg, I1& klaunch, C2 p, C2 z, C2 t, 
         qsat_hPa(tmix(i, k), p(i, k), est, qsmix(i, k));
       }
       if (k < klaunch(i)) {
+        // layer means (1 + 4*2), dpdz/dzdp (4), dmpdp (1), sp/qtp/mp updates (3 + 3 + 2), smix/qtmix (3 + 3), LCL test (2)
+        FL(9 + 4 + 1 + 8 + 6 + 2);
         dp = (p(i, k) - p(i, k + 1));
         qtenv = 0.5 * (q(i, k) + q(i, k + 1));
         tenv = 0.5 * (t(i, k) + t(i, k + 1));
@@ -310,6 +337,7 @@ void parcel_dilute(int lchnk, int ncol, int msg, I1& klaunch, C2 p, C2 z, C2 t, 
 
         if (qsmix(i, k) <= qtmix(i, k) && qsmix(i, k + 1) > qtmix(i, k + 1)) {
           lcl(i) = k;
+          FL(2 + 2 + 2 + 3 + 2 + 2 + 3 + 3);   // the interpolation to the LCL (zm_conv.F90:5113-5127)
           qxsk = qtmix(i, k) - qsmix(i, k);
           qxskp1 = qtmix(i, k + 1) - qsmix(i, k + 1);
           dqxsdp = (qxsk - qxskp1) / dp;
@@ -340,7 +368,11 @@ void parcel_dilute(int lchnk, int ncol, int msg, I1& klaunch, C2 p, C2 z, C2 t, 
       }
       if (k < klaunch(i)) {
         smix(i, k) = entropy(tmix(i, k), p(i, k), qtmix(i, k));
+        FL(6 + 1);                     // tpv of this level (6), new_q > qsmix
         for (int ii = 0; ii <= nit_lheat - 1; ++ii) {
+          // xsh2o (3), ds_xsh2o (1 division, 1 difference, max, 2 products, 1 difference = 6), freezing tests (4) and
+          // term (up to 5), new_s (2), new_q (1)
+          FL(3 + 6 + 4 + 5 + 2 + 1);
           xsh2o(i, k) = fmax2(0.0, qtmix(i, k) - qsmix(i, k) - lwmax);
           ds_xsh2o(i, k) = ds_xsh2o(i, k + 1) -
                            g.cpliq * c_log(tmix(i, k) / g.tfreez) *
@@ -418,6 +450,9 @@ void buoyan_dilute(int lchnk, int ncol, C2 q, C2 t, C2 p, C2 z, C2 pf, A2 tp, A2
     parcel_ztop(i) = parcel_dz(i) + zs(i);
     parcel_hdp(i) = 0.0; parcel_dp(i) = 0.0; parcel_qdp(i) = 0.0; hpar(i) = 0.0; qpar(i) = 0.0;
   }
+  FL((long long)ncol * pver * 5);            // tv of every level
+  FL((long long)ncol * (pver - msg) * (g.lparcel_pbl ? 22 : 19));   // moist static energy of the launch search
+  FL((long long)ncol * (pver - msg) * (5 + 2));                       // tv / buoyancy after the parcel, level tests
   for (int k = 1; k <= pver; ++k)
     for (int i = 1; i <= ncol; ++i) {
       tp(i, k) = t(i, k);
@@ -516,6 +551,7 @@ void buoyan_dilute(int lchnk, int ncol, C2 q, C2 t, C2 p, C2 z, C2 pf, A2 tp, A2
     for (int k = msg + 1; k <= pver; ++k)
       for (int i = 1; i <= ncol; ++i) {
         if (plge600[i - 1] && k <= mx(i) && k > LELTEN(i, n)) {
+          FL(4 + 5);                   // cape term (division, 2 products, sum), cin term (min, division, 2 products, difference)
           capeten(i, n) = capeten(i, n) + rd * buoy(i, k) * c_log(pf(i, k + 1) / pf(i, k));
           cinten(i, n) = cinten(i, n) - rd * fmin2(buoy(i, k), 0.0) * c_log(pf(i, k + 1) / pf(i, k));
         }
@@ -1338,9 +1374,11 @@ int convr(int lchnk, int ncol, const double* t_, const double* qh_, double* prec
     buoyan(lchnk, ncol, q, t, p, z, pf, tp, qstp, tl.v.data(), rl, cape_, pblt.v.data(),
            lcl.v.data(), lel.v.data(), lon.v.data(), maxi.v.data(), rgas, grav, cpres, msg, tpert_);
   } else {
+    fl_phase = 1;
     buoyan_dilute(lchnk, ncol, q, t, p, z, pf, tp, qstp, tl.v.data(), cape_, cin.v.data(),
                   pblt.v.data(), lcl.v.data(), lel.v.data(), lon.v.data(), maxi.v.data(), rgas, grav,
                   cpres, msg, zi, zs.v.data(), tpert_, landfrac_, dmpdz);
+    fl_phase = 0;
   }
 
   lengath = 0;
@@ -1433,9 +1471,11 @@ int convr(int lchnk, int ncol, const double* t_, const double* qh_, double* prec
         for (int k = 1; k <= pver; ++k) dmpdz(ideep(i), k) = val;
       }
     }
+    fl_phase = 2;
     buoyan_dilute(lchnk, ncol, q, t, p, z, pf, tp, qstp, tl.v.data(), cape_, cin.v.data(),
                   pblt.v.data(), lcl.v.data(), lel.v.data(), lon.v.data(), maxi.v.data(), rgas, grav,
                   cpres, msg, zi, zs.v.data(), tpert_, landfrac_, dmpdz);
+    fl_phase = 0;
 
     lengath = 0;
     for (int i = 1; i <= pcols; ++i) { ideep(i) = 0; indxd(i) = 0; }
@@ -1990,7 +2030,13 @@ void zmo_org_fields(const double* org, double* orgt, double* org2d) {
 }
 void zmo_trace_set(int* buf, int cap) { trace_buf = buf; trace_cap = cap; trace_n = 0; }
 int zmo_trace_count(void) { return trace_n / 4; }
-void zmo_counters_reset(void) { for (int i = 0; i < 10; ++i) cnt[i] = 0; }
+void zmo_counters_reset(void) {
+  for (int i = 0; i < 10; ++i) cnt[i] = 0;
+  for (auto& ph : fl) for (auto& v : ph) v = 0;
+}
+void zmo_flops_get(long long* out24) {
+  for (int ph = 0; ph < 3; ++ph) for (int j = 0; j < 8; ++j) out24[ph * 8 + j] = fl[ph][j];
+}
 void zmo_counters_get(long long* out10) { for (int i = 0; i < 10; ++i) out10[i] = cnt[i]; }
 
 int zmo_convr_batch(int nchunks, const int* ncol, const double* t, const double* qh, double* prec,

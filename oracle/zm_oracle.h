@@ -103,6 +103,11 @@ int zmo_trace_count(void);
 /* out[0]=qsat_hPa calls, [1]=entropy, [2]=enthalpy, [3]=ientropy, [4]=ienthalpy,
  * [5]=log, [6]=log10, [7]=pow10, [8]=exp, [9]=pow  */
 void zmo_counters_get(long long* out10);
+/* FP64 operation count of the calling thread since zmo_counters_reset, 3 phases x 8 columns:
+ * phase 0 everything outside the CAPE passes (transcendental calls only), 1 first buoyan_dilute call, 2 second;
+ * columns: basic operations (+ - * / compare = 1 each), log, log10, 10**x, exp, x**y calls, state-function
+ * evaluations, Brent iterations.  Run single-threaded (nthreads = 1) to see a whole batch. */
+void zmo_flops_get(long long* out24);
 
 /* chunk-loop drivers (OpenMP over chunks, mirroring physpkg.F90:1147) used for timing and
  * for whole-grid parity.  All arrays are [chunk][k][i] i.e. Fortran chunks back-to-back. */

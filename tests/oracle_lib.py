@@ -113,6 +113,12 @@ class Oracle:
         self.lib.zmo_counters_get(out)
         return list(out)
 
+    def flops(self):
+        """3 phases x 8 columns operation count of this thread (zmo_flops_get)."""
+        c = (C.c_longlong * 24)()
+        self.lib.zmo_flops_get(c)
+        return np.array(list(c), dtype=np.int64).reshape(3, 8)
+
     def counters_reset(self):
         self.lib.zmo_counters_reset()
 
