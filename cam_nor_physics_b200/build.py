@@ -28,18 +28,40 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def needs_build() -> bool:
+def source_hash() -> str:
+    """sha256 over the contents of every source the library is built from and the compiler flags: compiled into the
+    library (zm_build_info), so a binary that does not belong to the sources in the tree is recognised whatever the
+    file times say."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in DEPS:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:32]
+
+
+def built_hash() -> str | None:
+    """The source hash recorded inside the built library (read from the file, without loading it)."""
     if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+        return None
+    with open(LIB, "rb") as f:
+        blob = f.read()
+    i = blob.find(b"ZMSRCHASH:")
+    return blob[i + 10:i + 42].decode(errors="replace") if i >= 0 else None
+
+
+def needs_build() -> bool:
+    return built_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     extra = os.environ.get("ZM_NVCC_EXTRA", "").split()       # experiments only, e.g. -DPL_WARPS=8
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+          [f"-DZM_SOURCE_HASH=\"{source_hash()}\"", "-o", LIB, SRC]
     env = dict(os.environ)
     env.pop("CXX", None)
     env.pop("CC", None)     # the image exports a gcc wrapper that nvcc should not pick up

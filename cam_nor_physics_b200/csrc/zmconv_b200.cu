@@ -941,6 +941,12 @@ int zm_last_error(char* buf, int buflen) {
   return (int)tls_err.size();
 }
 
+#ifndef ZM_SOURCE_HASH
+#define ZM_SOURCE_HASH "unknown"
+#endif
+// hash of the sources and flags this binary was built from (cam_nor_physics_b200/build.py compares it with the tree)
+const char* zm_build_info(void) { return "ZMSRCHASH:" ZM_SOURCE_HASH " sm_100a"; }
+
 int zm_set_profiling(int on) { g_profile = on != 0; return 0; }
 long long zm_launch_count(int reset) { long long v = tls_launches; if (reset) tls_launches = 0; return v; }
 

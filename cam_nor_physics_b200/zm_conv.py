@@ -62,6 +62,7 @@ def lib() -> C.CDLL:
                           "(or __graft_entry__.build()); there is no CPU fallback")
         _lib = C.CDLL(_LIBPATH)
         _lib.zm_fp64_peak_flops.restype = C.c_double
+        _lib.zm_build_info.restype = C.c_char_p
         _lib.zm_launch_count.restype = C.c_longlong
     return _lib
 
@@ -76,7 +77,7 @@ EXPORTS = [
     "zm_math_eval_dev", "zm_math_eval_host", "zm_thermo_eval_dev", "zm_fp64_peak_flops",
     "zm_set_profiling", "zm_get_kernel_times", "zm_launch_count",
     "zm_convtran1_fields", "zm_conv_tend_diag_batch", "zm_conv_tend_diag_batch_dev", "zm_get_timers",
-    "zm_conv_tend_2_batch_dev", "zm_tend_transfer_bytes",
+    "zm_conv_tend_2_batch_dev", "zm_tend_transfer_bytes", "zm_build_info",
 ]
 
 

@@ -294,6 +294,8 @@ int zm_get_kernel_times(int* n, const char** names, float* ms);
  * zm_convr, zm_conv_evap, momtran, convtran1, convtran2 (+ physics_update for the glue kernels); *n in = capacity
  * (>= 6), out = count.  Covers the calling thread's last profiled zm_conv_tend_batch_dev and zm_conv_tend_2_batch. */
 int zm_get_timers(int* n, const char** names, float* ms);
+/* "ZMSRCHASH:<sha256 prefix of the sources and flags the binary was built from> sm_100a" */
+const char* zm_build_info(void);
 /* number of kernel launches issued by this thread since the last call (bench's gpu_launches) */
 long long zm_launch_count(int reset);
 

@@ -17,12 +17,20 @@ def test_library_exports_every_declared_symbol(built):
     from cam_nor_physics_b200 import zm_conv as Z
     hdr = open(os.path.join(ROOT, "include", "zmconv_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    names = set(re.findall(r"\b(?:int|void|double|long long)\s+(zm_[a-z0-9_]+)\s*\(", hdr))
+    names = set(re.findall(r"\b(?:int|void|double|long long|const char\*)\s+(zm_[a-z0-9_]+)\s*\(", hdr))
     assert len(names) >= 20
     lib = Z.lib()
     missing = [n for n in sorted(names) if not hasattr(lib, n)]
     assert not missing, missing
     assert set(Z.EXPORTS) <= names | {"zm_params_default"}
+
+
+def test_library_is_built_from_the_sources_in_the_tree(built):
+    """The hash of the sources and compiler flags is compiled into the library: a stale binary cannot be tested."""
+    from cam_nor_physics_b200 import build, zm_conv as Z
+    info = Z.lib().zm_build_info().decode()
+    assert info.startswith("ZMSRCHASH:") and build.source_hash() in info
+    assert build.built_hash() == build.source_hash() and not build.needs_build()
 
 
 def test_sm100a_code_is_embedded(built):

@@ -222,6 +222,53 @@ def test_f09_full_step_vs_oracle(built):
                     skip_cols=near)
 
 
+def test_config5_shard_L58_full_step_vs_oracle(built):
+    """BASELINE config 5, one GPU's shard at full size (131,072 columns, L58, parcel_pbl, 40 % convective) through
+    zm_conv_tend: bit for bit against the portable-math oracle, within the north-star tolerance against the
+    glibc-libm one (near-threshold columns reported and left out)."""
+    over = dict(lparcel_pbl=1)
+    Z = init_cuda(16, 58, **over)
+    ch = S.make_chunks(131072, 58, 16, p_conv=0.4)
+    out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
+    o, _, _ = get_oracle("pm", 16, 58, **over)
+    ref = o.conv_tend_batch(ch)
+    assert ref["rc"] == 0
+    assert_same(out, ref, TEND_KEYS, 16, exact=True, what="config-5 shard zm_conv_tend")
+    assert 0.1 < ref["lengath"].sum() / 131072 < 0.6
+    o2, _, _ = get_oracle("libm", 16, 58, **over)
+    ref2 = o2.conv_tend_batch(ch)
+    near = near_threshold_columns(ref2["cape"])
+    print("near-threshold columns (reported, left out of the comparison):", near.tolist())
+    cv = o2.convr_batch(ch)
+    scales = {"ptend_s": np.abs(cv["heat"]) + np.abs(ref2["ptend_s"] - cv["heat"]),
+              "ptend_q": np.abs(cv["qtnd"]) + np.abs(ref2["evapcdp"])}
+    keys = TEND_KEYS if not len(near) else [k for k in TEND_KEYS if k not in GATHERED_2D + GATHERED_1D + INT_KEYS]
+    assert_same(out, ref2, keys, 16, exact=False, what="config-5 shard vs libm oracle", scales=scales,
+                skip_cols=near if len(near) else None)
+
+
+def test_config4_f09_convtran_41_constituents_vs_oracle(built):
+    """BASELINE config 4 at full size: the f09 grid with a 41-constituent stand-in for the OsloAero tracer set --
+    convtran1 (2 constituents) inside zm_conv_tend and convtran2 (38, every third 'dry') in zm_conv_tend_2 from the
+    device pbuf mirror -- bit for bit against the oracle's batch drivers."""
+    Z = init_cuda(16, 32)
+    o, _, _ = get_oracle("pm", 16, 32)
+    ch = S.make_chunks(55296, 32, 16, p_conv=0.35)
+    pcnst = 41
+    q, fracis, pdeldry = S.make_tracers(ch, pcnst)
+    do1 = np.zeros(pcnst, np.int32); do1[1:3] = 1
+    do2 = np.zeros(pcnst, np.int32); do2[3:] = 1
+    dry = np.zeros(pcnst, np.int32); dry[3::3] = 1
+    t1 = dict(doconvtran=do1, cnst_is_dry=dry, q=q, fracis=fracis)
+    ref = o.conv_tend_batch(ch, convtran1=t1)
+    refq = o.conv_tend_2_batch(do2, q, pdeldry, fracis, ch.ztodt, dry, ref, ptend_q=ref["ptend_qc"])
+    out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt, keep_pbuf_on_device=True, convtran1=t1)
+    dq = Z.zm_conv_tend_2(do2, q, pdeldry, fracis, ch.ztodt, dry, ptend_q=out["ptend_qc"])
+    assert np.array_equal(out["ptend_qc"], ref["ptend_qc"])
+    assert np.array_equal(dq, refq)
+    assert np.count_nonzero(dq[:, 3:]) > 0 and np.count_nonzero(dq[:, 1:3]) > 0 and not dq[:, 0].any()
+
+
 def test_sharding_invariance_and_properties_L58_large(built):
     """BASELINE config 5 shard (131,072 columns L58, 10-60% convective): size-independent properties --
     chunk partition invariance, water closure, sorted ideep, zero rows outside the cloud."""
