@@ -211,9 +211,10 @@ def test_f09_full_step_vs_oracle(built):
     # the tolerance is taken against the magnitude of the terms (which are themselves compared against it)
     cv = o2.convr_batch(ch)
     cvo = cuda_convr(Z, ch)
-    assert_same(cvo, cv, CONVR_KEYS, 16, exact=False, what="f09 zm_convr vs libm oracle", skip_cols=near)
+    assert_same(cvo, cv, CONVR_KEYS, 16, exact=False, what="f09 zm_convr vs libm oracle", skip_cols=near,
+                scales={"cape": np.full_like(cv["cape"], 70.0)})
     scales = {"ptend_s": np.abs(cv["heat"]) + np.abs(ref2["ptend_s"] - cv["heat"]),
-              "ptend_q": np.abs(cv["qtnd"]) + np.abs(ref2["evapcdp"])}
+              "ptend_q": np.abs(cv["qtnd"]) + np.abs(ref2["evapcdp"]), "cape": np.full_like(ref2["cape"], 70.0)}
     if not len(near):          # gathered outputs shift when a column enters or leaves ideep
         assert_same(out, ref2, TEND_KEYS, 16, exact=False, what="f09 zm_conv_tend vs libm oracle", scales=scales)
     else:
@@ -240,8 +241,11 @@ def test_config5_shard_L58_full_step_vs_oracle(built):
     near = near_threshold_columns(ref2["cape"])
     print("near-threshold columns (reported, left out of the comparison):", near.tolist())
     cv = o2.convr_batch(ch)
+    # cape is a sum of signed buoyancy terms (zm_conv.F90:4785-4796), each of the order of the trigger threshold or
+    # larger, that can cancel to a fraction of a J/kg: the tolerance is taken against capelmt, the number it is
+    # compared with (zm_conv.F90:908)
     scales = {"ptend_s": np.abs(cv["heat"]) + np.abs(ref2["ptend_s"] - cv["heat"]),
-              "ptend_q": np.abs(cv["qtnd"]) + np.abs(ref2["evapcdp"])}
+              "ptend_q": np.abs(cv["qtnd"]) + np.abs(ref2["evapcdp"]), "cape": np.full_like(ref2["cape"], 70.0)}
     keys = TEND_KEYS if not len(near) else [k for k in TEND_KEYS if k not in GATHERED_2D + GATHERED_1D + INT_KEYS]
     assert_same(out, ref2, keys, 16, exact=False, what="config-5 shard vs libm oracle", scales=scales,
                 skip_cols=near if len(near) else None)
