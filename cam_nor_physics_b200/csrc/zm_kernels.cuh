@@ -75,9 +75,11 @@ __global__ void k_convr_init(ConvrIn in, ConvrOut o, ConvrWork w) {
   size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t nth = (size_t)gridDim.x * blockDim.x;
   for (size_t e = tid; e < ncolpad * pver; e += nth) {
-    o.qtnd[e] = 0.0; o.heat[e] = 0.0; o.cme[e] = 0.0; o.eurt[e] = 0.0; o.dlf[e] = 0.0;
+    o.qtnd[e] = 0.0; o.heat[e] = 0.0; o.cme[e] = 0.0; o.dlf[e] = 0.0;
     o.zdu[e] = 0.0; o.rprd[e] = 0.0; o.mu[e] = 0.0; o.md[e] = 0.0; o.du[e] = 0.0; o.eu[e] = 0.0;
-    o.ed[e] = 0.0; o.dp[e] = 0.0; o.ql[e] = 0.0; o.dif[e] = 0.0; o.dnlf[e] = 0.0; o.dnif[e] = 0.0;
+    o.ed[e] = 0.0; o.dp[e] = 0.0; o.ql[e] = 0.0;
+    // eurt, dif, dnlf, dnif are outputs of zm_convr that zm_conv_tend does not pass on: NULL inside the fused sequence
+    if (o.eurt) { o.eurt[e] = 0.0; o.dif[e] = 0.0; o.dnlf[e] = 0.0; o.dnif[e] = 0.0; }
   }
   for (size_t e = tid; e < ncolpad * pverp; e += nth) { o.mcon[e] = 0.0; o.pflx[e] = 0.0; }
   for (size_t e = tid; e < ncolpad; e += nth) {

@@ -783,7 +783,7 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
     o.heat[e] = S(A_W1, k) * P.cpres;
     o.dlf[e] = S(A_W3, k);
     o.ql[e] = S(A_QL, k);
-    o.eurt[e] = -dmpdz;
+    if (o.eurt) o.eurt[e] = -dmpdz;
     const size_t ep = cidx(c, k - 1, i, pverp);
     o.mcon[ep] = S(A_MC, k);
     o.pflx[ep] = S(A_PFLX, k);

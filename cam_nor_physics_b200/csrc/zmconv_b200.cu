@@ -1245,9 +1245,10 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
   if (ws.ensure(convr_work_bytes(nc, (int)L) + 19 * al(n2, 8) + 6 * al(2 * n2, 8) + chunk_bounds_bytes(nchunks, (int)nc) + 8192))
     return -100;
   cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
-  double *heat = ws.take<double>(n2), *qtnd = ws.take<double>(n2), *eurt = ws.take<double>(n2),
-         *dif = ws.take<double>(n2), *dnlf = ws.take<double>(n2), *dnif = ws.take<double>(n2),
-         *t1 = ws.take<double>(n2), *q1 = ws.take<double>(n2), *ev_s = ws.take<double>(n2),
+  // eurt, dif, dnlf, dnif of zm_convr (history diagnostics EURT / DIFZM and the microphysics number tendencies) are
+  // not among zm_conv_tend's outputs: not materialised here (all four NULL together)
+  double *heat = ws.take<double>(n2), *qtnd = ws.take<double>(n2), *eurt = nullptr, *dif = nullptr, *dnlf = nullptr,
+         *dnif = nullptr, *t1 = ws.take<double>(n2), *q1 = ws.take<double>(n2), *ev_s = ws.take<double>(n2),
          *ev_q = ws.take<double>(n2), *snwprd = ws.take<double>(n2), *snwevmlt = ws.take<double>(n2),
          *ntprprd = ws.take<double>(n2), *ntsnprd = ws.take<double>(n2), *seten = ws.take<double>(n2);
   double *winds = ws.take<double>(2 * n2), *wtend = ws.take<double>(2 * n2), *pgu = ws.take<double>(2 * n2),
