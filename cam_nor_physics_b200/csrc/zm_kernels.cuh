@@ -45,6 +45,7 @@ struct ConvrWork {
   double *cape, *cin, *tl, *dmpdz;       // [ncolpad]
   int *lcl, *lel, *mx;                   // [ncolpad]
   double *tp, *qstp;                     // [pver][ncolpad]
+  double *ab;                            // [3][pver][ncolpad] first-loop parcel handed to the second loop (k_buoyan_dilute_ws)
   int *wl1, *wl2;                        // worklists: pass-1 columns; final (col, slot) pairs
   int *okey;                             // [ncolpad] launch level of the dilute parcel (the CAPE kernels' work key)
   int *ord1, *ord2;                      // [ncolpad] columns of CAPE pass 1 / pass 2, most parcel levels first
@@ -53,6 +54,8 @@ struct ConvrWork {
   double *errinfo;                       // first failure: rcall, col, p, Tfg, qt, s
   int *n1chunk;                          // [nchunks] pass-1 convective columns per chunk (k_trigger<0>)
   int skip_idle_chunks;                  // CAPE kernel: leave chunks with n1chunk == 0 alone (cam3 second pass)
+  int ws_gate;                           // second pass: worklists up to this size go to k_buoyan_dilute_ws, larger ones
+                                         // to k_buoyan_dilute (both are launched, the device-side count decides)
 };
 
 __device__ __forceinline__ size_t cidx(int c, int k0, int i, int nlev) {
@@ -215,7 +218,7 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int col;
   if (PASS == 1) { if (gid >= w.count[3]) return; col = w.ord1[gid]; }     // work-ordered lists (k_order_*)
-  else           { if (gid >= w.count[0]) return; col = w.ord2[gid]; }
+  else           { if (gid >= w.count[0] || w.count[0] <= w.ws_gate) return; col = w.ord2[gid]; }
   const int c = col / pcols, i = col - c * pcols;
   // zm_convr returns after the first gather when a chunk has no convective column (zm_conv.F90:917): its
   // first-pass results stand
@@ -445,6 +448,291 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
     cape = fmax2(cape, 0.0);
   }
   w.cape[col] = cape; w.cin[col] = cin; w.tl[col] = tl;
+  w.lcl[col] = lcl; w.lel[col] = lel; w.mx[col] = mx;
+#undef BUOY
+#undef IN2
+#undef IN2P
+}
+
+// ---- buoyan_dilute + parcel_dilute with the two parcel loops on two warps -------------------------------------
+// Same arithmetic as k_buoyan_dilute, for launches whose columns leave most schedulers idle (the second CAPE pass,
+// small batches, a GPU's share of a strongly scaled grid): there the time is the length of one column's dependency
+// chain, and a third of that chain -- the first parcel loop (mixing + one enthalpy inversion per level,
+// zm_conv.F90:4997-5148) -- does not depend on the second loop (rain-out / freezing, two entropy inversions per
+// level, :5175-5273) at all.  A block is two warps over the same 32 columns: warp 0 runs the first loop and hands
+// (tmix, qsmix, qtmix) of every level to warp 1 through global scratch, publishing its progress per lane in shared
+// memory; warp 1 runs the second loop one or more levels behind, then the CAPE / CIN sums.  Every quantity is
+// computed by the same operations as in the one-thread version.
+template <int PASS, bool ORG = false>
+__global__ void __launch_bounds__(64, 4)
+k_buoyan_dilute_ws(ConvrIn in, ConvrWork w) {
+  extern __shared__ double sm_buoy[];               // [pver+2][32], then 2*32 ints of handshake state
+  zmm::hot_tables_load();
+  zmm::hot_svp_load();
+  const int pcols = P.pcols, pver = P.pver, msg = P.msg;
+  const int ncolpad = in.nchunks * pcols;
+  const int lane = threadIdx.x & 31;
+  const bool roleA = threadIdx.x < 32;
+  volatile int* prog = reinterpret_cast<volatile int*>(sm_buoy + (size_t)(pver + 2) * 32);   // [32] level published
+  int* sh_i = const_cast<int*>(prog) + 32;                                                 // [32] lcl of the column
+  if (roleA) prog[lane] = 0x7fffffff;
+  __syncthreads();
+  const int gid = blockIdx.x * 32 + lane;
+  int col;
+  if (PASS == 1) { if (gid >= w.count[3]) return; col = w.ord1[gid]; }
+  else           { if (gid >= w.count[0] || w.count[0] > w.ws_gate) return; col = w.ord2[gid]; }
+  const int c = col / pcols, i = col - c * pcols;
+  if (w.skip_idle_chunks && w.n1chunk[c] == 0) return;
+#define BUOY(k) sm_buoy[(k) * 32 + lane]
+#define IN2(a, k) in.a[cidx(c, (k) - 1, i, pver)]
+#define IN2P(a, k) in.a[cidx(c, (k) - 1, i, pver + 1)]
+  const size_t n2 = (size_t)ncolpad * pver;
+  double* ab_t = w.ab + col;                         // stride ncolpad per level
+  double* ab_qs = w.ab + n2 + col;
+  double* ab_qt = w.ab + 2 * n2 + col;
+
+  const double eps1 = P.eps1, grav = P.grav, cp = P.cpres, rl = P.rl;
+  const double zs = in.geos[(size_t)c * pcols + i] * P.rgrav;
+  const double pblh = in.pblh[(size_t)c * pcols + i];
+  const double tpert = in.tpert[(size_t)c * pcols + i];
+  const double org2rkm = 10.0, org2Tpert = 0.0;     // zm_conv.F90:4948-4951
+  // launch level: both warps derive it (inputs only)
+  const int pblt = pbl_top_level(in, c, i, zs, pblh);
+  const int lon = min(pver, pblt + 2);
+  int mx = lon;
+  double tl, ql, pl, zl = 0.0;
+  if (P.lparcel_pbl) {
+    double pbl_dz = (IN2(zm, pblt) + zs) - zs;
+    double parcel_dz = fmax2(IN2P(zi, pver), P.parcel_hscale * pbl_dz);
+    double parcel_ztop = parcel_dz + zs;
+    double parcel_hdp = 0.0, parcel_qdp = 0.0, parcel_dp = 0.0;
+    int ipar = 0;
+    for (int k = pver; k >= msg + 1; --k) {
+      if (IN2P(zi, k + 1) <= parcel_dz) {
+        ipar = k;
+        double dp_zfrac;
+        if (k == pver) dp_zfrac = 1.0;
+        else dp_zfrac = fmin2(1.0, (parcel_dz - IN2P(zi, k + 1)) / (IN2P(zi, k) - IN2P(zi, k + 1)));
+        double qk = IN2(qh, k), tk = IN2(t, k), zk = IN2(zm, k) + zs;
+        double hmn_lev = hmn_launch(tk, qk, zk);
+        double dp_lev = IN2P(paph, k + 1) * 0.01 - IN2P(paph, k) * 0.01;
+        parcel_hdp = parcel_hdp + (hmn_lev * dp_lev) * dp_zfrac;
+        parcel_qdp = parcel_qdp + (qk * dp_lev) * dp_zfrac;
+        parcel_dp = parcel_dp + dp_lev * dp_zfrac;
+      }
+    }
+    double hpar = parcel_hdp / parcel_dp, qpar = parcel_qdp / parcel_dp;
+    mx = ipar;
+    tl = (hpar - rl * qpar - grav * parcel_ztop) / cp;
+    ql = qpar;
+    pl = IN2(pap, mx) * 0.01;
+  } else {
+    double hmax = 0.0;
+    for (int k = lon; k >= max(pblt, msg + 1); --k) {
+      double qk = IN2(qh, k), tk = IN2(t, k), zk = IN2(zm, k) + zs;
+      double hmn = hmn_launch(tk, qk, zk);
+      if (hmn > hmax) { hmax = hmn; mx = k; }
+    }
+    tl = IN2(t, mx);
+    ql = IN2(qh, mx);
+    pl = IN2(pap, mx) * 0.01;
+  }
+  const double lwmax = 1.e-3, tscool = 0.0;
+
+  if (roleA) {
+    // ================= first parcel loop (zm_conv.F90:5002-5144) =================
+    const double dmpdz = w.dmpdz[col];
+    const double landfrac = ORG ? in.landfrac[(size_t)c * pcols + i] : 0.0;
+    int lcl = mx;
+    double t_p = IN2(t, mx), q_p = IN2(qh, mx), p_p = IN2(pap, mx) * 0.01, z_p = IN2(zm, mx) + zs;
+    double tmix1_p = t_p, qtmix_p, qsmix1_p, smix_p;
+    double sp = 0.0, qtp = 0.0, mp = 0.0, sp0, qtp0;
+    const double mp0 = 1.0;
+    double dum;
+    if (P.lparcel_pbl) {
+      qtp0 = ql; sp0 = enthalpy_q(tl, pl, qtp0, zl, dum);
+      (void)enthalpy_q(tmix1_p, p_p, qtp0, z_p, qsmix1_p);     // qsmix = qsat_hPa(tmix, p)
+    } else {
+      qtp0 = q_p; sp0 = enthalpy_q(t_p, p_p, qtp0, z_p, qsmix1_p);
+    }
+    smix_p = sp0; qtmix_p = qtp0;
+    ab_qs[(size_t)(mx - 1) * ncolpad] = qsmix1_p;              // the second loop starts from qsmix(mx)
+    __threadfence_block();
+    prog[lane] = mx;
+    for (int k = mx - 1; k >= msg + 1; --k) {
+      const double t_k = IN2(t, k), q_k = IN2(qh, k), p_k = IN2(pap, k) * 0.01, z_k = IN2(zm, k) + zs;
+      const double org_k = ORG ? IN2(org, k) : 0.0;
+      double dp = (p_k - p_p);
+      double qtenv = 0.5 * (q_k + q_p);
+      double tenv = 0.5 * (t_k + t_p);
+      double penv = 0.5 * (p_k + p_p);
+      double zenv = 0.5 * (z_k + z_p);
+      double senv = enthalpy_q(tenv, penv, qtenv, zenv, dum);
+      double dpdz = -(penv * grav) / (P.rgas * tenv);
+      double dzdp = 1.0 / dpdz;
+      double dmpdp;
+      if (ORG) {                                   // tht_tweaks: dmpdz_lnd = dmpdz_mask (zm_conv.F90:5072)
+        double dmpdz_mask = dmpdz;
+        const double dmpdz_lnd = dmpdz_mask;
+        dmpdz_mask = landfrac * dmpdz_lnd + (1.0 - landfrac) * dmpdz_mask;
+        dmpdp = (dmpdz_mask / (1.0 + org_k * org2rkm)) * dzdp;
+      } else {
+        dmpdp = dmpdz * dzdp;
+      }
+      sp = sp - dmpdp * dp * senv;
+      qtp = qtp - dmpdp * dp * qtenv;
+      mp = mp - dmpdp * dp;
+      double smix_k = (sp0 + sp) / (mp0 + mp);
+      double qtmix_k = (qtp0 + qtp) / (mp0 + mp);
+      double tmix_k, qsmix_k;
+      if (!invert<1>(smix_k, p_k, z_k, qtmix_k, tmix1_p, tmix_k, qsmix_k))
+        report_fail(w, 2, col, p_k, tmix1_p, qtmix_k, smix_k);
+      // hand level k to the second loop before the (rare) LCL inversion
+      ab_t[(size_t)(k - 1) * ncolpad] = tmix_k;
+      ab_qs[(size_t)(k - 1) * ncolpad] = qsmix_k;
+      ab_qt[(size_t)(k - 1) * ncolpad] = qtmix_k;
+      __threadfence_block();
+      prog[lane] = k;
+      if (qsmix_k <= qtmix_k && qsmix1_p > qtmix_p) {
+        lcl = k;
+        double qxsk = qtmix_k - qsmix_k;
+        double qxskp1 = qtmix_p - qsmix1_p;
+        double dqxsdp = (qxsk - qxskp1) / dp;
+        pl = p_p - qxskp1 / dqxsdp;
+        zl = z_p - qxskp1 / dqxsdp * dzdp;
+        double dsdp = (smix_k - smix_p) / dp;
+        double dqtdp = (qtmix_k - qtmix_p) / dp;
+        double slcl = smix_p + dsdp * (pl - p_p);
+        double qtlcl = qtmix_p + dqtdp * (pl - p_p);
+        double qslcl;
+        if (!invert<1>(slcl, pl, zl, qtlcl, tmix_k, tl, qslcl))
+          report_fail(w, 3, col, pl, tmix_k, qtlcl, slcl);
+      }
+      t_p = t_k; q_p = q_k; p_p = p_k; z_p = z_k;
+      tmix1_p = tmix_k; qtmix_p = qtmix_k; qsmix1_p = qsmix_k; smix_p = smix_k;
+    }
+    // lcl, pl, tl are final: the second loop's CAPE sums wait for them
+    w.tl[col] = tl;
+    w.cin[col] = pl;                                // pl travels through the cin slot until warp 1 overwrites it
+    sh_i[lane] = lcl;
+    __threadfence_block();
+    prog[lane] = 0;
+    return;
+  }
+
+  // ================= second parcel loop (zm_conv.F90:5180-5269), CAPE / CIN =================
+  double* tp_o = w.tp + col;        // stride ncolpad per level
+  double* qstp_o = w.qstp + col;
+  // levels outside [msg+1, mx] keep environment values (zm_conv.F90:4597-4598, 4760-4761)
+  for (int k = 1; k <= pver; ++k)
+    if (k <= msg || k > mx) {
+      tp_o[(size_t)(k - 1) * ncolpad] = IN2(t, k);
+      qstp_o[(size_t)(k - 1) * ncolpad] = IN2(qh, k);
+    }
+  double xsh2o_p = 0.0, ds_xsh2o_p = 0.0, ds_freeze_p = 0.0;
+  {
+    const int k = mx;                        // launch level (zm_conv.F90:5180-5200)
+    const double t_p = IN2(t, k), q_p = IN2(qh, k);
+    double tpk = t_p, qstpk = q_p;
+    double tpv;
+    if (ORG) tpv = (tpk + (org2Tpert * IN2(org, k) + tpert)) * (1.0 + qstpk / eps1) / (1.0 + qstpk);
+    else     tpv = (tpk + tpert) * (1.0 + qstpk / eps1) / (1.0 + qstpk);
+    double tv = t_p * (1.0 + q_p / eps1) / (1.0 + q_p);
+    BUOY(k) = tpv - tv + P.tiedke_add;
+    tp_o[(size_t)(k - 1) * ncolpad] = tpk;
+    qstp_o[(size_t)(k - 1) * ncolpad] = qstpk;
+  }
+  while (prog[lane] > mx) { }
+  __threadfence_block();
+  double qsmix2_p = *((volatile double*)&ab_qs[(size_t)(mx - 1) * ncolpad]);
+  for (int k = mx - 1; k >= msg + 1; --k) {
+    const double t_k = IN2(t, k), q_k = IN2(qh, k), p_k = IN2(pap, k) * 0.01;
+    const double org_k = ORG ? IN2(org, k) : 0.0;
+    while (prog[lane] > k) { }
+    __threadfence_block();
+    const double tmix_k = *((volatile double*)&ab_t[(size_t)(k - 1) * ncolpad]);
+    const double qsmix_k = *((volatile double*)&ab_qs[(size_t)(k - 1) * ncolpad]);
+    const double qtmix_k = *((volatile double*)&ab_qt[(size_t)(k - 1) * ncolpad]);
+    double dum;
+    double tmix2 = tmix_k, qsmix2 = qsmix_k;
+    double smix2 = entropy_q(tmix2, p_k, qtmix_k, dum);
+    double xsh2o_k = 0.0, ds_xsh2o_k = 0.0, ds_freeze_k = 0.0, new_s = 0.0, new_q = 0.0;
+#pragma unroll 1
+    for (int ii = 0; ii < 2; ++ii) {
+      xsh2o_k = fmax2(0.0, qtmix_k - qsmix2 - lwmax);
+      ds_xsh2o_k = ds_xsh2o_p - P.cpliq * zmm::log_(tmix2 / P.tfreez) * fmax2(0.0, (xsh2o_k - xsh2o_p));
+      if (tmix2 <= P.tfreez + tscool && ds_freeze_p == 0.0)
+        ds_freeze_k = (P.latice / tmix2) * fmax2(0.0, qtmix_k - qsmix2 - xsh2o_k);
+      if (tmix2 <= P.tfreez + tscool && ds_freeze_p != 0.0)
+        ds_freeze_k = ds_freeze_p + (P.latice / tmix2) * fmax2(0.0, (qsmix2_p - qsmix2));
+      new_s = smix2 + ds_xsh2o_k + ds_freeze_k;
+      new_q = qtmix_k - xsh2o_k;
+      double tfg = tmix2;
+      if (!invert<0>(new_s, p_k, 0.0, new_q, tfg, tmix2, qsmix2))
+        report_fail(w, 4, col, p_k, tfg, new_q, new_s);
+    }
+    double tpk = tmix2;
+    double qstpk = (new_q > qsmix2) ? qsmix2 : new_q;
+    double tpv;
+    if (ORG) tpv = (tpk + (org2Tpert * org_k + tpert)) * (1.0 + qstpk / eps1) / (1.0 + new_q);
+    else     tpv = (tpk + tpert) * (1.0 + qstpk / eps1) / (1.0 + new_q);
+    double tv = t_k * (1.0 + q_k / eps1) / (1.0 + q_k);
+    BUOY(k) = tpv - tv + P.tiedke_add;
+    tp_o[(size_t)(k - 1) * ncolpad] = tpk;
+    qstp_o[(size_t)(k - 1) * ncolpad] = qstpk;
+    qsmix2_p = qsmix2; xsh2o_p = xsh2o_k; ds_xsh2o_p = ds_xsh2o_k; ds_freeze_p = ds_freeze_k;
+  }
+  while (prog[lane] > 0) { }
+  __threadfence_block();
+  const int lcl = sh_i[lane];
+  pl = *((volatile double*)&w.cin[col]);
+
+  // ---- CAPE / CIN (zm_conv.F90:4742-4816) ----------------------------------------------------
+  const bool plge600 = pl >= P.plclmin;
+  double cape = 0.0, cin = 0.0;
+  int lel = pver;
+  if (!plge600) {
+    for (int k = msg + 1; k <= mx; ++k) {
+      tp_o[(size_t)(k - 1) * ncolpad] = IN2(t, k);
+      qstp_o[(size_t)(k - 1) * ncolpad] = IN2(qh, k);
+    }
+  } else {
+    int lelten[ZM_MAXCIN];
+    double capeten[ZM_MAXCIN], cinten[ZM_MAXCIN];
+#pragma unroll
+    for (int n = 0; n < ZM_MAXCIN; ++n) { lelten[n] = pver; capeten[n] = 0.0; cinten[n] = 0.0; }
+    int knt = 0;
+    for (int k = msg + 2; k <= pver; ++k) {
+      if (k < lcl) {
+        if (BUOY(k + 1) > 0.0 && BUOY(k) <= 0.0) {
+          knt = min(P.num_cin, knt + 1);
+#pragma unroll
+          for (int n = 0; n < ZM_MAXCIN; ++n) if (n == knt - 1) lelten[n] = k;
+        }
+      }
+    }
+    double pf_k = IN2P(paph, msg + 1) * 0.01, pf_n = IN2P(paph, msg + 2) * 0.01;
+    for (int k = msg + 1; k <= mx; ++k) {
+      const double pf_k1 = pf_n;
+      if (k < mx) pf_n = IN2P(paph, k + 2) * 0.01;
+      double lg = zmm::log_hot(div_hot(pf_k1, pf_k));        // log(pf(k+1)/pf(k)), zm_conv.F90:4789
+      pf_k = pf_k1;
+      double b = BUOY(k);
+#pragma unroll
+      for (int n = 0; n < ZM_MAXCIN; ++n) {
+        if (n < P.num_cin && k > lelten[n]) {
+          capeten[n] = capeten[n] + P.rgas * b * lg;
+          cinten[n] = cinten[n] - P.rgas * fmin2(b, 0.0) * lg;
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < ZM_MAXCIN; ++n) {
+      if (n < P.num_cin && capeten[n] > cape) { cape = capeten[n]; cin = cinten[n]; lel = lelten[n]; }
+    }
+    cape = fmax2(cape, 0.0);
+  }
+  w.cape[col] = cape; w.cin[col] = cin;
   w.lcl[col] = lcl; w.lel[col] = lel; w.mx[col] = mx;
 #undef BUOY
 #undef IN2

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <algorithm>
 #include <string>
 #include <mutex>
 #include <chrono>
@@ -351,7 +352,7 @@ void tick(Workspace& ws, cudaStream_t s, const char* name) {
 int lmax_for(int pver) { return pver <= 32 ? 32 : (pver <= 64 ? 64 : (pver <= 128 ? 128 : 0)); }
 
 size_t convr_work_bytes(size_t ncolpad, int pver) {
-  return 4 * al(ncolpad, 8) + 3 * al(ncolpad, 4) + 2 * al(ncolpad * pver, 8) + al(ncolpad, 4) +
+  return 4 * al(ncolpad, 8) + 3 * al(ncolpad, 4) + 5 * al(ncolpad * pver, 8) + al(ncolpad, 4) +
          al(2 * ncolpad, 4) + 4 * al(ncolpad, 4) + al(4 + ZM_ORD_INTS, 4) + al(8, 8) + 4096;
 }
 
@@ -371,10 +372,15 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   w.dmpdz = ws.take<double>(ncolpad);
   w.lcl = ws.take<int>(ncolpad); w.lel = ws.take<int>(ncolpad); w.mx = ws.take<int>(ncolpad);
   w.tp = ws.take<double>(ncolpad * pver); w.qstp = ws.take<double>(ncolpad * pver);
+  w.ab = ws.take<double>(3 * ncolpad * pver);
   w.wl1 = ws.take<int>(ncolpad); w.wl2 = ws.take<int>(2 * ncolpad);
   w.okey = ws.take<int>(ncolpad); w.ord1 = ws.take<int>(ncolpad); w.ord2 = ws.take<int>(ncolpad);
   w.count = ws.take<int>(4 + ZM_ORD_INTS); w.errinfo = ws.take<double>(8);
   w.n1chunk = ws.take<int>((size_t)in.nchunks); w.skip_idle_chunks = 0;
+  // Two-warp CAPE kernel (first parcel loop on one warp, second on another): for launches that leave the schedulers
+  // mostly idle.  2 x 32 threads per 32 columns at <= 192 registers fit one wave up to ~25k columns.
+  static const int ws_env = getenv("ZM_CAPE_TWO_WARPS") ? atoi(getenv("ZM_CAPE_TWO_WARPS")) : 1;
+  w.ws_gate = ws_env ? 24576 : -1;
   ws.last_count = w.count; ws.last_err = w.errinfo;
   for (auto e : ws.tev) cudaEventDestroy(e);
   ws.tev.clear(); ws.tnames.clear();
@@ -400,6 +406,15 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
     CK(cudaFuncSetAttribute((k_buoyan_dilute<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute((k_buoyan_dilute<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
+  const int nblk_ws = (int)((ncolpad + 31) / 32);
+  const size_t smem_ws = (size_t)(pver + 2) * 32 * sizeof(double) + 64 * sizeof(int);
+  if (smem_ws + 22 * 1024 > 48 * 1024) {
+    CK(cudaFuncSetAttribute((k_buoyan_dilute_ws<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+    CK(cudaFuncSetAttribute((k_buoyan_dilute_ws<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+    CK(cudaFuncSetAttribute((k_buoyan_dilute_ws<2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+    CK(cudaFuncSetAttribute((k_buoyan_dilute_ws<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+  }
+  const bool ws1 = w.ws_gate > 0 && ncolpad <= (size_t)w.ws_gate;       // first pass: the host knows the column count
   tick(ws, s, "start");
   k_convr_init<<<592, 256, 0, s>>>(in, o, w); ++tls_launches;
   if (org_on) {      // zm_conv.F90:555-556, 793-819
@@ -410,6 +425,8 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   k_order_scatter<1><<<nblk_ord, 256, 0, s>>>(in, w); ++tls_launches;
   tick(ws, s, "convr_init");
   if (g_params.cam3) k_buoyan_undilute<<<nblk_cols, TB, smem, s>>>(in, w);     // zm_conv.F90:871-880
+  else if (ws1 && org_on) k_buoyan_dilute_ws<1, true><<<nblk_ws, 64, smem_ws, s>>>(in, w);
+  else if (ws1)           k_buoyan_dilute_ws<1, false><<<nblk_ws, 64, smem_ws, s>>>(in, w);
   else if (org_on)   k_buoyan_dilute<1, true><<<nblk_cols, TB, smem, s>>>(in, w);
   else if (ncolpad <= 24576)                 // few columns: the per-column chain is all that counts (latency mode)
     k_buoyan_dilute<1, false, true><<<nblk_cols, TB, smem, s>>>(in, w);
@@ -440,6 +457,12 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
     const size_t smem2 = (size_t)(pver + 2) * tb2 * sizeof(double);
     if (org_on) k_buoyan_dilute<2, true><<<nblk2, tb2, smem2, s>>>(in, w);
     else        k_buoyan_dilute<2><<<nblk2, tb2, smem2, s>>>(in, w);
+    if (w.ws_gate > 0) {       // worklists up to ws_gate columns take the two-warp kernel instead (device-side gate)
+      const int nb = (int)std::min<size_t>((size_t)nblk_ws, (size_t)(w.ws_gate + 31) / 32);
+      if (org_on) k_buoyan_dilute_ws<2, true><<<nb, 64, smem_ws, s>>>(in, w);
+      else        k_buoyan_dilute_ws<2, false><<<nb, 64, smem_ws, s>>>(in, w);
+      ++tls_launches;
+    }
   }
   ++tls_launches;
   tick(ws, s, "buoyan_dilute_pass2");
