@@ -464,7 +464,7 @@ k_buoyan_dilute(ConvrIn in, ConvrWork w) {
 // memory; warp 1 runs the second loop one or more levels behind, then the CAPE / CIN sums.  Every quantity is
 // computed by the same operations as in the one-thread version.
 template <int PASS, bool ORG = false>
-__global__ void __launch_bounds__(64, 4)
+__global__ void __launch_bounds__(64, 6)
 k_buoyan_dilute_ws(ConvrIn in, ConvrWork w) {
   extern __shared__ double sm_buoy[];               // [pver+2][32], then 2*32 ints of handshake state
   zmm::hot_tables_load();
