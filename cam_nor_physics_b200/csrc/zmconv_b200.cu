@@ -378,9 +378,15 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   w.count = ws.take<int>(4 + ZM_ORD_INTS); w.errinfo = ws.take<double>(8);
   w.n1chunk = ws.take<int>((size_t)in.nchunks); w.skip_idle_chunks = 0;
   // Two-warp CAPE kernel (first parcel loop on one warp, second on another): for launches that leave the schedulers
-  // mostly idle.  2 x 32 threads per 32 columns at <= 192 registers fit one wave up to ~25k columns.
+  // mostly idle.  Six 64-thread blocks (32 columns each) are resident per SM at <= 170 registers: one wave holds
+  // 6 x 32 x SMs columns (28,416 on a B200); larger launches keep one thread per column.
   static const int ws_env = getenv("ZM_CAPE_TWO_WARPS") ? atoi(getenv("ZM_CAPE_TWO_WARPS")) : 1;
-  w.ws_gate = ws_env ? 24576 : -1;
+  static const int ws_cap = [] {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return 6 * 32 * sms;
+  }();
+  w.ws_gate = ws_env ? ws_cap : -1;
   ws.last_count = w.count; ws.last_err = w.errinfo;
   for (auto e : ws.tev) cudaEventDestroy(e);
   ws.tev.clear(); ws.tnames.clear();
