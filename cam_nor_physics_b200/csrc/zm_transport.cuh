@@ -28,8 +28,10 @@ k_conv_evap(EvapArgs a) {
     // what goes back to the host never depends on stale device memory
     for (int k = 0; k < pver; ++k) {
       const size_t e = cidx(c, k, i, pver);
-      a.tend_s[e] = 0.0; a.tend_q[e] = 0.0; a.tend_s_snwprd[e] = 0.0; a.tend_s_snwevmlt[e] = 0.0;
-      a.ntprprd[e] = 0.0; a.ntsnprd[e] = 0.0;
+      a.tend_s[e] = 0.0; a.tend_q[e] = 0.0;
+      // tend_s_snwprd, tend_s_snwevmlt, ntprprd, ntsnprd are history diagnostics (zm_conv_intr.F90:779-794): all four
+      // NULL inside the fused zm_conv_tend step
+      if (a.ntprprd) { a.tend_s_snwprd[e] = 0.0; a.tend_s_snwevmlt[e] = 0.0; a.ntprprd[e] = 0.0; a.ntsnprd[e] = 0.0; }
     }
     for (int k = 0; k < pverp; ++k) { a.flxprec[cidx(c, k, i, pverp)] = 0.0; a.flxsnow[cidx(c, k, i, pverp)] = 0.0; }
     a.snow[col] = 0.0;
@@ -71,10 +73,12 @@ k_conv_evap(EvapArgs a) {
     work2 = fmax2(fsnow_conv, work1);
     if (snowmlt > 0.0) work2 = 0.0;
     const double ntsnprd = prdprec * work2 - evpsnow - snowmlt;
-    a.tend_s_snwprd[e] = prdprec * work2 * latice;
-    a.tend_s_snwevmlt[e] = -(evpsnow + snowmlt) * latice;
-    a.ntprprd[e] = ntprprd;
-    a.ntsnprd[e] = ntsnprd;
+    if (a.ntprprd) {
+      a.tend_s_snwprd[e] = prdprec * work2 * latice;
+      a.tend_s_snwevmlt[e] = -(evpsnow + snowmlt) * latice;
+      a.ntprprd[e] = ntprprd;
+      a.ntsnprd[e] = ntsnprd;
+    }
     flxprec = flxprec + ntprprd * pdel / gravit;
     flxsnow = flxsnow + ntsnprd * pdel / gravit;
     flxprec = fmax2(flxprec, 0.0);
@@ -165,8 +169,12 @@ __global__ void k_momtran_init(MomArgs a) {
     // e -> (c, m, k, i)
     size_t i = e % pcols, r = e / pcols;
     size_t m = (r / pver) % a.ncnst, c = r / ((size_t)pver * a.ncnst);
-    a.pguall[e] = 0.0; a.pgdall[e] = 0.0;
-    if ((int)i < a.ncol[c]) { a.icwu[e] = a.q[e]; a.icwd[e] = a.q[e]; }
+    // pguall / pgdall / icwu / icwd are history diagnostics (ZMUPGU ... ZMICVD, zm_conv_intr.F90:846-857): all four
+    // NULL inside the fused zm_conv_tend step, which does not return them
+    if (a.pguall) {
+      a.pguall[e] = 0.0; a.pgdall[e] = 0.0;
+      if ((int)i < a.ncol[c]) { a.icwu[e] = a.q[e]; a.icwd[e] = a.q[e]; }
+    }
     if (m < 2 && a.domom[m]) a.dqdt[e] = 0.0;
   }
   for (size_t e = tid; e < n2; e += nth) a.seten[e] = 0.0;
@@ -306,10 +314,12 @@ k_momtran_t(MomArgs a) {
       if (k >= ktm) dc = +(X_p - X_k + Y_p - Y_k) / dp_k;
       if (k >= kbm && k == mx) dc = (1.0 / dp_k) * (-X_k - Y_k);
       a.dqdt[QI(m, k)] = dc;
-      a.pguall[QI(m, k)] = -SA(M_PGU + m, k);
-      a.pgdall[QI(m, k)] = -SA(M_PGD + m, k);
-      a.icwu[QI(m, k)] = SA(M_CONU + m, k);
-      a.icwd[QI(m, k)] = SA(M_COND + m, k);
+      if (a.pguall) {
+        a.pguall[QI(m, k)] = -SA(M_PGU + m, k);
+        a.pgdall[QI(m, k)] = -SA(M_PGD + m, k);
+        a.icwu[QI(m, k)] = SA(M_CONU + m, k);
+        a.icwd[QI(m, k)] = SA(M_COND + m, k);
+      }
       SA(M_MF + m, k) = (k >= ktm) ? (-X_k - Y_k) : 0.0;
     }
   }

@@ -1278,10 +1278,11 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
   // not among zm_conv_tend's outputs: not materialised here (all four NULL together)
   double *heat = ws.take<double>(n2), *qtnd = ws.take<double>(n2), *eurt = nullptr, *dif = nullptr, *dnlf = nullptr,
          *dnif = nullptr, *t1 = ws.take<double>(n2), *q1 = ws.take<double>(n2), *ev_s = ws.take<double>(n2),
-         *ev_q = ws.take<double>(n2), *snwprd = ws.take<double>(n2), *snwevmlt = ws.take<double>(n2),
-         *ntprprd = ws.take<double>(n2), *ntsnprd = ws.take<double>(n2), *seten = ws.take<double>(n2);
-  double *winds = ws.take<double>(2 * n2), *wtend = ws.take<double>(2 * n2), *pgu = ws.take<double>(2 * n2),
-         *pgd = ws.take<double>(2 * n2), *icwu = ws.take<double>(2 * n2), *icwd = ws.take<double>(2 * n2);
+         *ev_q = ws.take<double>(n2), *snwprd = nullptr, *snwevmlt = nullptr, *ntprprd = nullptr, *ntsnprd = nullptr,
+         *seten = ws.take<double>(n2);     // zm_conv_evap's four history diagnostics are not materialised either
+  // momtran's pguall / pgdall / icwu / icwd are history diagnostics the step does not return: not materialised
+  double *winds = ws.take<double>(2 * n2), *wtend = ws.take<double>(2 * n2), *pgu = nullptr, *pgd = nullptr,
+         *icwu = nullptr, *icwd = nullptr;
   ConvrIn in{nchunks, ncol, t, q, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac, 0.5 * ztodt};
   ConvrOut o{prec, jctop, jcbot, qtnd, heat, mcon, cme, cape, eurt, dlf, pflx, zdu, rprd,
              mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, lengath, ql, rliq, dif, dnlf, dnif, rice};
