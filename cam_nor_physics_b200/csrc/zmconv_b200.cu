@@ -702,28 +702,35 @@ __global__ void k_tend_finalize(int n2, int n2p, int nper, const double* heat, c
 }
 
 // ---- global water / energy budget terms (what check_energy_chng tests after ZM, physpkg.F90:2865) --
-// Deterministic two-stage reduction: one partial per block, then a single block adds them in order.
-__global__ void k_conservation_partial(int nchunks, const int* ncol, const double* pdel, const double* pq,
-                                       const double* ps, const double* prec, const double* snow,
-                                       const double* rliq, const int* lengath, double* partial) {
+// Deterministic two-stage reduction (the result depends on nothing but the inputs and the grid): one thread per column
+// sums its levels top-down, a fixed tree adds the 128 columns of a block, then one warp per quantity adds the block
+// partials -- each lane its own stride-32 subsequence in order, then a fixed shuffle tree.
+__global__ void __launch_bounds__(128)
+k_conservation_partial(int nchunks, const int* ncol, const double* pdel, const double* pq,
+                       const double* ps, const double* prec, const double* snow,
+                       const double* rliq, const int* lengath, double* partial) {
   __shared__ double sh[6][128];
   const int pcols = P.pcols, pver = P.pver;
   double a[6] = {0, 0, 0, 0, 0, 0};
-  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < nchunks * pcols; col += gridDim.x * blockDim.x) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col < nchunks * pcols) {
     const int c = col / pcols, i = col - c * pcols;
-    if (i >= ncol[c]) continue;
-    double wq = 0.0, ws = 0.0;
-    for (int k = 0; k < pver; ++k) {
-      size_t e = cidx(c, k, i, pver);
-      wq += pdel[e] / P.gravit * pq[e];
-      ws += pdel[e] / P.gravit * ps[e];
+    if (i < ncol[c]) {
+      double wq = 0.0, ws = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < pver; ++k) {
+        const size_t e = cidx(c, k, i, pver);
+        const double m = div_hot(pdel[e], P.gravit);      // layer mass: pdel/g (the IEEE quotient for these operands)
+        wq += m * pq[e];
+        ws += m * ps[e];
+      }
+      a[0] = wq;
+      a[1] = 1000.0 * (prec[col] + rliq[col]);
+      a[2] = ws;
+      a[3] = 1000.0 * (P.latvap * (prec[col] + rliq[col]) + P.latice * snow[col]);
+      a[5] = 1.0;
+      if (i == 0) a[4] = (double)lengath[c];
     }
-    a[0] += wq;
-    a[1] += 1000.0 * (prec[col] + rliq[col]);
-    a[2] += ws;
-    a[3] += 1000.0 * (P.latvap * (prec[col] + rliq[col]) + P.latice * snow[col]);
-    a[5] += 1.0;
-    if (i == 0) a[4] += (double)lengath[c];
   }
   for (int j = 0; j < 6; ++j) sh[j][threadIdx.x] = a[j];
   __syncthreads();
@@ -734,12 +741,12 @@ __global__ void k_conservation_partial(int nchunks, const int* ncol, const doubl
   }
   if (threadIdx.x < 6) partial[blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
 }
-__global__ void k_conservation_final(int nblocks, const double* partial, double* out6) {
-  if (threadIdx.x < 6) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partial[b * 6 + threadIdx.x];
-    out6[threadIdx.x] = s;
-  }
+__global__ void __launch_bounds__(192) k_conservation_final(int nblocks, const double* partial, double* out6) {
+  const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;       // one warp per quantity
+  double s = 0.0;
+  for (int b = lane; b < nblocks; b += 32) s += partial[b * 6 + j];
+  for (int off = 16; off; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+  if (lane == 0) out6[j] = s;
 }
 
 // freqzm, mu_out / md_out, pcont / pconb of zm_conv_tend (zm_conv_intr.F90:685-688, 575-576 + 700-706, 721-729):
@@ -1968,13 +1975,18 @@ int zm_conservation_dev(int nchunks, const int* ncol, const double* pdel, const 
                         const int* lengath, double* out6, void* stream) {
   NEED_INIT();
   static thread_local double* partial = nullptr;
-  const int nb = 296;
-  if (!partial) CK(cudaMalloc(&partial, nb * 6 * sizeof(double)));
+  static thread_local int partial_cap = 0;
+  const int nb = (nchunks * g_params.pcols + 127) / 128;
+  if (nb > partial_cap) {
+    if (partial) { CK(cudaDeviceSynchronize()); CK(cudaFree(partial)); partial = nullptr; }
+    partial_cap = nb + 64;
+    CK(cudaMalloc(&partial, (size_t)partial_cap * 6 * sizeof(double)));
+  }
   Workspace& ws = tls_work;
   if (!ws.stream && ws.ensure(0)) return -100;
   cudaStream_t s = (cudaStream_t)stream;      // NULL = the CUDA default stream
   k_conservation_partial<<<nb, 128, 0, s>>>(nchunks, ncol, pdel, ptend_q, ptend_s, prec, snow, rliq, lengath, partial);
-  k_conservation_final<<<1, 32, 0, s>>>(nb, partial, out6);
+  k_conservation_final<<<1, 192, 0, s>>>(nb, partial, out6);
   tls_launches += 2;
   CK(cudaGetLastError());
   return 0;
