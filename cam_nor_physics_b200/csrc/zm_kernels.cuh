@@ -210,7 +210,10 @@ __global__ void __launch_bounds__(128, LAT ? 2 : 3)
 k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   extern __shared__ double sm_buoy[];               // [pver+2][blockDim.x]
   constexpr bool PAIR = LAT;                         // paired bracket evaluation only where latency-bound
-  zmm::hot_tables_load();                            // before any early return (block-wide barrier inside)
+  // blocks without work leave before the tables are staged (both conditions are uniform over the block)
+  if (PASS == 2 && w.count[0] <= w.ws_gate) return;                  // this worklist goes to k_buoyan_dilute_ws
+  if ((int)(blockIdx.x * blockDim.x) >= (PASS == 1 ? w.count[3] : w.count[0])) return;
+  zmm::hot_tables_load();                            // before any per-thread return (block-wide barrier inside)
   zmm::hot_svp_load();
   const int pcols = P.pcols, pver = P.pver, msg = P.msg;
   const int ncolpad = in.nchunks * pcols;
@@ -467,6 +470,9 @@ template <int PASS, bool ORG = false>
 __global__ void __launch_bounds__(64, 6)
 k_buoyan_dilute_ws(ConvrIn in, ConvrWork w) {
   extern __shared__ double sm_buoy[];               // [pver+2][32], then 2*32 ints of handshake state
+  // blocks without work leave before the tables are staged (both conditions are uniform over the block)
+  if (PASS == 2 && w.count[0] > w.ws_gate) return;                   // this worklist goes to k_buoyan_dilute
+  if ((int)(blockIdx.x * 32) >= (PASS == 1 ? w.count[3] : w.count[0])) return;
   zmm::hot_tables_load();
   zmm::hot_svp_load();
   const int pcols = P.pcols, pver = P.pver, msg = P.msg;
