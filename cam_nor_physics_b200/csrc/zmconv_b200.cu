@@ -381,12 +381,15 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   // mostly idle.  Six 64-thread blocks (32 columns each) are resident per SM at <= 170 registers: one wave holds
   // 6 x 32 x SMs columns (28,416 on a B200); larger launches keep one thread per column.
   static const int ws_env = getenv("ZM_CAPE_TWO_WARPS") ? atoi(getenv("ZM_CAPE_TWO_WARPS")) : 1;
-  static const int ws_cap = [] {
+  static const int ws_sms = [] {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return 6 * 32 * sms;
+    return sms;
   }();
-  w.ws_gate = ws_env ? ws_cap : -1;
+  // resident blocks per SM: 6 by registers, fewer when the buoyancy rows of a deep grid fill the shared memory
+  const size_t ws_block_smem = (size_t)(pver + 2) * 32 * sizeof(double) + 64 * sizeof(int) + 22 * 1024 + 1024;
+  const int ws_bps = (int)std::min<size_t>(6, (227 * 1024) / ws_block_smem);
+  w.ws_gate = ws_env ? ws_bps * 32 * ws_sms : -1;
   ws.last_count = w.count; ws.last_err = w.errinfo;
   for (auto e : ws.tev) cudaEventDestroy(e);
   ws.tev.clear(); ws.tnames.clear();
