@@ -555,33 +555,36 @@ struct CdiagArgs {
   double *cmfmc, *qc, *qc2, *rliq, *rliq2, *cnt, *cnb, *cmfmc2, *rprdsh, *rprdtot, *pcnt, *pcnb;
   const double *pmid, *rprddp;
 };
-__global__ void __launch_bounds__(128)
+// Level-wise statements run one element per thread (grid-stride over the (chunk, level, column) elements, coalesced);
+// the per-column statements (cloud top / base merge and their pressures) follow in a second grid-stride loop.
+__global__ void __launch_bounds__(256)
 k_convect_diagnostics(CdiagArgs a) {
   const int pcols = P.pcols, pver = P.pver, pverp = P.pverp;
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= a.nchunks * pcols) return;
-  const int c = col / pcols, i = col - c * pcols;
-  const bool real_col = i < a.ncol[c];
-  for (int k = 0; k < pverp; ++k) {
-    const size_t ep = cidx(c, k, i, pverp);
-    a.cmfmc2[ep] = 0.0;                                  // zeroed for all pcols (whole-array assignment)
-    if (real_col) a.cmfmc[ep] = a.cmfmc[ep] + 0.0;
-    if (k < pver) {
-      const size_t e = cidx(c, k, i, pver);
-      a.rprdsh[e] = 0.0; a.qc2[e] = 0.0;
-      if (real_col) { a.rprdtot[e] = 0.0 + a.rprddp[e]; a.qc[e] = a.qc[e] + 0.0; }
-    }
+  const size_t nth = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n2p = (size_t)a.nchunks * pverp * pcols, n2 = (size_t)a.nchunks * pver * pcols;
+  for (size_t e = tid; e < n2p; e += nth) {
+    const int i = (int)(e % pcols), c = (int)(e / ((size_t)pverp * pcols));
+    a.cmfmc2[e] = 0.0;                                   // zeroed for all pcols (whole-array assignment)
+    if (i < a.ncol[c]) a.cmfmc[e] = a.cmfmc[e] + 0.0;
   }
-  a.rliq2[col] = 0.0;
-  if (real_col) {
-    const double cnt2 = (double)pver, cnb2 = 1.0;
-    double cnt = a.cnt[col], cnb = a.cnb[col];
-    if (cnt2 < cnt) cnt = cnt2;
-    if (cnb2 > cnb) cnb = cnb2;
-    if (cnb == 1.0) cnb = cnt;
-    a.cnt[col] = cnt; a.cnb[col] = cnb;
-    a.pcnt[col] = a.pmid[cidx(c, (int)cnt - 1, i, pver)];
-    a.pcnb[col] = a.pmid[cidx(c, (int)cnb - 1, i, pver)];
-    a.rliq[col] = a.rliq[col] + 0.0;
+  for (size_t e = tid; e < n2; e += nth) {
+    const int i = (int)(e % pcols), c = (int)(e / ((size_t)pver * pcols));
+    a.rprdsh[e] = 0.0; a.qc2[e] = 0.0;
+    if (i < a.ncol[c]) { a.rprdtot[e] = 0.0 + a.rprddp[e]; a.qc[e] = a.qc[e] + 0.0; }
+  }
+  for (size_t col = tid; col < (size_t)a.nchunks * pcols; col += nth) {
+    const int c = (int)(col / pcols), i = (int)(col - (size_t)c * pcols);
+    a.rliq2[col] = 0.0;
+    if (i < a.ncol[c]) {
+      const double cnt2 = (double)pver, cnb2 = 1.0;
+      double cnt = a.cnt[col], cnb = a.cnb[col];
+      if (cnt2 < cnt) cnt = cnt2;
+      if (cnb2 > cnb) cnb = cnb2;
+      if (cnb == 1.0) cnb = cnt;
+      a.cnt[col] = cnt; a.cnb[col] = cnb;
+      a.pcnt[col] = a.pmid[cidx(c, (int)cnt - 1, i, pver)];
+      a.pcnb[col] = a.pmid[cidx(c, (int)cnb - 1, i, pver)];
+      a.rliq[col] = a.rliq[col] + 0.0;
+    }
   }
 }

@@ -753,38 +753,40 @@ __global__ void __launch_bounds__(192) k_conservation_final(int nblocks, const d
 }
 
 // freqzm, mu_out / md_out, pcont / pconb of zm_conv_tend (zm_conv_intr.F90:685-688, 575-576 + 700-706, 721-729):
-// one warp per chunk.  pcont / pconb are assigned for i <= ncol only (:721-722); the rest of the row is zero-filled.
-__global__ void k_tend_diag(int nchunks, const int* ncol, const double* ps, const double* pmid, const double* mu,
-                            const double* md, const int* jt, const int* maxg, const int* ideep, const int* lengath,
-                            double* freqzm, double* mu_out, double* md_out, double* pcont, double* pconb) {
+// one block per chunk.  The chunk's map column -> gathered slot is built in shared memory, then the (pcols,pver)
+// rows are written in order (coalesced): the scaled mass flux where the column convects, zero elsewhere.
+// pcont / pconb are assigned for i <= ncol only (:721-722); the rest of the row is zero-filled.
+__global__ void __launch_bounds__(128)
+k_tend_diag(int nchunks, const int* ncol, const double* ps, const double* pmid, const double* mu,
+            const double* md, const int* jt, const int* maxg, const int* ideep, const int* lengath,
+            double* freqzm, double* mu_out, double* md_out, double* pcont, double* pconb) {
+  extern __shared__ int sh_inv[];                  // [pcols] gathered slot of a column, -1 if it does not convect
   const int pcols = P.pcols, pver = P.pver;
-  const int lane = threadIdx.x & 31;
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int c = blockIdx.x;
   if (c >= nchunks) return;
   const int n = ncol[c], len = lengath[c];
   const size_t c1 = (size_t)c * pcols;
-  for (int i = lane; i < pcols; i += 32) {
-    freqzm[c1 + i] = 0.0;
-    pcont[c1 + i] = (i < n) ? ps[c1 + i] : 0.0;
-    pconb[c1 + i] = (i < n) ? ps[c1 + i] : 0.0;
-  }
-  for (int e = lane; e < pcols * pver; e += 32) {
-    mu_out[(size_t)c * pcols * pver + e] = 0.0;
-    md_out[(size_t)c * pcols * pver + e] = 0.0;
-  }
-  __syncwarp();
-  for (int i = lane; i < len; i += 32) {
-    const int ii = ideep[c1 + i] - 1;
-    freqzm[c1 + ii] = 1.0;
-    const int j = jt[c1 + i], mx = maxg[c1 + i];
-    if (mx > j) {
-      pcont[c1 + ii] = pmid[cidx(c, j - 1, ii, pver)];
-      pconb[c1 + ii] = pmid[cidx(c, mx - 1, ii, pver)];
+  for (int i = threadIdx.x; i < pcols; i += blockDim.x) sh_inv[i] = -1;
+  __syncthreads();
+  for (int g = threadIdx.x; g < len; g += blockDim.x) sh_inv[ideep[c1 + g] - 1] = g;
+  __syncthreads();
+  for (int i = threadIdx.x; i < pcols; i += blockDim.x) {
+    const int g = sh_inv[i];
+    freqzm[c1 + i] = (g >= 0) ? 1.0 : 0.0;
+    double pt = (i < n) ? ps[c1 + i] : 0.0, pb = pt;
+    if (g >= 0) {
+      const int j = jt[c1 + g], mx = maxg[c1 + g];
+      if (mx > j) { pt = pmid[cidx(c, j - 1, i, pver)]; pb = pmid[cidx(c, mx - 1, i, pver)]; }
     }
-    for (int k = 0; k < pver; ++k) {
-      mu_out[cidx(c, k, ii, pver)] = mu[cidx(c, k, i, pver)] * 100.0 / P.gravit;
-      md_out[cidx(c, k, ii, pver)] = md[cidx(c, k, i, pver)] * 100.0 / P.gravit;
-    }
+    pcont[c1 + i] = pt; pconb[c1 + i] = pb;
+  }
+  for (int e = threadIdx.x; e < pcols * pver; e += blockDim.x) {
+    const int k = e / pcols, i = e - k * pcols;
+    const int g = sh_inv[i];
+    double vu = 0.0, vd = 0.0;
+    if (g >= 0) { vu = mu[cidx(c, k, g, pver)] * 100.0 / P.gravit; vd = md[cidx(c, k, g, pver)] * 100.0 / P.gravit; }
+    mu_out[(size_t)c * pcols * pver + e] = vu;
+    md_out[(size_t)c * pcols * pver + e] = vd;
   }
 }
 
@@ -1917,9 +1919,8 @@ int zm_conv_tend_diag_batch_dev(int nchunks, const int* ncol, const double* ps, 
                                 void* stream) {
   NEED_INIT();
   if (nchunks <= 0) return 0;
-  k_tend_diag<<<(nchunks * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nchunks, ncol, ps, pmid, mu, md, jt, maxg,
-                                                                            ideep, lengath, freqzm, mu_out, md_out,
-                                                                            pcont, pconb);
+  k_tend_diag<<<nchunks, 128, (size_t)g_params.pcols * sizeof(int), (cudaStream_t)stream>>>(
+      nchunks, ncol, ps, pmid, mu, md, jt, maxg, ideep, lengath, freqzm, mu_out, md_out, pcont, pconb);
   ++tls_launches;
   CK(cudaGetLastError());
   return 0;
@@ -2103,7 +2104,8 @@ int zm_convect_diagnostics_batch_dev(int nchunks, const int* ncol, double* cmfmc
   if (nchunks <= 0) return 0;
   CdiagArgs a{nchunks, ncol, cmfmc, qc, qc2, rliq, rliq2, cnt, cnb, cmfmc2, rprdsh, rprdtot, pcnt, pcnb, pmid, rprddp};
   const int ncolpad = nchunks * g_params.pcols;
-  k_convect_diagnostics<<<(ncolpad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a); ++tls_launches;
+  (void)ncolpad;
+  k_convect_diagnostics<<<1184, 256, 0, (cudaStream_t)stream>>>(a); ++tls_launches;
   CK(cudaGetLastError());
   return 0;
 }
