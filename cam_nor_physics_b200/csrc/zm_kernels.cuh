@@ -202,14 +202,14 @@ __global__ void __launch_bounds__(256) k_order_scatter(ConvrIn in, ConvrWork w) 
 // ---- buoyan_dilute + parcel_dilute, one thread per column ----------------------------------
 // zm_conv.F90:4425-4819 and 4824-5277.  PASS 1: every column (list ord1).  PASS 2: worklist wl1 only (as ord2).
 // ORG = true adds the zm_org branches of parcel_dilute (zm_conv.F90:5066-5074, 5186-5188, 5255-5257).
-// LAT = true: latency mode for launches with few columns (second pass; first pass of small batches): paired bracket
-// evaluation and up to 255 registers; LAT = false: throughput mode (168 registers so that a whole f09 shard is
-// resident in one wave, single-site evaluation).
+// LAT = true: up to 255 registers, for launches with few columns (second passes too large for k_buoyan_dilute_ws);
+// LAT = false: 168 registers so that a whole f09 shard is resident in one wave.  (PAIR is a leftover of round 1's
+// paired bracket evaluation: both bracket ends are evaluated side by side by Brent::open in either mode now.)
 template <int PASS, bool ORG = false, bool LAT = (PASS == 2)>
 __global__ void __launch_bounds__(128, LAT ? 2 : 3)
 k_buoyan_dilute(ConvrIn in, ConvrWork w) {
   extern __shared__ double sm_buoy[];               // [pver+2][blockDim.x]
-  constexpr bool PAIR = LAT;                         // paired bracket evaluation only where latency-bound
+  constexpr bool PAIR = LAT;
   // blocks without work leave before the tables are staged (both conditions are uniform over the block)
   if (PASS == 2 && w.count[0] <= w.ws_gate) return;                  // this worklist goes to k_buoyan_dilute_ws
   if ((int)(blockIdx.x * blockDim.x) >= (PASS == 1 ? w.count[3] : w.count[0])) return;

@@ -7,7 +7,7 @@
 // lane == level, while the order-dependent recurrences (k1..i4, hu, su/qu, ql, hd, sd, pflx and the
 // running sums) are executed redundantly by every lane in the reference's own order, so every sum
 // is accumulated exactly as the serial Fortran does (bit-exact vs the CPU oracle).
-// A convective column therefore costs one Goff-Gratch evaluation of latency plus a few short
+// A convective column therefore costs one saturation-pressure evaluation of latency plus a few short
 // scans instead of a 32-level serial chain per thread.
 // The reference's chunk-wide loop bounds (khighest/klowest 3573-3578, kmin/kmax 4245-4246,
 // ktm/kbm 4350-4355) only trim loops whose bodies are re-guarded per column, so a per-column
