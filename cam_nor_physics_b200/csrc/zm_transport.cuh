@@ -510,6 +510,242 @@ k_convtran_t(TranArgs a) {
 #undef CU
 }
 
+// ---- convtran, block per chunk slice -------------------------------------------------------------------
+// The same statements (zm_conv.F90:2108-2302) organised around the memory system instead of around one column:
+//   * a block owns one chunk and walks over groups of G = floor(32 / lengath) active constituents, i.e.
+//     T = G*lengath <= 32 (column, constituent) pairs at a time: lane = pair, warp = level (levels w, w+NW, ...),
+//     so every warp is 27-32 lanes wide whatever the chunk's number of convective columns (CTC_BPC blocks share
+//     the groups of a chunk);
+//   * every row of q and fracis is fetched once (phase A: gather, interface values chat, the level-local products
+//     of the two recurrences -- all level-parallel); the only serial part are the two first-order recurrences
+//     conu (bottom-up, warp 0) and cond (top-down, warp 1), which run side by side out of shared memory (phase B);
+//   * fluxes and the limited tendency are level-parallel again (phase C), and the dqdt slices leave the block as
+//     whole 128-byte rows with the zero-fill of zm_conv.F90:2298 in the same pass (phase D): no k_convtran_zero,
+//     no updraft values parked in HBM, no second sweep over q / fracis.
+// DRAM traffic per launch = q + fracis (touched sectors) + dqdt (once) + the mass-flux arrays once (the blocks of
+// one chunk are neighbours in the grid: L2) -- 1.7 GB for 38 constituents on the f09 shard against 4.4 GB for
+// k_convtran_zero + k_convtran_t.
+// Shared memory, one row per level: [const | chat | eu*fis*c*dp -> conu | ed*fis*c*dp -> cond | mupdudp -> dcondt]
+// x 32 lanes, then mu[pcols], md[pcols]; every access is lane pointer + level*row + compile-time offset.
+// Used when pcols is a power of two from 2 to 32, the rows fit and dqdt is 16-byte aligned; k_convtran_t otherwise.
+#define CTC_T 32
+#define CTC_NW 8
+#define CTC_BPC 3
+#define CTC_GZERO 8
+#define CTC_CONST 0
+#define CTC_CHAT 32
+#define CTC_CONU 64
+#define CTC_COND 96
+#define CTC_DC 128
+#define CTC_MU 160
+__host__ __device__ inline int convtran_c_row(int pcols) { return CTC_MU + 2 * pcols; }
+__host__ __device__ inline size_t convtran_c_smem_bytes(int pver, int pcols) {
+  return (size_t)pver * convtran_c_row(pcols) * sizeof(double);
+}
+__host__ inline bool convtran_c_fits(int pver, int pcols) {
+  return pcols >= 2 && pcols <= CTC_T && (pcols & (pcols - 1)) == 0 && convtran_c_smem_bytes(pver, pcols) <= 200 * 1024;
+}
+// blocks per chunk: no more than the constituent groups a chunk can have (smallest G: floor(32 / pcols))
+__host__ inline int convtran_c_blocks_per_chunk(int nactive, int pcols) {
+  const int gmin = CTC_T / pcols > 0 ? CTC_T / pcols : 1;
+  const int groups = (nactive + gmin - 1) / gmin;
+  return groups < CTC_BPC ? groups : CTC_BPC;
+}
+
+__global__ void __launch_bounds__(32 * CTC_NW, 4)
+k_convtran_c(TranArgs a, int bpc) {
+  extern __shared__ double sm_ctc[];
+  __shared__ int s_inv[CTC_T];
+  const int pcols = P.pcols, pver = P.pver;
+  const int c = blockIdx.x / bpc, g0 = blockIdx.x - c * bpc;
+  const int len = a.lengath[c];
+  const int G = len > 0 ? CTC_T / len : CTC_GZERO;
+  if (g0 * G >= a.nactive) return;                     // uniform over the block: more blocks than groups
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slice = pver * pcols;
+  const size_t cbase = (size_t)c * a.ncnst * slice;    // this chunk's q / fracis / dqdt slices
+  if (len == 0) {                                      // nothing convective in this chunk: dqdt(:,:,m) = 0
+    for (int g = g0; g * G < a.nactive; g += bpc)
+      for (int j = g * G; j < min(g * G + G, a.nactive); ++j) {
+        double* d = a.dqdt + cbase + (size_t)a.active[j] * slice;
+        for (int e = threadIdx.x; e < slice; e += blockDim.x) d[e] = 0.0;
+      }
+    return;
+  }
+  const int row = convtran_c_row(pcols);
+  const double mbsth = 1.e-15;
+  // once per block: column -> gathered position, mu / md of the chunk's convective columns
+  if (threadIdx.x < pcols) s_inv[threadIdx.x] = -1;
+  __syncthreads();
+  if (threadIdx.x < len) s_inv[a.ideep[(size_t)c * pcols + threadIdx.x] - 1] = threadIdx.x;
+  if (lane < len) {
+    const double* mup = a.mu + (size_t)c * slice + lane;
+    const double* mdp = a.md + (size_t)c * slice + lane;
+    double* rg = sm_ctc + CTC_MU + lane;
+#pragma unroll 4
+    for (int k0 = warp; k0 < pver; k0 += CTC_NW) {
+      rg[k0 * row] = mup[k0 * pcols];
+      rg[k0 * row + pcols] = mdp[k0 * pcols];
+    }
+  }
+  zmm::hot_tables_load();                              // ends with a block-wide barrier
+  const int ktm = a.ktm[c], kbm = a.kbm[c];
+  // phase D: a warp stores one constituent's slice, a lane two neighbouring columns of a row (16 bytes)
+  const int hp = pcols >> 1;
+  const int di = (lane % hp) * 2, dk = lane / hp, dstep = 32 / hp;
+  const int ds0 = s_inv[di], ds1 = s_inv[di + 1];
+  // this lane's (column, constituent) pair inside a group
+  const int jl = lane / len, gi = lane - jl * len;
+  const int ii = a.ideep[(size_t)c * pcols + gi] - 1;
+  const int mx = a.mx[(size_t)c * pcols + gi];
+  const size_t go = (size_t)c * slice + gi;                                // gathered arrays, + k0*pcols
+  double* rl = sm_ctc + lane;                                              // + k0*row + CTC_*
+  const double* rg = sm_ctc + CTC_MU + gi;                                 // mu; md at + pcols
+
+  for (int g = g0; g * G < a.nactive; g += bpc) {
+    const int j0 = g * G, ng = min(G, a.nactive - j0);
+    const bool on = jl < ng;
+    const int m = a.active[j0 + (on ? jl : 0)];
+    const bool dry = a.is_dry[m] != 0;
+    const double* qp = a.q + cbase + (size_t)m * slice + ii;               // + k0*pcols
+    const double* fp = a.fracis + cbase + (size_t)m * slice + ii;
+
+    // ---- phase A1: gather const and fisg (every DRAM-latency load of the group is in flight here) ----
+    if (on) {
+#pragma unroll 4
+      for (int k0 = warp; k0 < pver; k0 += CTC_NW) {
+        rl[k0 * row + CTC_CONST] = qp[k0 * pcols];
+        rl[k0 * row + CTC_CONU] = fp[k0 * pcols];      // fisg, replaced by the updraft term in phase A2
+      }
+    }
+    __syncthreads();
+    // ---- phase A2: chat (zm_conv.F90:2119-2147), the level-local terms of the two recurrences ----
+    if (on) {
+#pragma unroll 2
+      for (int k0 = warp; k0 < pver; k0 += CTC_NW) {
+        double* r = rl + k0 * row;
+        const double ck = r[CTC_CONST], ckm1 = (k0 > 0) ? r[CTC_CONST - row] : ck;
+        const double fis = r[CTC_CONU];
+        const size_t gx = go + (size_t)(k0 * pcols);
+        double dpt = a.dp[gx], eut = a.eu[gx], edt = a.ed[gx], dut = a.du[gx];
+        if (dry) {                                     // zm_conv.F90:2087-2095: x*dp/dpdry, one reciprocal for the three
+          const double dpd = a.dpdry[gx], rdpd = rcp_hot(dpd);
+          dut = zmm::div_rcp(dut * dpt, dpd, rdpd); eut = zmm::div_rcp(eut * dpt, dpd, rdpd);
+          edt = zmm::div_rcp(edt * dpt, dpd, rdpd);
+          dpt = dpd;
+        }
+        r[CTC_CHAT] = convtran_chat(ckm1, ck);
+        r[CTC_CONU] = eut * fis * ck * dpt;
+        r[CTC_COND] = edt * fis * ck * dpt;
+        r[CTC_DC] = rg[k0 * row] + dut * dpt;
+      }
+    }
+    __syncthreads();
+    // ---- phase B: conu bottom-up on warp 0 (2152-2175), cond top-down on warp 1 (2153-2186).  The operands of the
+    // next level are loaded, and the reciprocal of its divisor refined, before this level's result is stored, so
+    // that only  multiply-add, quotient, select  remain on the chain; the quotient is formed unconditionally and
+    // selected (a discarded one may be inf / nan) ----
+    if (on && warp == 0) {
+      double conu_kp1 = 0.0, mu_kp1 = 0.0;
+      double* r = rl + (pver - 1) * row;
+      const double* q = rg + (pver - 1) * row;
+      double b_n = r[CTC_DC], u_n = r[CTC_CONU], ch_n = r[CTC_CHAT], mu_n = q[0], rb_n = rcp_hot(b_n);
+      for (int k0 = pver - 1; k0 >= 0; --k0, r -= row, q -= row) {
+        const double mupdudp = b_n, u = u_n, ch = ch_n, rb = rb_n, mu_k = mu_n;
+        const int nx = (k0 > 0) ? -row : 0;            // no branch: the last level reloads itself
+        b_n = r[CTC_DC + nx]; u_n = r[CTC_CONU + nx]; ch_n = r[CTC_CHAT + nx]; mu_n = q[nx];
+        rb_n = rcp_hot(b_n);
+        const double num = (k0 == pver - 1) ? u : mu_kp1 * conu_kp1 + u;
+        const double quo = zmm::div_rcp(num, mupdudp, rb);
+        const double conu = (mupdudp > mbsth) ? quo : ch;
+        r[CTC_CONU] = conu;
+        conu_kp1 = conu; mu_kp1 = mu_k;
+      }
+    } else if (on && warp == 1) {
+      double cond_km1 = 0.0, md_km1 = 0.0, t_km1 = 0.0;
+      double* r = rl;
+      const double* q = rg + pcols;
+      double b_n = q[0], t_n = r[CTC_COND], ch_n = r[CTC_CHAT], rb_n = rcp_hot(b_n);
+      for (int k0 = 0; k0 < pver; ++k0, r += row, q += row) {
+        const double md_k = b_n, t_k = t_n, ch = ch_n, rb = rb_n;
+        const int nx = (k0 < pver - 1) ? row : 0;
+        b_n = q[nx]; t_n = r[CTC_COND + nx]; ch_n = r[CTC_CHAT + nx];
+        rb_n = rcp_hot(b_n);
+        const double num = (k0 == 1) ? -t_km1 : md_km1 * cond_km1 - t_km1;
+        const double quo = zmm::div_rcp(num, md_k, rb);
+        const double cond = (k0 >= 1 && md_k < -mbsth) ? quo : ch;
+        r[CTC_COND] = cond;
+        cond_km1 = cond; md_km1 = md_k; t_km1 = t_k;
+      }
+    }
+    else if (warp >= 2 && (g + bpc) * G < a.nactive) {
+      // the other warps pull the next group's q / fracis rows into L2 meanwhile
+      const int j0n = (g + bpc) * G;
+      if (jl < min(G, a.nactive - j0n)) {
+        const size_t mo = cbase + (size_t)a.active[j0n + jl] * slice + ii;
+        for (int k0 = warp - 2; k0 < pver; k0 += CTC_NW - 2) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.q + mo + k0 * pcols));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.fracis + mo + k0 * pcols));
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase C: limited fluxes and the tendency (2189-2254) ----
+    if (on) {
+      const double* dpp = (dry ? a.dpdry : a.dp) + go;
+#pragma unroll 2
+      for (int k0 = warp; k0 < pver; k0 += CTC_NW) {
+        const int k = k0 + 1;
+        double* r = rl + k0 * row;
+        const double* rm = (k0 > 0) ? r - row : r;
+        const double* rp = (k0 < pver - 1) ? r + row : r;
+        const double* q = rg + k0 * row;
+        const double* qn = (k0 < pver - 1) ? q + row : q;
+        const double dpt_j = dpp[k0 * pcols];
+        const double mu_j = q[0], mu_p = qn[0], md_j = q[pcols], md_p = qn[pcols];
+        const double conu_j = r[CTC_CONU], conu_p = rp[CTC_CONU];
+        const double cond_j = r[CTC_COND], cond_p = rp[CTC_COND];
+        const double chat_j = r[CTC_CHAT], chat_p = rp[CTC_CHAT];
+        const double c_jm1 = rm[CTC_CONST], cj = r[CTC_CONST], c_p = rp[CTC_CONST];
+        double dc = 0.0;
+        if (k >= ktm) {
+          const double fluxin = mu_p * conu_p + mu_j * fmin2(chat_j, c_jm1) - (md_j * cond_j + md_p * fmin2(chat_p, c_p));
+          const double fluxout = mu_j * conu_j + mu_p * fmin2(chat_p, cj) - (md_p * cond_p + md_j * fmin2(chat_j, cj));
+          double netflux = fluxin - fluxout;
+          if (fabs(netflux) < fmax2(fluxin, fluxout) * 1.e-12) netflux = 0.0;
+          dc = div_hot(netflux, dpt_j);
+        }
+        if (k >= kbm) {
+          if (k == mx) {
+            const double fluxin = mu_j * fmin2(chat_j, c_jm1) - md_j * cond_j;
+            const double fluxout = mu_j * conu_j - md_j * fmin2(chat_j, cj);
+            double netflux = fluxin - fluxout;
+            if (fabs(netflux) < fmax2(fluxin, fluxout) * 1.e-12) netflux = 0.0;
+            dc = div_hot(netflux, dpt_j);
+          } else if (k > mx) {
+            dc = 0.0;
+          }
+        }
+        r[CTC_DC] = dc;
+      }
+    }
+    __syncthreads();
+    // ---- phase D: dqdt(:,:,m) = 0, dqdt(ideep(i),k,m) = dcondt(i,k) (2298-2304) as whole rows ----
+    for (int j = warp; j < ng; j += CTC_NW) {
+      double* d = a.dqdt + cbase + (size_t)a.active[j0 + j] * slice + (dk * pcols + di);
+      const double* s = sm_ctc + CTC_DC + j * len + dk * row;
+#pragma unroll 4
+      for (int k0 = dk; k0 < pver; k0 += dstep, d += dstep * pcols, s += dstep * row) {
+        double2 v;
+        v.x = (ds0 >= 0) ? s[ds0] : 0.0;
+        v.y = (ds1 >= 0) ? s[ds1] : 0.0;
+        *reinterpret_cast<double2*>(d) = v;
+      }
+    }
+    // the next group's phase A1 only writes const, which nobody reads any more; its barrier orders phase D above
+    // against the writes of phase A2
+  }
+}
 
 // ---- N4 neighbours of the path ------------------------------------------------
 // geopotential_t (physics/geopotential.F90:153-247): thread per column, bottom-up scan, registers only.

@@ -634,6 +634,21 @@ int convtran_enqueue(cudaStream_t s, TranArgs a, const ChunkBounds& cb) {
   const int ncolpad = a.nchunks * pcols;
   if (a.nactive == 0) return 0;
   a.ktm = cb.ktm; a.kbm = cb.kbm; a.slots = cb.slots; a.count = cb.count;
+  // block per (chunk, constituent group) with every row of q / fracis / dqdt moved once (ZM_CONVTRAN_KERNEL=t keeps
+  // the thread-per-(column, constituent) kernel, which also serves shapes whose work arrays do not fit an SM)
+  static const bool force_t = [] { const char* e = getenv("ZM_CONVTRAN_KERNEL"); return e && e[0] == 't'; }();
+  if (!force_t && convtran_c_fits(pver, pcols) && (reinterpret_cast<uintptr_t>(a.dqdt) & 15) == 0) {
+    const size_t smem = convtran_c_smem_bytes(pver, pcols);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      CK(cudaFuncSetAttribute(k_convtran_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    const int bpc = convtran_c_blocks_per_chunk(a.nactive, pcols);
+    k_convtran_c<<<(unsigned)((size_t)a.nchunks * bpc), 32 * CTC_NW, smem, s>>>(a, bpc); ++tls_launches;
+    CK(cudaGetLastError());
+    return 0;
+  }
   k_convtran_zero<<<a.nchunks * a.nactive, 128, 0, s>>>(a); ++tls_launches;
   const int cpb = convtran_cnst_per_block(pver);
   dim3 blk(32, cpb);
