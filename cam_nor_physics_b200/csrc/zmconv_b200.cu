@@ -56,6 +56,17 @@ struct Workspace {
   int chunk0 = 0;                     // first chunk of this arena's (sub-)batch, for error messages
   cudaStream_t side = nullptr;        // zm_conv_evap runs here, concurrently with momtran
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side2 = nullptr;       // convtran1 runs here, concurrently with momtran and zm_conv_evap
+  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
+  int side_priority = 0; bool side_priority_set = false;
+  int ensure_side2() {
+    if (side2) return 0;
+    if (side_priority_set) CK(cudaStreamCreateWithPriority(&side2, cudaStreamNonBlocking, side_priority));
+    else CK(cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_fork2, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_join2, cudaEventDisableTiming));
+    return 0;
+  }
   int ensure(size_t bytes) {
     if (!stream) CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (bytes > dcap) {
@@ -74,6 +85,9 @@ struct Workspace {
     if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
     if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
     if (side) { cudaStreamDestroy(side); side = nullptr; }
+    if (ev_fork2) { cudaEventDestroy(ev_fork2); ev_fork2 = nullptr; }
+    if (ev_join2) { cudaEventDestroy(ev_join2); ev_join2 = nullptr; }
+    if (side2) { cudaStreamDestroy(side2); side2 = nullptr; }
     if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
     last_count = nullptr; last_err = nullptr;
   }
@@ -317,6 +331,7 @@ struct TendPipe {
       CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // hi = greatest priority (numerically lowest)
       int pr = hi + ninit; if (pr > lo) pr = lo;
       if (!work[ninit].stream) CK(cudaStreamCreateWithPriority(&work[ninit].stream, cudaStreamNonBlocking, pr));
+      work[ninit].side_priority = pr; work[ninit].side_priority_set = true;
       if (!work[ninit].side) {
         CK(cudaStreamCreateWithPriority(&work[ninit].side, cudaStreamNonBlocking, pr));
         CK(cudaEventCreateWithFlags(&work[ninit].ev_fork, cudaEventDisableTiming));
@@ -1360,6 +1375,15 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
     rc = chunk_bounds_enqueue(ws, s, nchunks, jt, maxg, lengath, cb);
     if (rc) return rc;
   }
+  // convtran1 depends on zm_convr's outputs and the chunk bounds only (the constituents it moves are not touched by
+  // the state update): with the fork it runs on a second side stream beside momtran and zm_conv_evap
+  cudaStream_t tran_stream = s;
+  if (fork && do_tran1) {
+    if (ws.ensure_side2()) return -100;
+    CK(cudaEventRecord(ws.ev_fork2, s));
+    CK(cudaStreamWaitEvent(ws.side2, ws.ev_fork2, 0));
+    tran_stream = ws.side2;
+  }
   if (do_mom) {
     MomArgs ma;
     ma.nchunks = nchunks; ma.ncnst = 2; ma.ncol = ncol; ma.jt = jt; ma.mx = maxg; ma.ideep = ideep;
@@ -1375,16 +1399,18 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
     // convtran1 (zm_conv_intr.F90:865-880) on state1%q: its constituents m >= 2 are the caller's (only q(:,:,1)
     // was updated); fake_dpdry = 0 (the transported species are moist; a zeroed array stands in if one is 'dry')
     double* fake_dpdry = ws.take<double>(n2);
-    if (tr1->any_dry) CK(cudaMemsetAsync(fake_dpdry, 0, n2 * sizeof(double), s));
+    if (tr1->any_dry) CK(cudaMemsetAsync(fake_dpdry, 0, n2 * sizeof(double), tran_stream));
     TranArgs ta;
     ta.nchunks = nchunks; ta.ncnst = tr1->ncnst; ta.nactive = tr1->nactive; ta.jt = jt; ta.mx = maxg; ta.ideep = ideep;
     ta.lengath = lengath; ta.active = tr1->active; ta.is_dry = tr1->is_dry;
     ta.q = tr1->q; ta.fracis = tr1->fracis; ta.mu = mu; ta.md = md; ta.du = du; ta.eu = eu; ta.ed = ed; ta.dp = dp;
     ta.dpdry = fake_dpdry; ta.dqdt = tr1->dqdt;
-    rc = convtran_enqueue(s, ta, cb);
+    rc = convtran_enqueue(tran_stream, ta, cb);
     if (rc) return rc;
+    if (tran_stream != s) CK(cudaEventRecord(ws.ev_join2, ws.side2));
     tick(ws, s, "convtran1");
   }
+  if (tran_stream != s) CK(cudaStreamWaitEvent(s, ws.ev_join2, 0));
   if (fork) CK(cudaStreamWaitEvent(s, ws.ev_join, 0));
   if (do_mom)
     k_tend_finalize<true><<<1184, 256, 0, s>>>((int)n2, (int)n2p, nper, heat, qtnd, ev_s, ev_q, seten, wtend, ptend_s,
