@@ -245,7 +245,7 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
       } else if (k >= jt && k < jb) {
         const double rmue = S(A_W1, k);
         S(A_EU, k) = (rmue - S(A_MU, k + 1)) / S(A_DZ, k);
-        S(A_DU, k) = (rmue - S(A_MU, k)) / S(A_DZ, k);
+        S(A_DU, k) = div_z(rmue - S(A_MU, k), S(A_DZ, k));
       }
     }
     WSYNC();
@@ -399,7 +399,9 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
     S(A_RPRD, k) = 0.0;
     if (k >= jt && k < jb && eps0 > 0.0 && S(A_MU, k) >= 0.0) {
       const double muk = S(A_MU, k), dz = S(A_DZ, k);
-      S(A_W1, k) = (muk > 0.0) ? 1.0 / muk : 0.0;
+      double mus = (muk > 0.0) ? muk : 1.0;       // no 1/0 on the idle path (it would leave the inline division)
+      asm("" : "+d"(mus));
+      S(A_W1, k) = (muk > 0.0) ? 1.0 / mus : 0.0;
       S(A_W2, k) = dz * S(A_DU, k);
       S(A_W3, k) = dz * S(A_CU, k);
       S(A_W4, k) = 1.0 + dz * c0mask;
@@ -476,7 +478,7 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
     const double small = 1.e-20;
     // ed level parallel, hd serial (zm_conv.F90:3916-3924)
     PAR(k, msg + 1, pver) {
-      if (k >= jt) S(A_ED, k - 1) = (S(A_MD, k - 1) - S(A_MD, k)) / S(A_DZ, k - 1);
+      if (k >= jt) S(A_ED, k - 1) = div_z(S(A_MD, k - 1) - S(A_MD, k), S(A_DZ, k - 1));
     }
     WSYNC();
     PAR(k, msg + 1, pver) {
@@ -657,13 +659,13 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
   // 1/m -> 1/mb (zm_conv.F90:1252-1262)
   PAR(k, msg + 1, pver) {
     const double dzf = S(A_ZF, k) - S(A_ZF, k + 1), dp = S(A_DP, k);
-    S(A_DU, k) = S(A_DU, k) * dzf / dp;
-    S(A_EU, k) = S(A_EU, k) * dzf / dp;
-    S(A_ED, k) = S(A_ED, k) * dzf / dp;
-    S(A_CU, k) = S(A_CU, k) * dzf / dp;
-    S(A_CMEG, k) = S(A_CMEG, k) * dzf / dp;
-    S(A_RPRD, k) = S(A_RPRD, k) * dzf / dp;
-    S(A_EVP, k) = S(A_EVP, k) * dzf / dp;
+    S(A_DU, k) = div_z(S(A_DU, k) * dzf, dp);
+    S(A_EU, k) = div_z(S(A_EU, k) * dzf, dp);
+    S(A_ED, k) = div_z(S(A_ED, k) * dzf, dp);
+    S(A_CU, k) = div_z(S(A_CU, k) * dzf, dp);
+    S(A_CMEG, k) = div_z(S(A_CMEG, k) * dzf, dp);
+    S(A_RPRD, k) = div_z(S(A_RPRD, k) * dzf, dp);
+    S(A_EVP, k) = div_z(S(A_EVP, k) * dzf, dp);
   }
   WSYNC();
 
@@ -733,7 +735,7 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
   // mass-flux limiter (zm_conv.F90:1285-1308)
   {
     double mumax = 0.0;                        // max is exact in any order: lane-parallel + shuffle
-    PAR(k, msg + 2, pver) mumax = fmax2(mumax, S(A_MU, k) / S(A_DP, k));
+    PAR(k, msg + 2, pver) mumax = fmax2(mumax, div_z(S(A_MU, k), S(A_DP, k)));
     for (int off = 16; off; off >>= 1) mumax = fmax2(mumax, __shfl_xor_sync(0xffffffffu, mumax, off));
     if (mumax > 0.0) mb = fmin2(mb, 0.5 / (delt * mumax));
     else mb = 0.0;
@@ -746,7 +748,7 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
     S(A_DU, k) = S(A_DU, k) * mb; S(A_EU, k) = S(A_EU, k) * mb; S(A_ED, k) = S(A_ED, k) * mb;
     S(A_CMEG, k) = S(A_CMEG, k) * mb; S(A_RPRD, k) = S(A_RPRD, k) * mb; S(A_CU, k) = S(A_CU, k) * mb;
     S(A_EVP, k) = S(A_EVP, k) * mb;
-    S(A_PFLX, k + 1) = S(A_PFLX, k + 1) * mb * 100.0 / grav;
+    S(A_PFLX, k + 1) = div_z(S(A_PFLX, k + 1) * mb * 100.0, grav);
   }
   WSYNC();
 
@@ -755,10 +757,10 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
     double dsdt = 0.0, dqdt = 0.0, dl = 0.0;
     if (k <= pver - 1) {
       const double emc = -S(A_CU, k) + S(A_EVP, k);
-      dsdt = -rl / cp * emc + (S(A_MU, k + 1) * (S(A_SU, k + 1) - S(A_SHAT, k + 1)) - S(A_MU, k) * (S(A_SU, k) - S(A_SHAT, k)) +
-                               S(A_MD, k + 1) * (S(A_SD, k + 1) - S(A_SHAT, k + 1)) - S(A_MD, k) * (S(A_SD, k) - S(A_SHAT, k))) / S(A_DP, k);
-      dqdt = emc + (S(A_MU, k + 1) * (S(A_QU, k + 1) - S(A_QHAT, k + 1)) - S(A_MU, k) * (S(A_QU, k) - S(A_QHAT, k)) +
-                    S(A_MD, k + 1) * (S(A_QD, k + 1) - S(A_QHAT, k + 1)) - S(A_MD, k) * (S(A_QD, k) - S(A_QHAT, k))) / S(A_DP, k);
+      dsdt = -rl / cp * emc + div_z(S(A_MU, k + 1) * (S(A_SU, k + 1) - S(A_SHAT, k + 1)) - S(A_MU, k) * (S(A_SU, k) - S(A_SHAT, k)) +
+                                    S(A_MD, k + 1) * (S(A_SD, k + 1) - S(A_SHAT, k + 1)) - S(A_MD, k) * (S(A_SD, k) - S(A_SHAT, k)), S(A_DP, k));
+      dqdt = emc + div_z(S(A_MU, k + 1) * (S(A_QU, k + 1) - S(A_QHAT, k + 1)) - S(A_MU, k) * (S(A_QU, k) - S(A_QHAT, k)) +
+                         S(A_MD, k + 1) * (S(A_QD, k + 1) - S(A_QHAT, k + 1)) - S(A_MD, k) * (S(A_QD, k) - S(A_QHAT, k)), S(A_DP, k));
       dl = S(A_DU, k) * S(A_QCDE, k + 1);
     }
     S(A_W1, k) = dsdt; S(A_W2, k) = dqdt; S(A_W3, k) = dl;
@@ -803,7 +805,7 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
     const double qnew = qhk + 2.0 * delt * ((k >= msg + 1) ? S(A_W2, k) : 0.0);
     S(A_W4, k) = dppk * (qnew - qhk);
     S(A_W5, k) = dppk * (dlfk + 0.0) * 2.0 * delt;
-    S(A_W1, k) = (dlfk + 0.0) * dppk / P.gravit;
+    S(A_W1, k) = div_z((dlfk + 0.0) * dppk, P.gravit);
   }
   WSYNC();
   for (int k = pver; k >= msg + 1; --k) prec = prec - S(A_W4, k) - S(A_W5, k);

@@ -50,25 +50,25 @@ k_conv_evap(EvapArgs a) {
     qsat_table(t, pmid, es, qs);
     cldfrc_fice(t, fice, fsnow_conv);
     double flxsntm, snowmlt;
-    if (t > tmelt) { flxsntm = 0.0; snowmlt = flxsnow * gravit / pdel; }
+    if (t > tmelt) { flxsntm = 0.0; snowmlt = div_z(flxsnow * gravit, pdel); }
     else           { flxsntm = flxsnow; snowmlt = 0.0; }
     double evplimit = fmax2(1.0 - q / (1.0 + q) / qs, 0.0);
     // zm_conv.F90:1860-1864
     const double kemask = P.zm_org ? P.ke * (1.0 - a.landfrac[col]) + P.ke_lnd * a.landfrac[col] : P.ke;
-    double evpprec = kemask * (1.0 - cldfrc) * evplimit * sqrt(flxprec);
-    evplimit = fmin2(evplimit, flxprec * gravit / pdel);
-    evplimit = fmin2(evplimit, (prec - evpvint) * gravit / pdel);
+    double evpprec = kemask * (1.0 - cldfrc) * evplimit * sqrt_z(flxprec);
+    evplimit = fmin2(evplimit, div_z(flxprec * gravit, pdel));
+    evplimit = fmin2(evplimit, div_z((prec - evpvint) * gravit, pdel));
     evpprec = fmin2(evplimit, evpprec);
     double evpsnow, work1, work2;
     if (flxprec > 0.0) {
-      work1 = fmin2(fmax2(0.0, flxsntm / flxprec), 1.0);
+      work1 = fmin2(fmax2(0.0, div_z(flxsntm, flxprec)), 1.0);
       evpsnow = evpprec * work1;
     } else {
       evpsnow = 0.0;
     }
-    evpvint = evpvint + evpprec * pdel / gravit;
+    evpvint = evpvint + div_z(evpprec * pdel, gravit);
     const double ntprprd = prdprec - evpprec;
-    if (flxprec > 0.0) work1 = fmin2(fmax2(0.0, flxsnow / flxprec), 1.0);
+    if (flxprec > 0.0) work1 = fmin2(fmax2(0.0, div_z(flxsnow, flxprec)), 1.0);
     else work1 = 0.0;
     work2 = fmax2(fsnow_conv, work1);
     if (snowmlt > 0.0) work2 = 0.0;
@@ -79,8 +79,8 @@ k_conv_evap(EvapArgs a) {
       a.ntprprd[e] = ntprprd;
       a.ntsnprd[e] = ntsnprd;
     }
-    flxprec = flxprec + ntprprd * pdel / gravit;
-    flxsnow = flxsnow + ntsnprd * pdel / gravit;
+    flxprec = flxprec + div_z(ntprprd * pdel, gravit);
+    flxsnow = flxsnow + div_z(ntsnprd * pdel, gravit);
     flxprec = fmax2(flxprec, 0.0);
     flxsnow = fmax2(flxsnow, 0.0);
     a.flxprec[cidx(c, k, i, pverp)] = flxprec;
@@ -88,8 +88,8 @@ k_conv_evap(EvapArgs a) {
     a.tend_s[e] = -evpprec * latvap + ntsnprd * latice;
     a.tend_q[e] = evpprec;
   }
-  a.prec[col] = flxprec / 1000.0;
-  a.snow[col] = flxsnow / 1000.0;
+  a.prec[col] = div_z(flxprec, 1000.0);
+  a.snow[col] = div_z(flxsnow, 1000.0);
 }
 
 // ---- zm_org (organisation tracer) -------------------------------------------------------------
@@ -250,11 +250,11 @@ k_momtran_t(MomArgs a) {
       if (k == 1) {
         pgu = 0.0; pgd = 0.0;
       } else if (k == pver) {
-        pgu = -P.momcu * (mu_k * (c_k - c_km1) / dp_km1);
-        pgd = -P.momcd * (md_k * (c_k - c_km1) / dp_km1);
+        pgu = -P.momcu * div_z(mu_k * (c_k - c_km1), dp_km1);
+        pgd = -P.momcd * div_z(md_k * (c_k - c_km1), dp_km1);
       } else {
-        pgu = -P.momcu * 0.5 * (mu_k * (c_k - c_km1) / dp_km1 + mu_kp1 * (c_kp1 - c_k) / dp_k);
-        pgd = -P.momcd * 0.5 * (md_k * (c_k - c_km1) / dp_km1 + md_kp1 * (c_kp1 - c_k) / dp_k);
+        pgu = -P.momcu * 0.5 * (div_z(mu_k * (c_k - c_km1), dp_km1) + div_z(mu_kp1 * (c_kp1 - c_k), dp_k));
+        pgd = -P.momcd * 0.5 * (div_z(md_k * (c_k - c_km1), dp_km1) + div_z(md_kp1 * (c_kp1 - c_k), dp_k));
       }
       const double chat = 0.5 * (c_k + c_km1);
       SA(M_CHAT + m, k) = chat; SA(M_CONU + m, k) = chat; SA(M_COND + m, k) = chat;
@@ -311,7 +311,7 @@ k_momtran_t(MomArgs a) {
       const double X_p = SA(M_MU, kp1) * (SA(M_CONU + m, kp1) - SA(M_CHAT + m, kp1));
       const double Y_p = SA(M_MD, kp1) * (SA(M_COND + m, kp1) - SA(M_CHAT + m, kp1));
       double dc = 0.0;
-      if (k >= ktm) dc = +(X_p - X_k + Y_p - Y_k) / dp_k;
+      if (k >= ktm) dc = +div_z(X_p - X_k + Y_p - Y_k, dp_k);
       if (k >= kbm && k == mx) dc = (1.0 / dp_k) * (-X_k - Y_k);
       a.dqdt[QI(m, k)] = dc;
       if (a.pguall) {
@@ -328,7 +328,7 @@ k_momtran_t(MomArgs a) {
 #pragma unroll
     for (int m = 0; m < 2; ++m)
       if (a.domom[m])
-        SA(M_WF + m, k) = (k >= ktm) ? SA(M_C + m, k) - (SA(M_MF + m, k + 1) - SA(M_MF + m, k)) * dt / SA(M_DP, k) : 0.0;
+        SA(M_WF + m, k) = (k >= ktm) ? SA(M_C + m, k) - div_z((SA(M_MF + m, k + 1) - SA(M_MF + m, k)) * dt, SA(M_DP, k)) : 0.0;
   }
   __syncwarp();
   // ---- KE dissipation heating (zm_conv.F90:2675-2712) ----
@@ -343,9 +343,9 @@ k_momtran_t(MomArgs a) {
       const double vbot = (SA(M_C + 1, kp1) + v0) / 2.0;
       const double fket = utop * SA(M_MF, k) + vtop * SA(M_MF + 1, k);
       const double fkeb = ubot * SA(M_MF, k + 1) + vbot * SA(M_MF + 1, k + 1);
-      const double ketend_cons = (fket - fkeb) / SA(M_DP, k);
+      const double ketend_cons = div_z(fket - fkeb, SA(M_DP, k));
       const double uf = SA(M_WF, k), vf = SA(M_WF + 1, k);
-      const double ketend = ((uf * uf + vf * vf) - (u0 * u0 + v0 * v0)) * 0.5 / dt;
+      const double ketend = div_z(((uf * uf + vf * vf) - (u0 * u0 + v0 * v0)) * 0.5, dt);
       gset2 = ketend_cons - ketend;
     }
     a.seten[cidx(c, k - 1, ii, pver)] = gset2;

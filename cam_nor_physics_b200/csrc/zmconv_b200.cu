@@ -698,7 +698,7 @@ __global__ void k_state_update(int n2, int nper, const double* t, const double* 
                                double* t1, double* q1, double* winds) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += gridDim.x * blockDim.x) {
     if (PART != 2) {
-      t1[e] = t[e] + heat[e] * ztodt / P.cpair;
+      t1[e] = t[e] + div_z(heat[e] * ztodt, P.cpair);
       double qn = q[e] + qtnd[e] * ztodt;
       q1[e] = (qn < 1.e-12) ? 1.e-12 : qn;
     }
@@ -717,7 +717,7 @@ __global__ void k_tend_finalize(int n2, int n2p, int nper, const double* heat, c
                                 const double* wtend, double* ps, double* pq, double* pu, double* pv,
                                 double* evapcdp, double* mcon) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n2p; e += gridDim.x * blockDim.x) {
-    mcon[e] = mcon[e] * 100.0 / P.gravit;
+    mcon[e] = div_z(mcon[e] * 100.0, P.gravit);
     if (e < n2) {
       pq[e] = qtnd[e] + ev_q[e];
       if (MOM) {
@@ -814,7 +814,7 @@ k_tend_diag(int nchunks, const int* ncol, const double* ps, const double* pmid, 
     const int k = e / pcols, i = e - k * pcols;
     const int g = sh_inv[i];
     double vu = 0.0, vd = 0.0;
-    if (g >= 0) { vu = mu[cidx(c, k, g, pver)] * 100.0 / P.gravit; vd = md[cidx(c, k, g, pver)] * 100.0 / P.gravit; }
+    if (g >= 0) { vu = div_z(mu[cidx(c, k, g, pver)] * 100.0, P.gravit); vd = div_z(md[cidx(c, k, g, pver)] * 100.0, P.gravit); }
     mu_out[(size_t)c * pcols * pver + e] = vu;
     md_out[(size_t)c * pcols * pver + e] = vd;
   }
