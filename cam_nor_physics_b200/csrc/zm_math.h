@@ -40,6 +40,8 @@ static const double h_log_tab[384] = ZMM_LOG_TAB_VALUES;
 static const double h_exp2_tab[256] = ZMM_EXP2_TAB_VALUES;
 static const double h_svp_tab[ZMM_SVP_NCELL * ZMM_SVP_NCOEF] = ZMM_SVP_TAB_VALUES;
 
+// static shared memory of a kernel that calls hot_tables_load() and hot_svp_load()
+#define ZMM_HOT_SMEM_BYTES (128 * 16 + 128 * 8 + 128 * 16 + ZMM_SVP_NCELL * ZMM_SVP_NCOEF * 8)
 #if defined(__CUDACC__)
 // Shared-memory copies used by the *_hot variants (one LDS.128 per entry instead of __ldg loads that each
 // need a descriptor in uniform registers).  A kernel that calls a *_hot function must call
@@ -290,7 +292,12 @@ __device__ __noinline__ double svp_water_formula_cold(double t) { return svp_wat
 // The same function from the per-kelvin polynomials of zm_svp_table.h (scripts/gen_svp_table.py): for
 // ZMM_SVP_T0 - 0.5 <= t < ZMM_SVP_T0 + ZMM_SVP_NCELL - 0.5 one table cell and 12 multiply-adds (the formula costs
 // three 10**x, one log10 and two divisions, and in double it carries +-2 ulp from the rounding of its exponent
-// alone, tens of ulp below 200 K); < 2 ulp against the formula in 300-bit arithmetic; outside the table the formula.
+// alone, tens of ulp below 200 K); < 2 ulp against the formula in 300-bit arithmetic from 139.5 K up; outside the
+// table the formula.  The cells below 140 K exist for the parcels of cold, dry columns, which the CAPE sweep lifts
+// to 40 hPa along a dry adiabat (100-140 K; one lane there used to send its whole warp through the formula): the
+// formula collapses super-exponentially down there (es(120 K) = 9e-17 Pa, es(100 K) = 3e-42 Pa), the degree-9 cells
+// follow it to 3e-13 relative at 125 K, 1e-11 at 120 K, 4e-5 at 100 K -- an absolute error below 1e-23 Pa (one ulp at 139 K)
+// everywhere, 1e-28 of any pressure the path sees: no term of the state function can resolve it.
 // The cell is the integer nearest to t: t + 1.5*2^52 rounds t to that integer and leaves it in the low word of
 // the sum (no float<->int conversion on the dependency chain); x = t - centre is exact, |x| <= 0.5.
 // HOT = true reads the table from shared memory (hot_svp_load()).

@@ -402,7 +402,7 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
     return sms;
   }();
   // resident blocks per SM: 6 by registers, fewer when the buoyancy rows of a deep grid fill the shared memory
-  const size_t ws_block_smem = (size_t)(pver + 2) * 32 * sizeof(double) + 64 * sizeof(int) + 22 * 1024 + 1024;
+  const size_t ws_block_smem = (size_t)(pver + 2) * 32 * sizeof(double) + 64 * sizeof(int) + ZMM_HOT_SMEM_BYTES + 1024;
   const int ws_bps = (int)std::min<size_t>(6, (227 * 1024) / ws_block_smem);
   w.ws_gate = ws_env ? ws_bps * 32 * ws_sms : -1;
   ws.last_count = w.count; ws.last_err = w.errinfo;
@@ -422,7 +422,7 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   auto k_plm = pl_ld == 34 ? k_plume_w<34> : (pl_ld == 66 ? k_plume_w<66> : k_plume_w<130>);
   CK(cudaFuncSetAttribute(k_cld1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
   CK(cudaFuncSetAttribute(k_plm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
-  {   // static tables (22 KB) + the buoyancy rows exceed the 48 KB default: opt in (dynamic part)
+  {   // static tables (ZMM_HOT_SMEM_BYTES, 26 KB) + the buoyancy rows exceed the 48 KB default: opt in (dynamic part)
     CK(cudaFuncSetAttribute(k_buoyan_dilute<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute((k_buoyan_dilute<1, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_buoyan_dilute<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -432,7 +432,7 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   }
   const int nblk_ws = (int)((ncolpad + 31) / 32);
   const size_t smem_ws = (size_t)(pver + 2) * 32 * sizeof(double) + 64 * sizeof(int);
-  if (smem_ws + 22 * 1024 > 48 * 1024) {
+  if (smem_ws + ZMM_HOT_SMEM_BYTES > 48 * 1024) {
     CK(cudaFuncSetAttribute((k_buoyan_dilute_ws<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
     CK(cudaFuncSetAttribute((k_buoyan_dilute_ws<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
     CK(cudaFuncSetAttribute((k_buoyan_dilute_ws<2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));

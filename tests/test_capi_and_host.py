@@ -101,9 +101,23 @@ def test_saturation_vapour_pressure_table_host(built):
     assert np.max(np.abs(tab - frm) / frm) < 2e-14
     warm = T > 200.0
     assert np.max(np.abs(tab - frm)[warm] / frm[warm]) < 8e-15
-    out = np.array([100.0, 139.499, 349.5, 360.0, 420.0])
+    out = np.array([60.0, 89.499, 349.5, 360.0, 420.0])
     assert np.array_equal(Z.math_eval(10, out, device=False), Z.math_eval(11, out, device=False))
     assert np.all(np.diff(Z.math_eval(10, np.linspace(139.0, 350.5, 40001), device=False)) > 0)   # monotone across cells
+    # the cells below 140 K (parcels of cold columns lifted to 40 hPa) follow a function that collapses
+    # super-exponentially: relative accuracy degrades (3e-13 at 125 K, 4e-5 at 100 K), the absolute error stays
+    # below 1e-23 Pa (an ulp at 139 K) -- nothing the state function can resolve against pressures of 4e3 Pa and more
+    cold = np.concatenate([rng.uniform(89.5, 139.5, 1500), np.arange(90, 140) + 0.5, np.arange(90, 140).astype(float)])
+    tabc, frmc = Z.math_eval(10, cold, device=False), Z.math_eval(11, cold, device=False)
+    exact = np.array([float(svp(mp.mpf(float(t)))) for t in cold])
+    assert np.all(tabc > 0) and np.max(np.abs(tabc - exact)) < 1e-23
+    assert np.max(np.abs(tabc - frmc)) < 1e-21          # the formula in double is itself 1e-14 relative off here
+    near = cold >= 125.0
+    assert np.max(np.abs(tabc - exact)[near] / exact[near]) < 1e-12
+    assert np.all(np.diff(Z.math_eval(10, np.linspace(95.0, 139.6, 20001), device=False)) > 0)
+    # below 95 K (es < 1e-50 Pa) neighbouring cells meet with steps of the size of their own error
+    low = Z.math_eval(10, np.linspace(89.6, 95.0, 5001), device=False)
+    assert np.all(low > 0) and np.min(np.diff(low)) > -1e-50
 
 
 def test_hot_math_variants_equal_general_ones_host(built):
