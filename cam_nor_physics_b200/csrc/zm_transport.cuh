@@ -784,6 +784,52 @@ k_geopotential_t(GeoArgs a) {
   }
 }
 
+// geopotential_t, generalized-virtual-temperature branch (physics/geopotential.F90:248-310; dycore MPAS / SE):
+// thread per column; q3 is the chunk's q(pcols,pver,ncnst), species[] the 1-based indices of the thermodynamically
+// active species.  The two species loops of the reference (wet-to-dry factor, sum of dry mixing ratios) run per
+// level in the reference's order; the level's species values are read twice (L1-resident: the sweep is HBM-bound).
+struct GeoGenArgs {
+  int nchunks, dycore_lr, ncnst, nspecies;
+  const int *ncol, *species;
+  const double *piln, *pint, *pmid, *pdel, *rpdel, *t, *q3, *rair, *zvir;
+  double gravit;
+  double *zi, *zm;
+};
+__global__ void __launch_bounds__(128)
+k_geopotential_t_gen(GeoGenArgs a) {
+  const int pcols = P.pcols, pver = P.pver, pverp = P.pverp;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= a.nchunks * pcols) return;
+  const int c = col / pcols, i = col - c * pcols;
+  if (i >= a.ncol[c]) return;
+  const double* qc = a.q3 + (size_t)c * a.ncnst * pver * pcols + i;      // + (m*pver + k)*pcols
+  double zi_p = 0.0;
+  a.zi[cidx(c, pverp - 1, i, pverp)] = 0.0;
+  for (int k = pver; k >= 1; --k) {
+    const size_t e = cidx(c, k - 1, i, pver);
+    double qfac = 1.0;
+    for (int s = 0; s < a.nspecies; ++s) qfac = qfac - qc[((size_t)(a.species[s] - 1) * pver + (k - 1)) * pcols];
+    qfac = 1.0 / qfac;
+    double sdm = 1.0;
+    for (int s = 0; s < a.nspecies; ++s) sdm = sdm + qc[((size_t)(a.species[s] - 1) * pver + (k - 1)) * pcols] * qfac;
+    sdm = 1.0 / sdm;
+    double hkl, hkk;
+    if (a.dycore_lr) {
+      hkl = a.piln[cidx(c, k, i, pverp)] - a.piln[cidx(c, k - 1, i, pverp)];
+      hkk = 1.0 - a.pint[cidx(c, k - 1, i, pverp)] * hkl * a.rpdel[e];
+    } else {
+      hkl = a.pdel[e] / a.pmid[e];
+      hkk = 0.5 * hkl;
+    }
+    const double rog = a.rair[e] / a.gravit;
+    const double tvfac = (1.0 + (a.zvir[e] + 1.0) * qc[(size_t)(k - 1) * pcols] * qfac) * sdm;
+    const double tv = a.t[e] * tvfac;
+    a.zm[e] = zi_p + rog * tv * hkk;
+    zi_p = zi_p + rog * tv * hkl;
+    a.zi[cidx(c, k - 1, i, pverp)] = zi_p;
+  }
+}
+
 // convect_diagnostics_calc for shallow_scheme == 'CLUBB_SGS' (physics/convect_diagnostics.F90:115-249)
 struct CdiagArgs {
   int nchunks;

@@ -2137,6 +2137,54 @@ int zm_geopotential_t_batch(int nchunks, const int* ncol, int dycore_lr, const d
   return S.flush();
 }
 
+// generalized-virtual-temperature branch (physics/geopotential.F90:248-310)
+int zm_geopotential_t_gen_batch_dev(int nchunks, const int* ncol, int dycore_lr, int ncnst, int nspecies,
+                                    const int* species_idx, const double* piln, const double* pmln,
+                                    const double* pint, const double* pmid, const double* pdel, const double* rpdel,
+                                    const double* t, const double* q3, const double* rair, double gravit,
+                                    const double* zvir, double* zi, double* zm, void* stream) {
+  NEED_INIT();
+  (void)pmln;
+  if (nchunks <= 0) return 0;
+  if (ncnst < 1 || nspecies < 0) { tls_err = "geopotential_t: ncnst >= 1 and nspecies >= 0 required"; return -2; }
+  GeoGenArgs a{nchunks, dycore_lr, ncnst, nspecies, ncol, species_idx, piln, pint, pmid, pdel, rpdel, t, q3, rair, zvir,
+               gravit, zi, zm};
+  const int ncolpad = nchunks * g_params.pcols;
+  k_geopotential_t_gen<<<(ncolpad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a); ++tls_launches;
+  CK(cudaGetLastError());
+  return 0;
+}
+int zm_geopotential_t_gen_batch(int nchunks, const int* ncol, int dycore_lr, int ncnst, int nspecies,
+                                const int* species_idx, const double* piln, const double* pmln, const double* pint,
+                                const double* pmid, const double* pdel, const double* rpdel, const double* t,
+                                const double* q3, const double* rair, double gravit, const double* zvir, double* zi,
+                                double* zm) {
+  NEED_INIT();
+  if (nchunks <= 0) return 0;
+  if (ncnst < 1 || nspecies < 0) { tls_err = "geopotential_t: ncnst >= 1 and nspecies >= 0 required"; return -2; }
+  for (int s = 0; s < nspecies; ++s)
+    if (species_idx[s] < 1 || species_idx[s] > ncnst) {
+      tls_err = "geopotential_t: thermodynamic_active_species_idx outside 1..ncnst";
+      return -2;
+    }
+  const size_t pc = g_params.pcols, L = g_params.pver, nc = (size_t)nchunks * pc, n2 = nc * L, n2p = nc * (L + 1);
+  Workspace& st = tls_stage;
+  if (st.ensure(al(nchunks, 4) + al((size_t)nspecies + 1, 4) + 7 * al(n2, 8) + al(n2 * ncnst, 8) + 3 * al(n2p, 8) + 4096))
+    return -100;
+  Stager S(st);
+  const int* d_ncol = S.in(ncol, nchunks);
+  const int* d_sp = nspecies ? S.in(species_idx, (size_t)nspecies) : nullptr;
+  const double *d_piln = S.in(piln, n2p), *d_pint = S.in(pint, n2p), *d_pmid = S.in(pmid, n2), *d_pdel = S.in(pdel, n2),
+               *d_rpdel = S.in(rpdel, n2), *d_t = S.in(t, n2), *d_q3 = S.in(q3, n2 * ncnst), *d_rair = S.in(rair, n2),
+               *d_zvir = S.in(zvir, n2);
+  double *d_zi = S.inout(zi, n2p), *d_zm = S.inout(zm, n2);
+  int rc = zm_geopotential_t_gen_batch_dev(nchunks, d_ncol, dycore_lr, ncnst, nspecies, d_sp, d_piln, nullptr, d_pint,
+                                           d_pmid, d_pdel, d_rpdel, d_t, d_q3, d_rair, gravit, d_zvir, d_zi, d_zm,
+                                           (void*)st.stream);
+  if (rc) return rc;
+  return S.flush();
+}
+
 int zm_convect_diagnostics_batch_dev(int nchunks, const int* ncol, double* cmfmc, double* qc, double* qc2,
                                      double* rliq, double* rliq2, const double* pmid, const double* rprddp,
                                      double* cnt, double* cnb, double* cmfmc2, double* rprdsh, double* rprdtot,

@@ -72,7 +72,8 @@ EXPORTS = [
     "zm_convr_batch_dev", "zm_conv_evap_batch", "zm_conv_evap_batch_dev", "zm_momtran_batch",
     "zm_momtran_batch_dev", "zm_convtran_batch", "zm_convtran_batch_dev", "zm_sync_check",
     "zm_conv_tend_batch", "zm_conv_tend_batch_dev", "zm_microbench", "zm_conservation_dev",
-    "zm_conv_tend_2_batch", "zm_tend_trace", "zm_org_fields", "zm_geopotential_t_batch", "zm_geopotential_t_batch_dev", "zm_convect_diagnostics_batch",
+    "zm_conv_tend_2_batch", "zm_tend_trace", "zm_org_fields", "zm_geopotential_t_batch", "zm_geopotential_t_batch_dev",
+    "zm_geopotential_t_gen_batch", "zm_geopotential_t_gen_batch_dev", "zm_convect_diagnostics_batch",
     "zm_convect_diagnostics_batch_dev",
     "zm_math_eval_dev", "zm_math_eval_host", "zm_thermo_eval_dev", "zm_fp64_peak_flops",
     "zm_set_profiling", "zm_get_kernel_times", "zm_launch_count",
@@ -356,6 +357,24 @@ def geopotential_t(ncol, piln, pmln, pint, pmid, pdel, rpdel, t, q, rair, gravit
     rc = lib().zm_geopotential_t_batch(C.c_int(nch), _ip(ncol), C.c_int(int(dycore_lr)), _dp(piln), _dp(pmln),
                                        _dp(pint), _dp(pmid), _dp(pdel), _dp(rpdel), _dp(t), _dp(q), _dp(rair),
                                        C.c_double(gravit), _dp(zvir), _dp(zi), _dp(zm))
+    _check(rc, "geopotential_t")
+    return zi, zm
+
+
+def geopotential_t_gen(ncol, piln, pmln, pint, pmid, pdel, rpdel, t, q3, rair, gravit, zvir, species_idx,
+                       dycore_lr=False):
+    """geopotential_t, generalized-virtual-temperature branch (physics/geopotential.F90:248-310; dycore MPAS / SE).
+    q3: (nchunks, ncnst, pver, pcols); species_idx: 1-based thermodynamic_active_species_idx.  Returns (zi, zm)."""
+    pc, L = _grid()
+    ncol = _i(ncol)
+    nch = ncol.shape[0]
+    zi, zm = np.zeros((nch, L + 1, pc)), np.zeros((nch, L, pc))
+    piln, pmln, pint, pmid, pdel, rpdel, t, q3, rair, zvir = map(_f, (piln, pmln, pint, pmid, pdel, rpdel, t, q3, rair, zvir))
+    sp = _i(species_idx)
+    rc = lib().zm_geopotential_t_gen_batch(C.c_int(nch), _ip(ncol), C.c_int(int(dycore_lr)), C.c_int(q3.shape[1]),
+                                           C.c_int(sp.shape[0]), _ip(sp), _dp(piln), _dp(pmln), _dp(pint), _dp(pmid),
+                                           _dp(pdel), _dp(rpdel), _dp(t), _dp(q3), _dp(rair), C.c_double(gravit),
+                                           _dp(zvir), _dp(zi), _dp(zm))
     _check(rc, "geopotential_t")
     return zi, zm
 

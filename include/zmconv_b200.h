@@ -183,7 +183,8 @@ int zm_conservation_dev(int nchunks, const int* ncol, const double* pdel, const 
 /* ---- "next" rows: neighbours of the path --------------------------------
  * geopotential_t (physics/geopotential.F90:153-247): zm/zi from t,q,p; dycore_lr != 0 selects the FV
  * ('LR') hydrostatic branch (:218-223), 0 the EUL/SE one (:224-233).  q is q(:,:,1); rair/zvir are
- * (pcols,pver) like the reference's dummy arrays.  The generalized-Tv branch (:248-310) is not built. */
+ * (pcols,pver) like the reference's dummy arrays.  The generalized-Tv branch (:248-310) is
+ * zm_geopotential_t_gen_batch below. */
 int zm_geopotential_t_batch(int nchunks, const int* ncol, int dycore_lr, const double* piln, const double* pmln,
                             const double* pint, const double* pmid, const double* pdel, const double* rpdel,
                             const double* t, const double* q, const double* rair, double gravit,
@@ -192,6 +193,22 @@ int zm_geopotential_t_batch_dev(int nchunks, const int* ncol, int dycore_lr, con
                             const double* pmln, const double* pint, const double* pmid, const double* pdel,
                             const double* rpdel, const double* t, const double* q, const double* rair,
                             double gravit, const double* zvir, double* zi, double* zm, void* stream);
+/* geopotential_t, generalized-virtual-temperature branch (physics/geopotential.F90:248-310), the one the reference
+ * takes when dycore_is('MPAS') or dycore_is('SE'): tvfac = (1 + (zvir+1)*q(:,:,1)*qfac) * 1/(1 + sum q_s*qfac) with
+ * qfac = 1/(1 - sum q_s) over the thermodynamically active species.  q3 is the constituent array q(pcols,pver,ncnst)
+ * of each chunk ([chunk][m][k][i]); species_idx[nspecies] are the 1-based constituent indices of
+ * air_composition::thermodynamic_active_species_idx (that module is not in the reference tree, hence an argument;
+ * a host array for the host-pointer call, a device array for the _dev call).  dycore_lr as above (:283-298). */
+int zm_geopotential_t_gen_batch(int nchunks, const int* ncol, int dycore_lr, int ncnst, int nspecies,
+                            const int* species_idx, const double* piln, const double* pmln, const double* pint,
+                            const double* pmid, const double* pdel, const double* rpdel, const double* t,
+                            const double* q3, const double* rair, double gravit, const double* zvir, double* zi,
+                            double* zm);
+int zm_geopotential_t_gen_batch_dev(int nchunks, const int* ncol, int dycore_lr, int ncnst, int nspecies,
+                            const int* species_idx, const double* piln, const double* pmln, const double* pint,
+                            const double* pmid, const double* pdel, const double* rpdel, const double* t,
+                            const double* q3, const double* rair, double gravit, const double* zvir, double* zi,
+                            double* zm, void* stream);
 /* convect_diagnostics_calc (physics/convect_diagnostics.F90:115-249) for shallow_scheme='CLUBB_SGS', the
  * only configuration in which its locals cnt2/cnb2 are defined (:187-198): zeroes the shallow-scheme
  * fields, merges them into cmfmc/qc/rliq, merges cloud top/bottom indices and looks up their pressures,

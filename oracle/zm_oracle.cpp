@@ -2238,7 +2238,7 @@ int zmo_conv_tend_batch(int nchunks, const int* ncol, const double* t, const dou
 
 // ---- "next" rows N4: neighbours of the path with source in the reference ----
 // geopotential_t, FV ('LR') and EUL/SE hydrostatic branches of physics/geopotential.F90:153-247
-// (the generalized-virtual-temperature branch :248-310 belongs to SE/MPAS thermodynamics: not restated).
+// (the generalized-virtual-temperature branch :248-310 is zmo_geopotential_t_gen below).
 void zmo_geopotential_t(int ncol, int dycore_lr, const double* piln_, const double* pmln_, const double* pint_,
                         const double* pmid_, const double* pdel_, const double* rpdel_, const double* t_,
                         const double* q_, const double* rair_, double gravit, const double* zvir_, double* zi_,
@@ -2266,6 +2266,58 @@ void zmo_geopotential_t(int ncol, int dycore_lr, const double* piln_, const doub
     }
     for (int i = 1; i <= ncol; ++i) {
       double tvfac = 1.0 + zvir(i, k) * q(i, k);
+      double tv = t(i, k) * tvfac;
+      zm(i, k) = zi(i, k + 1) + rog(i, k) * tv * hkk[i];
+      zi(i, k) = zi(i, k + 1) + rog(i, k) * tv * hkl[i];
+    }
+  }
+}
+
+// geopotential_t, generalized-virtual-temperature branch (physics/geopotential.F90:248-310), taken when
+// dycore_is('MPAS') or dycore_is('SE'): q3 is q(pcols,pver,ncnst), species_idx the 1-based constituent indices of
+// air_composition::thermodynamic_active_species_idx (the module is not in the reference tree: an input here).
+void zmo_geopotential_t_gen(int ncol, int dycore_lr, int ncnst, int nspecies, const int* species_idx,
+                            const double* piln_, const double* pmln_, const double* pint_, const double* pmid_,
+                            const double* pdel_, const double* rpdel_, const double* t_, const double* q3_,
+                            const double* rair_, double gravit, const double* zvir_, double* zi_, double* zm_) {
+  (void)pmln_; (void)ncnst;
+  const int pcols = g.pcols, pver = g.pver, pverp = g.pverp;
+  C2 piln{piln_, pcols}, pint{pint_, pcols}, pmid{pmid_, pcols}, pdel{pdel_, pcols}, rpdel{rpdel_, pcols},
+      t{t_, pcols}, rair{rair_, pcols}, zvir{zvir_, pcols};
+  auto q = [&](int i, int k, int m) { return q3_[((size_t)(m - 1) * pver + (k - 1)) * pcols + (i - 1)]; };
+  A2 zi{zi_, pcols}, zm{zm_, pcols};
+  std::vector<double> hkk(ncol + 1), hkl(ncol + 1);
+  W2 rog(pcols, pver), qfac(pcols, pver), sum_dry_mixing_ratio(pcols, pver);
+  for (int k = 1; k <= pver; ++k) for (int i = 1; i <= ncol; ++i) rog(i, k) = rair(i, k) / gravit;
+  for (int i = 1; i <= ncol; ++i) zi(i, pverp) = 0.0;
+  // factor converting wet to dry mixing ratio (:255-263)
+  for (int k = 1; k <= pver; ++k) for (int i = 1; i <= ncol; ++i) qfac(i, k) = 1.0;
+  for (int idx = 1; idx <= nspecies; ++idx)
+    for (int k = 1; k <= pver; ++k)
+      for (int i = 1; i <= ncol; ++i) qfac(i, k) = qfac(i, k) - q(i, k, species_idx[idx - 1]);
+  for (int k = 1; k <= pver; ++k) for (int i = 1; i <= ncol; ++i) qfac(i, k) = 1.0 / qfac(i, k);
+  // sum of dry water mixing ratios (:265-275)
+  for (int k = 1; k <= pver; ++k) for (int i = 1; i <= ncol; ++i) sum_dry_mixing_ratio(i, k) = 1.0;
+  for (int idx = 1; idx <= nspecies; ++idx)
+    for (int k = 1; k <= pver; ++k)
+      for (int i = 1; i <= ncol; ++i)
+        sum_dry_mixing_ratio(i, k) = sum_dry_mixing_ratio(i, k) + q(i, k, species_idx[idx - 1]) * qfac(i, k);
+  for (int k = 1; k <= pver; ++k)
+    for (int i = 1; i <= ncol; ++i) sum_dry_mixing_ratio(i, k) = 1.0 / sum_dry_mixing_ratio(i, k);
+  for (int k = pver; k >= 1; --k) {
+    if (dycore_lr) {
+      for (int i = 1; i <= ncol; ++i) {
+        hkl[i] = piln(i, k + 1) - piln(i, k);
+        hkk[i] = 1.0 - pint(i, k) * hkl[i] * rpdel(i, k);
+      }
+    } else {
+      for (int i = 1; i <= ncol; ++i) {
+        hkl[i] = pdel(i, k) / pmid(i, k);
+        hkk[i] = 0.5 * hkl[i];
+      }
+    }
+    for (int i = 1; i <= ncol; ++i) {
+      double tvfac = (1.0 + (zvir(i, k) + 1.0) * q(i, k, 1) * qfac(i, k)) * sum_dry_mixing_ratio(i, k);   // :303
       double tv = t(i, k) * tvfac;
       zm(i, k) = zi(i, k + 1) + rog(i, k) * tv * hkk[i];
       zi(i, k) = zi(i, k + 1) + rog(i, k) * tv * hkl[i];

@@ -157,6 +157,12 @@ void zmo_geopotential_t(int ncol, int dycore_lr, const double* piln, const doubl
                         const double* pmid, const double* pdel, const double* rpdel, const double* t,
                         const double* q, const double* rair, double gravit, const double* zvir, double* zi,
                         double* zm);
+/* geopotential_t, generalized-virtual-temperature branch (geopotential.F90:248-310; dycore MPAS / SE): q3 is
+ * q(pcols,pver,ncnst), species_idx[nspecies] the 1-based thermodynamic_active_species_idx. */
+void zmo_geopotential_t_gen(int ncol, int dycore_lr, int ncnst, int nspecies, const int* species_idx,
+                            const double* piln, const double* pmln, const double* pint, const double* pmid,
+                            const double* pdel, const double* rpdel, const double* t, const double* q3,
+                            const double* rair, double gravit, const double* zvir, double* zi, double* zm);
 void zmo_convect_diagnostics(int ncol, double* cmfmc, double* qc, double* qc2, double* rliq, double* rliq2,
                              const double* pmid, const double* rprddp, double* cnt, double* cnb,
                              double* cmfmc2, double* rprdsh, double* rprdtot, double* pcnt, double* pcnb);

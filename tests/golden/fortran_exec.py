@@ -72,6 +72,27 @@ class FArr:
     def setall(self, val):
         self.a[...] = val.a if isinstance(val, FArr) else val
 
+    # whole-array operands of elementwise expressions (`qfac = 1.0_r8/qfac`, geopotential.F90:263): the result is
+    # the numpy array of the elementwise IEEE operation, assigned back through setall()
+    @staticmethod
+    def _v(x):
+        return x.a if isinstance(x, FArr) else x
+
+    def __add__(self, o): return self.a + FArr._v(o)
+    def __radd__(self, o): return FArr._v(o) + self.a
+    def __sub__(self, o): return self.a - FArr._v(o)
+    def __rsub__(self, o): return FArr._v(o) - self.a
+    def __mul__(self, o): return self.a * FArr._v(o)
+    def __rmul__(self, o): return FArr._v(o) * self.a
+
+    def __truediv__(self, o):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return self.a / FArr._v(o)
+
+    def __rtruediv__(self, o):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return FArr._v(o) / self.a
+
 
 def _ipow(x, n):
     """x**n for a literal integer n the way GCC's powi expansion does it (square and multiply, left to right)."""

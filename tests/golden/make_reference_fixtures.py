@@ -308,6 +308,47 @@ def run_geopotential():
     print("geopotential_t -> %s (%d KB)" % (os.path.basename(path), os.path.getsize(path) // 1024))
 
 
+def run_geopotential_gen():
+    """geopotential_t, generalized-virtual-temperature branch (physics/geopotential.F90:248-310): dycore 'SE' (EUL-type
+    hydrostatic elements) and, for the inner LR test of the same branch (:283-287), a dycore that answers true to
+    both 'SE' and 'LR'.  thermodynamic_active_species_num / _idx come from air_composition, which is not in the
+    reference tree: supplied here (water vapour + two condensates out of five constituents)."""
+    pcols, L, ncnst = 16, 32, 5
+    species = np.array([1, 2, 4], np.int32)
+    F.FArr.UNDEFINED = np.nan
+    ch = S.make_chunks(13, L, pcols, p_conv=0.5, col0=7000)
+    c = physconst()
+    fx = {}
+    pint, pmid, pdel, t, q = (np.ascontiguousarray(getattr(ch, k)[0]) for k in ("pint", "pmid", "pdel", "t", "q"))
+    rng = np.random.default_rng(20261019)
+    q3 = np.zeros((ncnst, L, pcols))
+    q3[0] = q
+    q3[1] = 2e-4 * rng.random((L, pcols)) * (pmid > 4e4)           # cloud liquid
+    q3[2] = 1e-6 * rng.random((L, pcols))                           # not thermodynamically active
+    q3[3] = 1e-4 * rng.random((L, pcols)) * (pmid < 6e4)           # cloud ice
+    q3[4] = 1e-9 * rng.random((L, pcols))
+    for lr in (0, 1):
+        names = ("SE", "LR") if lr else ("SE",)
+        sp = F.FArr((len(species),), data=species.astype(np.int64)) if hasattr(F, "FArr") else species
+        m = F.Module("/root/reference/physics/geopotential.F90",
+                     dict(pcols=pcols, pver=L, pverp=L + 1, dycore_is=(lambda s, names=names: s in names),
+                          thermodynamic_active_species_num=len(species), thermodynamic_active_species_idx=sp),
+                     lenient=True)
+        m.load("geopotential_t")
+        piln, pmln, rpdel = np.log(pint), np.log(pmid), 1.0 / pdel
+        rair = np.full((L, pcols), c["rair"]); zvir = np.full((L, pcols), c["zvir"])
+        zi, zm = np.zeros((L + 1, pcols)), np.zeros((L, pcols))
+        m.ns["geopotential_t"](FA(piln), FA(pmln), FA(pint), FA(pmid), FA(pdel), FA(rpdel), FA(t),
+                               F.FArr(q3.T.shape, data=np.ascontiguousarray(q3.T)), FA(rair), c["gravit"], FA(zvir),
+                               FA(zi), FA(zm), 13)
+        fx.update({"in_piln": piln, "in_pint": pint, "in_pmid": pmid, "in_pdel": pdel, "in_rpdel": rpdel, "in_t": t,
+                   "in_q3": q3, "in_rair": rair, "in_zvir": zvir, "gravit": np.asarray(c["gravit"]), "ncol": np.asarray(13),
+                   "species_idx": species, "zi_lr%d" % lr: zi, "zm_lr%d" % lr: zm})
+    path = os.path.join(HERE, "reftext_geopotential_t_gen.npz")
+    np.savez_compressed(path, **fx)
+    print("geopotential_t (generalized Tv) -> %s (%d KB)" % (os.path.basename(path), os.path.getsize(path) // 1024))
+
+
 def run_convect_diagnostics():
     """convect_diagnostics_calc (physics/convect_diagnostics.F90:115-249), shallow_scheme = 'CLUBB_SGS'.
     The physics buffer is a dict of FArr; pbuf_get_field / pbuf_set_field are two-line shims."""
@@ -480,6 +521,8 @@ if __name__ == "__main__":
         run_case(**cs)
     if not only or "geopotential_t" in only:
         run_geopotential()
+    if not only or "geopotential_t_gen" in only:
+        run_geopotential_gen()
     if not only or "convect_diagnostics" in only:
         run_convect_diagnostics()
     if not only or "sweep" in only:

@@ -283,6 +283,19 @@ class Oracle:
                                     _dp(_f(rair)), C.c_double(gravit), _dp(_f(zvir)), _dp(zi), _dp(zm))
         return zi, zm
 
+    def geopotential_t_gen(self, ncol, dycore_lr, piln, pint, pmid, pdel, rpdel, t, q3, rair, gravit, zvir, species_idx):
+        """generalized-Tv branch (geopotential.F90:248-310); q3: (ncnst, pver, pcols), species_idx 1-based."""
+        P = self.params
+        L, pc = P.pver, P.pcols
+        zi, zm = np.zeros((L + 1, pc)), np.zeros((L, pc))
+        q3 = _f(q3)
+        sp = np.ascontiguousarray(species_idx, dtype=np.int32)
+        self.lib.zmo_geopotential_t_gen(C.c_int(ncol), C.c_int(int(dycore_lr)), C.c_int(q3.shape[0]), C.c_int(sp.shape[0]),
+                                        _ip(sp), _dp(_f(piln)), None, _dp(_f(pint)), _dp(_f(pmid)), _dp(_f(pdel)),
+                                        _dp(_f(rpdel)), _dp(_f(t)), _dp(q3), _dp(_f(rair)), C.c_double(gravit),
+                                        _dp(_f(zvir)), _dp(zi), _dp(zm))
+        return zi, zm
+
     def convect_diagnostics(self, ncol, cmfmc, qc, rliq, pmid, rprddp, cnt, cnb):
         P = self.params
         L, pc = P.pver, P.pcols

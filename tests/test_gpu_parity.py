@@ -393,6 +393,42 @@ def test_next_rows_geopotential_and_convect_diagnostics(built):
     assert np.all(out["cnb"][ch.ncol[:, None] > np.arange(16)[None, :]] >= 1)
 
 
+def test_geopotential_t_generalized_tv(built):
+    """geopotential_t, generalized-virtual-temperature branch (physics/geopotential.F90:248-310): bit-exact
+    against the oracle on 1000 columns x 7 constituents, both hydrostatic variants, several species lists (incl. none);
+    equal to the reference text's own output on the committed fixture; bad species indices are refused."""
+    Z = init_cuda(16, 32)
+    o, _, _ = get_oracle("pm", 16, 32)
+    ch = S.make_chunks(1000, 32, 16, p_conv=0.5)
+    zvir = np.full_like(ch.t, S.ZVIR); rair = np.full_like(ch.t, S.RAIR)
+    piln, rpdel = np.log(ch.pint), 1.0 / ch.pdel
+    rng = np.random.default_rng(7)
+    ncnst = 7
+    q3 = 1e-4 * rng.random((ch.nchunks, ncnst, 32, 16))
+    q3[:, 0] = ch.q
+    for species in ([1, 2, 3], [1], [1, 6, 2, 7, 4], []):
+        sp = np.array(species, np.int32)
+        for lr in (False, True):
+            zi, zm = Z.geopotential_t_gen(ch.ncol, piln, np.log(ch.pmid), ch.pint, ch.pmid, ch.pdel, rpdel, ch.t, q3, rair,
+                                          S.GRAVIT, zvir, sp, dycore_lr=lr)
+            for c in range(0, ch.nchunks, 3):
+                n = int(ch.ncol[c])
+                rzi, rzm = o.geopotential_t_gen(n, lr, piln[c], ch.pint[c], ch.pmid[c], ch.pdel[c], rpdel[c], ch.t[c],
+                                                q3[c], rair[c], S.GRAVIT, zvir[c], sp)
+                assert np.array_equal(zi[c][:, :n], rzi[:, :n]) and np.array_equal(zm[c][:, :n], rzm[:, :n]), (species, lr, c)
+    g = np.load(os.path.join(GOLD, "reftext_geopotential_t_gen.npz"))
+    n = int(g["ncol"])
+    one = lambda k: g[k][None]
+    for lr in (0, 1):
+        zi, zm = Z.geopotential_t_gen(np.array([n], np.int32), one("in_piln"), np.log(one("in_pmid")), one("in_pint"),
+                                      one("in_pmid"), one("in_pdel"), one("in_rpdel"), one("in_t"), one("in_q3"),
+                                      one("in_rair"), float(g["gravit"]), one("in_zvir"), g["species_idx"], dycore_lr=lr)
+        assert np.array_equal(zi[0][:, :n], g["zi_lr%d" % lr][:, :n]) and np.array_equal(zm[0][:, :n], g["zm_lr%d" % lr][:, :n])
+    with pytest.raises(Z.ZmError):
+        Z.geopotential_t_gen(ch.ncol, piln, np.log(ch.pmid), ch.pint, ch.pmid, ch.pdel, rpdel, ch.t, q3, rair, S.GRAVIT, zvir,
+                             np.array([1, ncnst + 1], np.int32))
+
+
 def test_conv_tend_2_uses_device_mirror(built):
     """zm_conv_tend with the pbuf fields kept on the device, then zm_conv_tend_2 (convtran2,
     zm_conv_intr.F90:955-1028) from that mirror: bit-exact vs oracle convtran on the oracle's fields."""

@@ -293,6 +293,27 @@ def test_oracle_geopotential_t_equals_reference_source_text():
         assert np.array_equal(zi[:, :n], g["zi_lr%d" % lr][:, :n]) and np.array_equal(zm[:, :n], g["zm_lr%d" % lr][:, :n]), lr
 
 
+def test_oracle_geopotential_t_generalized_tv_equals_reference_source_text():
+    """geopotential_t, generalized-virtual-temperature branch (physics/geopotential.F90:248-310; dycore MPAS / SE), with
+    both hydrostatic-element variants of that branch (:283-298): reference text executed through the translator."""
+    g = np.load(os.path.join(GOLD, "reftext_geopotential_t_gen.npz"))
+    o, _, _ = get_oracle("libm", 16, 32)
+    n = int(g["ncol"])
+    plain = np.load(os.path.join(GOLD, "reftext_geopotential_t.npz"))
+    for lr in (0, 1):
+        zi, zm = o.geopotential_t_gen(n, lr, g["in_piln"], g["in_pint"], g["in_pmid"], g["in_pdel"], g["in_rpdel"],
+                                      g["in_t"], g["in_q3"], g["in_rair"], float(g["gravit"]), g["in_zvir"],
+                                      g["species_idx"])
+        assert np.array_equal(zi[:, :n], g["zi_lr%d" % lr][:, :n]) and np.array_equal(zm[:, :n], g["zm_lr%d" % lr][:, :n]), lr
+        # the branch is not the plain one in disguise: condensate loading lowers the heights by up to metres
+        d = np.abs(zi[:, :n] - plain["zi_lr%d" % lr][:, :n])
+        assert 0.1 < d.max() < 50.0
+    # no active species: qfac = sum = 1 and the factor is 1 + (zvir+1)*q  (:303)
+    zi0, _ = o.geopotential_t_gen(n, 0, g["in_piln"], g["in_pint"], g["in_pmid"], g["in_pdel"], g["in_rpdel"], g["in_t"],
+                                  g["in_q3"], g["in_rair"], float(g["gravit"]), g["in_zvir"], np.zeros(0, np.int32))
+    assert np.all(zi0[:-1, :n] > g["zi_lr0"][:-1, :n])
+
+
 def test_oracle_convect_diagnostics_equals_reference_source_text():
     """convect_diagnostics_calc (physics/convect_diagnostics.F90:115-249), CLUBB_SGS branch."""
     g = np.load(os.path.join(GOLD, "reftext_convect_diagnostics.npz"))
