@@ -39,6 +39,8 @@ struct ConvrOut {
   double *mu, *md, *du, *eu, *ed, *dp, *dsubcld;
   int *jt, *maxg, *ideep, *lengath;
   double *ql, *rliq, *dif, *dnlf, *dnif, *rice;
+  int mcon_kgm2s = 0;                    // fused zm_conv_tend step: mcon leaves the plume kernel as mcon*100/gravit
+                                         // (the unit conversion of zm_conv_intr.F90:693; zm_convr itself returns mb/s)
 };
 // per-column scratch (all sized ncolpad = nchunks*pcols; 2-D ones [pver][ncolpad])
 struct ConvrWork {

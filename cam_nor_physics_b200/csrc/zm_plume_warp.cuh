@@ -787,7 +787,7 @@ k_plume_w(ConvrIn in, ConvrOut o, ConvrWork w) {
     o.ql[e] = S(A_QL, k);
     if (o.eurt) o.eurt[e] = -dmpdz;
     const size_t ep = cidx(c, k - 1, i, pverp);
-    o.mcon[ep] = S(A_MC, k);
+    o.mcon[ep] = o.mcon_kgm2s ? div_z(S(A_MC, k) * 100.0, P.gravit) : S(A_MC, k);
     o.pflx[ep] = S(A_PFLX, k);
   }
   // gathered outputs at gathered position gi of chunk c

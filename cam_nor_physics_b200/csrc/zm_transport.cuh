@@ -158,6 +158,11 @@ struct MomArgs {
   const double *q, *mu, *md, *du, *eu, *ed, *dp;
   double *dqdt, *pguall, *pgdall, *icwu, *icwd, *seten;
   double dt;
+  // Fused zm_conv_tend step: the two wind components come from / go to separate (pcols,pver) arrays (state%u, state%v
+  // -> ptend%u, ptend%v) instead of the packed winds(pcols,pver,2) / wind_tends(pcols,pver,2) of zm_conv_intr.F90:814-826,
+  // so the step neither packs the winds nor unpacks the tendencies.  NULL: the packed q / dqdt above.
+  const double *q_u = nullptr, *q_v = nullptr;
+  double *dq_u = nullptr, *dq_v = nullptr;
 };
 
 // initialisation of the outgoing fields (zm_conv.F90:2429-2443, 2630)
@@ -178,6 +183,13 @@ __global__ void k_momtran_init(MomArgs a) {
     if (m < 2 && a.domom[m]) a.dqdt[e] = 0.0;
   }
   for (size_t e = tid; e < n2; e += nth) a.seten[e] = 0.0;
+}
+// the same for the fused step (split wind arrays, no history diagnostics): three plain zero-fills, 16 bytes per store
+__global__ void k_momtran_init_split(double2* du, double2* dv, double2* seten, size_t nhalf) {
+  const double2 z = make_double2(0.0, 0.0);
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nhalf; e += (size_t)gridDim.x * blockDim.x) {
+    du[e] = z; dv[e] = z; seten[e] = z;
+  }
 }
 
 // Warp per gathered (convective) column, lane = level.  Everything that is independent from level to level
@@ -219,12 +231,18 @@ k_momtran_t(MomArgs a) {
 #define SA(arr, k) S[(arr) * ld + (k)]
 #define QI(m, k) ((((size_t)c * 2 + (m)) * pver + (k) - 1) * pcols + ii)
 #define PAR for (int k = lane + 1; k <= pver; k += 32)
+  // wind component m of level k: packed (pcols,pver,2) arrays or the split ones of the fused step
+  const bool split = a.q_u != nullptr;
+  const double* qsrc[2] = {split ? a.q_u : a.q, split ? a.q_v : a.q + (size_t)pver * pcols};
+  double* qdst[2] = {split ? a.dq_u : a.dqdt, split ? a.dq_v : a.dqdt + (size_t)pver * pcols};
+  const size_t wbase = (size_t)c * (split ? 1 : 2) * pver * pcols + ii;
+#define WI(k) (wbase + (size_t)((k) - 1) * pcols)
   // ---- stage the column ----
   PAR {
     const size_t g = cidx(c, k - 1, gi, pver);
     SA(M_MU, k) = a.mu[g]; SA(M_MD, k) = a.md[g]; SA(M_ED, k) = a.ed[g]; SA(M_DP, k) = a.dp[g];
 #pragma unroll
-    for (int m = 0; m < 2; ++m) SA(M_C + m, k) = a.domom[m] ? a.q[QI(m, k)] : 0.0;
+    for (int m = 0; m < 2; ++m) SA(M_C + m, k) = a.domom[m] ? qsrc[m][WI(k)] : 0.0;
   }
   if (lane == 0) { SA(M_MF, pver + 1) = 0.0; SA(M_MF + 1, pver + 1) = 0.0; }
   __syncwarp();
@@ -313,7 +331,7 @@ k_momtran_t(MomArgs a) {
       double dc = 0.0;
       if (k >= ktm) dc = +div_z(X_p - X_k + Y_p - Y_k, dp_k);
       if (k >= kbm && k == mx) dc = (1.0 / dp_k) * (-X_k - Y_k);
-      a.dqdt[QI(m, k)] = dc;
+      qdst[m][WI(k)] = dc;
       if (a.pguall) {
         a.pguall[QI(m, k)] = -SA(M_PGU + m, k);
         a.pgdall[QI(m, k)] = -SA(M_PGD + m, k);
@@ -352,6 +370,7 @@ k_momtran_t(MomArgs a) {
   }
 #undef SA
 #undef QI
+#undef WI
 #undef PAR
 }
 

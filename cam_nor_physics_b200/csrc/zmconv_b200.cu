@@ -587,7 +587,16 @@ int momtran_launch(Workspace& ws, cudaStream_t s, MomArgs a, bool own_arena = tr
     cb = &own;
   }
   a.ktm = cb->ktm; a.kbm = cb->kbm; a.slots = cb->slots; a.count = cb->count;
-  k_momtran_init<<<592, 256, 0, s>>>(a); ++tls_launches;
+  if (a.q_u) {     // fused step: split wind arrays (pcols*pver is even for every supported pcols: 16-byte stores)
+    const size_t n2 = (size_t)ncolpad * pver;
+    if ((n2 & 1) || ((uintptr_t)a.dq_u | (uintptr_t)a.dq_v | (uintptr_t)a.seten) & 15) {
+      tls_err = "momtran: split wind tendencies need 16-byte aligned arrays of even length"; return -2;
+    }
+    k_momtran_init_split<<<1184, 256, 0, s>>>((double2*)a.dq_u, (double2*)a.dq_v, (double2*)a.seten, n2 / 2);
+  } else {
+    k_momtran_init<<<592, 256, 0, s>>>(a);
+  }
+  ++tls_launches;
   const size_t smem_mom = momtran_smem_bytes(pver);
   if (smem_mom > 48 * 1024)
     CK(cudaFuncSetAttribute(k_momtran_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mom));
@@ -709,27 +718,34 @@ __global__ void k_state_update(int n2, int nper, const double* t, const double* 
     }
   }
 }
-// ptend_all = sum of the three ptend_loc (physics_ptend_sum, physics_types.F90:698-844) and the
-// mcon unit conversion mb/s -> kg/m2/s (zm_conv_intr.F90:693)
-template <bool MOM>
+// ptend_all = sum of the three ptend_loc (physics_ptend_sum, physics_types.F90:698-844) and, unless the plume kernel
+// has done it (MCON = false), the mcon unit conversion mb/s -> kg/m2/s (zm_conv_intr.F90:693).
+// MODE 0: cam3, no momentum transport (zm_conv_intr.F90:808); 1: wind tendencies unpacked from wind_tends(pcols,pver,2);
+// 2: momtran has written ptend_u / ptend_v itself (split wind arrays).  evapcdp == ev_q when zm_conv_evap wrote its
+// tend_q straight into the caller's evapcdp.
+template <int MODE, bool MCON>
 __global__ void k_tend_finalize(int n2, int n2p, int nper, const double* heat, const double* qtnd,
                                 const double* ev_s, const double* ev_q, const double* seten,
                                 const double* wtend, double* ps, double* pq, double* pu, double* pv,
                                 double* evapcdp, double* mcon) {
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n2p; e += gridDim.x * blockDim.x) {
-    mcon[e] = div_z(mcon[e] * 100.0, P.gravit);
+  const int n = MCON ? n2p : n2;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    if (MCON) mcon[e] = div_z(mcon[e] * 100.0, P.gravit);
     if (e < n2) {
-      pq[e] = qtnd[e] + ev_q[e];
-      if (MOM) {
+      const double evq = ev_q[e];
+      pq[e] = qtnd[e] + evq;
+      if (MODE) {
         ps[e] = (heat[e] + ev_s[e]) + seten[e];
-        int c = e / nper, r = e - c * nper;
-        pu[e] = wtend[(size_t)c * 2 * nper + r];
-        pv[e] = wtend[(size_t)c * 2 * nper + nper + r];
-      } else {                      // cam3: no momentum transport (zm_conv_intr.F90:808)
+        if (MODE == 1) {
+          int c = e / nper, r = e - c * nper;
+          pu[e] = wtend[(size_t)c * 2 * nper + r];
+          pv[e] = wtend[(size_t)c * 2 * nper + nper + r];
+        }
+      } else {
         ps[e] = heat[e] + ev_s[e];
         pu[e] = 0.0; pv[e] = 0.0;
       }
-      evapcdp[e] = ev_q[e];
+      if (evapcdp != ev_q) evapcdp[e] = evq;
     }
   }
 }
@@ -1320,14 +1336,22 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
   // not among zm_conv_tend's outputs: not materialised here (all four NULL together)
   double *heat = ws.take<double>(n2), *qtnd = ws.take<double>(n2), *eurt = nullptr, *dif = nullptr, *dnlf = nullptr,
          *dnif = nullptr, *t1 = ws.take<double>(n2), *q1 = ws.take<double>(n2), *ev_s = ws.take<double>(n2),
-         *ev_q = ws.take<double>(n2), *snwprd = nullptr, *snwevmlt = nullptr, *ntprprd = nullptr, *ntsnprd = nullptr,
+         *ev_q_scratch = ws.take<double>(n2), *snwprd = nullptr, *snwevmlt = nullptr, *ntprprd = nullptr, *ntsnprd = nullptr,
          *seten = ws.take<double>(n2);     // zm_conv_evap's four history diagnostics are not materialised either
   // momtran's pguall / pgdall / icwu / icwd are history diagnostics the step does not return: not materialised
   double *winds = ws.take<double>(2 * n2), *wtend = ws.take<double>(2 * n2), *pgu = nullptr, *pgd = nullptr,
          *icwu = nullptr, *icwd = nullptr;
+  // zm_conv_evap's tend_q IS evapcdp (zm_conv_intr.F90:764-769 passes ptend_loc%q(:,:,1), :796 outputs it): written in place
+  double* ev_q = evapcdp ? evapcdp : ev_q_scratch;
+  const bool do_mom = !g_params.cam3;          // zm_conv_intr.F90:808: momentum transport is non-cam3 physics
+  // momtran reads state%u / state%v and writes ptend_u / ptend_v directly when they can take 16-byte stores
+  const bool split_env = !(getenv("ZM_TEND_SPLIT_WINDS") && atoi(getenv("ZM_TEND_SPLIT_WINDS")) == 0);   // 0: round-2a glue
+  const bool split = split_env && do_mom && !(n2 & 1) &&
+                     (((uintptr_t)ptend_u | (uintptr_t)ptend_v | (uintptr_t)seten) & 15) == 0;
   ConvrIn in{nchunks, ncol, t, q, pmid, pint, pdel, zm, zi, phis, pblh, tpert, landfrac, 0.5 * ztodt};
   ConvrOut o{prec, jctop, jcbot, qtnd, heat, mcon, cme, cape, eurt, dlf, pflx, zdu, rprd,
              mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, lengath, ql, rliq, dif, dnlf, dnif, rice};
+  o.mcon_kgm2s = split_env ? 1 : 0;            // unit conversion of zm_conv_intr.F90:693 inside the plume kernel
   in.org = g_params.zm_org ? org : nullptr;
   int rc = convr_launch(ws, s, in, o, false, orgt, org2d);
   if (rc) return rc;
@@ -1351,7 +1375,7 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
     CK(cudaEventRecord(ws.ev_fork, s));
     CK(cudaStreamWaitEvent(ws.side, ws.ev_fork, 0));
     k_state_update<1><<<1184, 256, 0, ws.side>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
-    if (!g_params.cam3) {       // winds feed momtran only
+    if (do_mom && !split) {     // packed winds feed momtran only
       k_state_update<2><<<1184, 256, 0, s>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
       ++tls_launches;
     }
@@ -1368,7 +1392,6 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
   }
   if (fork) CK(cudaEventRecord(ws.ev_join, ws.side));
   tick(ws, s, "zm_conv_evap");
-  const bool do_mom = !g_params.cam3;          // zm_conv_intr.F90:808: momentum transport is non-cam3 physics
   const bool do_tran1 = tr1 && tr1->nactive > 0;
   ChunkBounds cb;
   if (do_mom || do_tran1) {
@@ -1391,6 +1414,7 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
     ma.q = winds; ma.mu = mu; ma.md = md; ma.du = du; ma.eu = eu; ma.ed = ed; ma.dp = dp;
     ma.dqdt = wtend; ma.pguall = pgu; ma.pgdall = pgd; ma.icwu = icwu; ma.icwd = icwd; ma.seten = seten;
     ma.dt = ztodt;
+    if (split) { ma.q_u = u; ma.q_v = v; ma.dq_u = ptend_u; ma.dq_v = ptend_v; }
     rc = momtran_launch(ws, s, ma, false, &cb);
     if (rc) return rc;
   }
@@ -1412,12 +1436,13 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
   }
   if (tran_stream != s) CK(cudaStreamWaitEvent(s, ws.ev_join2, 0));
   if (fork) CK(cudaStreamWaitEvent(s, ws.ev_join, 0));
-  if (do_mom)
-    k_tend_finalize<true><<<1184, 256, 0, s>>>((int)n2, (int)n2p, nper, heat, qtnd, ev_s, ev_q, seten, wtend, ptend_s,
-                                               ptend_q, ptend_u, ptend_v, evapcdp, mcon);
-  else
-    k_tend_finalize<false><<<1184, 256, 0, s>>>((int)n2, (int)n2p, nper, heat, qtnd, ev_s, ev_q, seten, wtend, ptend_s,
-                                                ptend_q, ptend_u, ptend_v, evapcdp, mcon);
+  {
+    auto fin = !do_mom ? (o.mcon_kgm2s ? k_tend_finalize<0, false> : k_tend_finalize<0, true>)
+               : split ? (o.mcon_kgm2s ? k_tend_finalize<2, false> : k_tend_finalize<2, true>)
+                       : (o.mcon_kgm2s ? k_tend_finalize<1, false> : k_tend_finalize<1, true>);
+    fin<<<1184, 256, 0, s>>>((int)n2, (int)n2p, nper, heat, qtnd, ev_s, ev_q, seten, wtend, ptend_s, ptend_q, ptend_u,
+                             ptend_v, evapcdp ? evapcdp : ev_q, mcon);
+  }
   ++tls_launches;
   tick(ws, s, "tend_finalize");
   CK(cudaGetLastError());
