@@ -74,19 +74,12 @@ __device__ __forceinline__ void report_fail(const ConvrWork& w, int rcall, int c
 }
 
 // ---- output initialisation (zm_conv.F90:559-563, 625-650, 771-784, 906) ---------------------
-__global__ void k_convr_init(ConvrIn in, ConvrOut o, ConvrWork w) {
-  const int pcols = P.pcols, pver = P.pver, pverp = P.pverp;
+// Per-column outputs, the per-column scratch the CAPE passes read and the worklist counters: on the launching stream.
+__global__ void k_convr_init_cols(ConvrIn in, ConvrOut o, ConvrWork w) {
+  const int pcols = P.pcols, pver = P.pver;
   const size_t ncolpad = (size_t)in.nchunks * pcols;
   size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t nth = (size_t)gridDim.x * blockDim.x;
-  for (size_t e = tid; e < ncolpad * pver; e += nth) {
-    o.qtnd[e] = 0.0; o.heat[e] = 0.0; o.cme[e] = 0.0; o.dlf[e] = 0.0;
-    o.zdu[e] = 0.0; o.rprd[e] = 0.0; o.mu[e] = 0.0; o.md[e] = 0.0; o.du[e] = 0.0; o.eu[e] = 0.0;
-    o.ed[e] = 0.0; o.dp[e] = 0.0; o.ql[e] = 0.0;
-    // eurt, dif, dnlf, dnif are outputs of zm_convr that zm_conv_tend does not pass on: NULL inside the fused sequence
-    if (o.eurt) { o.eurt[e] = 0.0; o.dif[e] = 0.0; o.dnlf[e] = 0.0; o.dnif[e] = 0.0; }
-  }
-  for (size_t e = tid; e < ncolpad * pverp; e += nth) { o.mcon[e] = 0.0; o.pflx[e] = 0.0; }
   for (size_t e = tid; e < ncolpad; e += nth) {
     o.prec[e] = 0.0; o.rliq[e] = 0.0; o.rice[e] = 0.0; o.cape[e] = 0.0; o.dsubcld[e] = 0.0;
     // jctop = pver, jcbot = 1 for i <= ncol (zm_conv.F90:781-782); padding lanes are zero-filled
@@ -96,7 +89,37 @@ __global__ void k_convr_init(ConvrIn in, ConvrOut o, ConvrWork w) {
     w.dmpdz[e] = -P.tentrm;
   }
   for (size_t e = tid; e < (size_t)in.nchunks; e += nth) o.lengath[e] = 0;
-  if (tid < 4 + ZM_ORD_INTS) w.count[tid] = 0;
+  for (size_t e = tid; e < 4 + ZM_ORD_INTS; e += nth) w.count[e] = 0;
+}
+// The per-level outputs (zero outside the convective columns; nothing reads them before the plume kernel writes the
+// convective columns) and whatever else the caller wants zeroed with them (the fused step: ptend_u, ptend_v and the KE
+// heating, which momtran writes for convective columns only): 16-byte stores over a list of arrays.
+// Measured and dropped: the same fill on a side stream, either as ONE WARP PER SM with 32 registers -- resident beside
+// the single wave of the first CAPE pass, which leaves 1,024 of an SM's 65,536 registers free -- or as an ordinary grid
+// beside cldprp / the second CAPE pass, joined before the plume kernel: 2.107 / 2.109 ms against 2.108 ms with the
+// fill on the launching stream ahead of everything.
+#define ZM_FILL_MAX 24
+struct FillList {
+  double* p[ZM_FILL_MAX];
+  unsigned long long n[ZM_FILL_MAX];     // doubles
+  int cnt;
+};
+__global__ void __launch_bounds__(256)
+k_zero_fill(FillList f) {
+  const double2 z = make_double2(0.0, 0.0);
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  for (int a = 0; a < f.cnt; ++a) {
+    double* p = f.p[a];
+    const size_t n = f.n[a];
+    if ((((uintptr_t)p) & 15) == 0 && !(n & 1)) {
+      double2* q = reinterpret_cast<double2*>(p) + tid;
+      double2* const end = reinterpret_cast<double2*>(p) + (n >> 1);
+#pragma unroll 4
+      for (; q < end; q += nth) *q = z;
+    } else {
+      for (size_t e = tid; e < n; e += nth) p[e] = 0.0;
+    }
+  }
 }
 
 // ---- launch level of the dilute parcel and the work ordering of the CAPE passes ---------------------

@@ -163,6 +163,7 @@ struct MomArgs {
   // so the step neither packs the winds nor unpacks the tendencies.  NULL: the packed q / dqdt above.
   const double *q_u = nullptr, *q_v = nullptr;
   double *dq_u = nullptr, *dq_v = nullptr;
+  int prefilled = 0;                     // dq_u, dq_v, seten were zero-filled earlier in the step
 };
 
 // initialisation of the outgoing fields (zm_conv.F90:2429-2443, 2630)

@@ -59,6 +59,15 @@ struct Workspace {
   cudaStream_t side2 = nullptr;       // convtran1 runs here, concurrently with momtran and zm_conv_evap
   cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
   int side_priority = 0; bool side_priority_set = false;
+  int ensure_side() {
+    if (!side) {
+      if (side_priority_set) CK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, side_priority));
+      else CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    }
+    if (!ev_fork) CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    if (!ev_join) CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    return 0;
+  }
   int ensure_side2() {
     if (side2) return 0;
     if (side_priority_set) CK(cudaStreamCreateWithPriority(&side2, cudaStreamNonBlocking, side_priority));
@@ -373,7 +382,8 @@ size_t convr_work_bytes(size_t ncolpad, int pver) {
 
 // enqueue the whole zm_convr pipeline on stream s (no host synchronisation)
 int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOut& o,
-                 bool own_arena = true, double* orgt = nullptr, double* org2d = nullptr) {
+                 bool own_arena = true, double* orgt = nullptr, double* org2d = nullptr,
+                 const FillList* extra_fill = nullptr) {
   const int pcols = g_params.pcols, pver = g_params.pver;
   const bool org_on = g_params.zm_org != 0;
   if (org_on && !(in.org && orgt && org2d)) {
@@ -440,7 +450,19 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   }
   const bool ws1 = w.ws_gate > 0 && ncolpad <= (size_t)w.ws_gate;       // first pass: the host knows the column count
   tick(ws, s, "start");
-  k_convr_init<<<592, 256, 0, s>>>(in, o, w); ++tls_launches;
+  k_convr_init_cols<<<(unsigned)((ncolpad + 255) / 256), 256, 0, s>>>(in, o, w); ++tls_launches;
+  // zero-fill of the per-level outputs and of what the caller adds (the fused step's wind tendencies and KE heating)
+  FillList fl{};
+  {
+    const size_t n2 = ncolpad * pver, n2p = ncolpad * (pver + 1);
+    auto add = [&](double* p, size_t n) { if (p && fl.cnt < ZM_FILL_MAX) { fl.p[fl.cnt] = p; fl.n[fl.cnt] = n; ++fl.cnt; } };
+    for (double* p : {o.qtnd, o.heat, o.cme, o.dlf, o.zdu, o.rprd, o.mu, o.md, o.du, o.eu, o.ed, o.dp, o.ql}) add(p, n2);
+    // eurt, dif, dnlf, dnif are outputs of zm_convr that zm_conv_tend does not pass on: NULL inside the fused sequence
+    for (double* p : {o.eurt, o.dif, o.dnlf, o.dnif}) add(p, n2);
+    add(o.mcon, n2p); add(o.pflx, n2p);
+    if (extra_fill) for (int a = 0; a < extra_fill->cnt; ++a) add(extra_fill->p[a], extra_fill->n[a]);
+  }
+  k_zero_fill<<<1184, 256, 0, s>>>(fl); ++tls_launches;
   if (org_on) {      // zm_conv.F90:555-556, 793-819
     k_org2d<<<nblk_cols, TB, 0, s>>>(in.nchunks, in.ncol, in.org, in.dpp, orgt, org2d); ++tls_launches;
   }
@@ -587,16 +609,15 @@ int momtran_launch(Workspace& ws, cudaStream_t s, MomArgs a, bool own_arena = tr
     cb = &own;
   }
   a.ktm = cb->ktm; a.kbm = cb->kbm; a.slots = cb->slots; a.count = cb->count;
-  if (a.q_u) {     // fused step: split wind arrays (pcols*pver is even for every supported pcols: 16-byte stores)
+  if (a.q_u) {     // fused step: split wind arrays (even length and 16-byte alignment checked by the caller)
     const size_t n2 = (size_t)ncolpad * pver;
-    if ((n2 & 1) || ((uintptr_t)a.dq_u | (uintptr_t)a.dq_v | (uintptr_t)a.seten) & 15) {
-      tls_err = "momtran: split wind tendencies need 16-byte aligned arrays of even length"; return -2;
+    if (!a.prefilled) {      // else zero-filled with zm_convr's outputs at the start of the step
+      k_momtran_init_split<<<1184, 256, 0, s>>>((double2*)a.dq_u, (double2*)a.dq_v, (double2*)a.seten, n2 / 2);
+      ++tls_launches;
     }
-    k_momtran_init_split<<<1184, 256, 0, s>>>((double2*)a.dq_u, (double2*)a.dq_v, (double2*)a.seten, n2 / 2);
   } else {
-    k_momtran_init<<<592, 256, 0, s>>>(a);
+    k_momtran_init<<<592, 256, 0, s>>>(a); ++tls_launches;
   }
-  ++tls_launches;
   const size_t smem_mom = momtran_smem_bytes(pver);
   if (smem_mom > 48 * 1024)
     CK(cudaFuncSetAttribute(k_momtran_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mom));
@@ -1353,7 +1374,11 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
              mu, md, du, eu, ed, dp, dsubcld, jt, maxg, ideep, lengath, ql, rliq, dif, dnlf, dnif, rice};
   o.mcon_kgm2s = split_env ? 1 : 0;            // unit conversion of zm_conv_intr.F90:693 inside the plume kernel
   in.org = g_params.zm_org ? org : nullptr;
-  int rc = convr_launch(ws, s, in, o, false, orgt, org2d);
+  // split winds: ptend_u / ptend_v / seten are zero outside the convective columns momtran writes -- filled with
+  // zm_convr's own outputs at the start of the step
+  FillList xf{};
+  if (split) { xf.p[0] = ptend_u; xf.p[1] = ptend_v; xf.p[2] = seten; xf.n[0] = xf.n[1] = xf.n[2] = n2; xf.cnt = 3; }
+  int rc = convr_launch(ws, s, in, o, false, orgt, org2d, split ? &xf : nullptr);
   if (rc) return rc;
   if (hooks) {
     CK(cudaEventRecord(hooks->convr_done, s));            // zm_convr outputs are final from here on
@@ -1367,11 +1392,7 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
   // the wind half); kept serial while per-kernel profiling is on
   const bool fork = !g_profile;
   if (fork) {
-    if (!ws.side) {
-      CK(cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&ws.ev_fork, cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&ws.ev_join, cudaEventDisableTiming));
-    }
+    if (ws.ensure_side()) return -100;
     CK(cudaEventRecord(ws.ev_fork, s));
     CK(cudaStreamWaitEvent(ws.side, ws.ev_fork, 0));
     k_state_update<1><<<1184, 256, 0, ws.side>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
@@ -1414,7 +1435,7 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
     ma.q = winds; ma.mu = mu; ma.md = md; ma.du = du; ma.eu = eu; ma.ed = ed; ma.dp = dp;
     ma.dqdt = wtend; ma.pguall = pgu; ma.pgdall = pgd; ma.icwu = icwu; ma.icwd = icwd; ma.seten = seten;
     ma.dt = ztodt;
-    if (split) { ma.q_u = u; ma.q_v = v; ma.dq_u = ptend_u; ma.dq_v = ptend_v; }
+    if (split) { ma.q_u = u; ma.q_v = v; ma.dq_u = ptend_u; ma.dq_v = ptend_v; ma.prefilled = 1; }
     rc = momtran_launch(ws, s, ma, false, &cb);
     if (rc) return rc;
   }
