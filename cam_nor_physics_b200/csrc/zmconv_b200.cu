@@ -462,13 +462,29 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
     add(o.mcon, n2p); add(o.pflx, n2p);
     if (extra_fill) for (int a = 0; a < extra_fill->cnt; ++a) add(extra_fill->p[a], extra_fill->n[a]);
   }
+  // the work ordering of the first CAPE pass (latency-bound, inputs only) runs on the side stream beside the fill
+  // (bandwidth-bound); ZM_ORDER_SIDE=0 keeps both on this stream
+  const bool order_side = !g_profile && !(getenv("ZM_ORDER_SIDE") && atoi(getenv("ZM_ORDER_SIDE")) == 0);
+  const int nblk_ord = (int)((ncolpad + 255) / 256);
+  if (order_side) {
+    if (ws.ensure_side()) return -100;
+    CK(cudaEventRecord(ws.ev_fork, s));                        // after k_convr_init_cols: the counters are zero
+    CK(cudaStreamWaitEvent(ws.side, ws.ev_fork, 0));
+    k_order_count<1><<<nblk_ord, 256, 0, ws.side>>>(in, w);
+    k_order_scatter<1><<<nblk_ord, 256, 0, ws.side>>>(in, w);
+    CK(cudaEventRecord(ws.ev_join, ws.side));
+  }
   k_zero_fill<<<1184, 256, 0, s>>>(fl); ++tls_launches;
   if (org_on) {      // zm_conv.F90:555-556, 793-819
     k_org2d<<<nblk_cols, TB, 0, s>>>(in.nchunks, in.ncol, in.org, in.dpp, orgt, org2d); ++tls_launches;
   }
-  const int nblk_ord = (int)((ncolpad + 255) / 256);
-  k_order_count<1><<<nblk_ord, 256, 0, s>>>(in, w); ++tls_launches;           // CAPE work order: most parcel levels first
-  k_order_scatter<1><<<nblk_ord, 256, 0, s>>>(in, w); ++tls_launches;
+  if (order_side) {
+    CK(cudaStreamWaitEvent(s, ws.ev_join, 0));
+  } else {
+    k_order_count<1><<<nblk_ord, 256, 0, s>>>(in, w);           // CAPE work order: most parcel levels first
+    k_order_scatter<1><<<nblk_ord, 256, 0, s>>>(in, w);
+  }
+  tls_launches += 2;
   tick(ws, s, "convr_init");
   if (g_params.cam3) k_buoyan_undilute<<<nblk_cols, TB, smem, s>>>(in, w);     // zm_conv.F90:871-880
   else if (ws1 && org_on) k_buoyan_dilute_ws<1, true><<<nblk_ws, 64, smem_ws, s>>>(in, w);
