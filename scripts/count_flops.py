@@ -64,7 +64,9 @@ def main():
             name = row.get("Kernel Name", {}).get("value", "")
             if "k_buoyan_dilute<1" in name or "k_buoyan_dilute<(int)1" in name:
                 d["executed_flops_per_column"] = row["fp64_flops_per_launch"] / NCOLS
-                d["dram_bytes_per_launch"] = (row["dram__bytes_read.sum"]["value"] + row["dram__bytes_write.sum"]["value"]) * 1e6
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}     # ncu picks the unit per value
+                d["dram_bytes_per_launch"] = sum(row[m]["value"] * scale[row[m]["unit"]]
+                                                 for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
                 d["executed_source"] = f"{os.path.relpath(sys.argv[1], ROOT)} (ncu --set full): 2*dfma+dadd+dmul thread-level executed ops of {name.strip()}"
                 d["executed_kernel_hash"] = kernel_hash()
     d["kernel_hash_now"] = kernel_hash()
