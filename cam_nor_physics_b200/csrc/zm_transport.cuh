@@ -15,8 +15,15 @@ struct EvapArgs {
   double *tend_s, *tend_s_snwprd, *tend_s_snwevmlt, *tend_q, *prec, *snow, *ntprprd, *ntsnprd,
       *flxprec, *flxsnow;
   double deltat;
+  // Fused zm_conv_tend step (k_conv_evap<true>): t, q above are the state BEFORE zm_convr's tendencies and the kernel
+  // applies physics_update itself (t + heat*dt/cpair, q + qtnd*dt clipped at 1e-12: physics_types.F90:322-329, 427,
+  // the statements of k_state_update), then stores the sums of the two ptend_loc instead of its own tend_s:
+  // ps = heat + tend_s, pq = qtnd + tend_q (zm_conv_intr.F90:736, 803); tend_q still goes to a.tend_q (= evapcdp).
+  const double *heat = nullptr, *qtnd = nullptr;
+  double *ps = nullptr, *pq = nullptr;
 };
 
+template <bool FUSED>
 __global__ void __launch_bounds__(128)
 k_conv_evap(EvapArgs a) {
   const int pcols = P.pcols, pver = P.pver, pverp = P.pverp;
@@ -28,7 +35,8 @@ k_conv_evap(EvapArgs a) {
     // what goes back to the host never depends on stale device memory
     for (int k = 0; k < pver; ++k) {
       const size_t e = cidx(c, k, i, pver);
-      a.tend_s[e] = 0.0; a.tend_q[e] = 0.0;
+      if (FUSED) { a.ps[e] = 0.0; a.pq[e] = 0.0; } else a.tend_s[e] = 0.0;
+      a.tend_q[e] = 0.0;
       // tend_s_snwprd, tend_s_snwevmlt, ntprprd, ntsnprd are history diagnostics (zm_conv_intr.F90:779-794): all four
       // NULL inside the fused zm_conv_tend step
       if (a.ntprprd) { a.tend_s_snwprd[e] = 0.0; a.tend_s_snwevmlt[e] = 0.0; a.ntprprd[e] = 0.0; a.ntsnprd[e] = 0.0; }
@@ -44,8 +52,14 @@ k_conv_evap(EvapArgs a) {
   a.flxsnow[cidx(c, 0, i, pverp)] = 0.0;
   for (int k = 1; k <= pver; ++k) {
     const size_t e = cidx(c, k - 1, i, pver);
-    const double t = a.t[e], pmid = a.pmid[e], pdel = a.pdel[e], q = a.q[e], prdprec = a.prdprec[e],
-                 cldfrc = a.cldfrc[e];
+    const double pmid = a.pmid[e], pdel = a.pdel[e], prdprec = a.prdprec[e], cldfrc = a.cldfrc[e];
+    double t = a.t[e], q = a.q[e], heat_k = 0.0, qtnd_k = 0.0;
+    if (FUSED) {
+      heat_k = a.heat[e]; qtnd_k = a.qtnd[e];
+      t = t + div_z(heat_k * a.deltat, P.cpair);
+      const double qn = q + qtnd_k * a.deltat;
+      q = (qn < 1.e-12) ? 1.e-12 : qn;
+    }
     double es, qs, fice, fsnow_conv;
     qsat_table(t, pmid, es, qs);
     cldfrc_fice(t, fice, fsnow_conv);
@@ -85,7 +99,8 @@ k_conv_evap(EvapArgs a) {
     flxsnow = fmax2(flxsnow, 0.0);
     a.flxprec[cidx(c, k, i, pverp)] = flxprec;
     a.flxsnow[cidx(c, k, i, pverp)] = flxsnow;
-    a.tend_s[e] = -evpprec * latvap + ntsnprd * latice;
+    const double tend_s = -evpprec * latvap + ntsnprd * latice;
+    if (FUSED) { a.ps[e] = heat_k + tend_s; a.pq[e] = qtnd_k + evpprec; } else a.tend_s[e] = tend_s;
     a.tend_q[e] = evpprec;
   }
   a.prec[col] = div_z(flxprec, 1000.0);

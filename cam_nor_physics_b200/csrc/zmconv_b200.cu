@@ -594,7 +594,9 @@ struct Stager {      // host-pointer API: bump-allocate device copies of user ar
 
 int evap_launch(cudaStream_t s, const EvapArgs& a) {
   const int ncolpad = a.nchunks * g_params.pcols;
-  k_conv_evap<<<(ncolpad + 127) / 128, 128, 0, s>>>(a); ++tls_launches;
+  if (a.heat) k_conv_evap<true><<<(ncolpad + 127) / 128, 128, 0, s>>>(a);
+  else        k_conv_evap<false><<<(ncolpad + 127) / 128, 128, 0, s>>>(a);
+  ++tls_launches;
   CK(cudaGetLastError());
   return 0;
 }
@@ -784,6 +786,17 @@ __global__ void k_tend_finalize(int n2, int n2p, int nper, const double* heat, c
       }
       if (evapcdp != ev_q) evapcdp[e] = evq;
     }
+  }
+}
+
+// the last term of ptend_s when zm_conv_evap has stored heat + tend_s itself: ptend_s = (heat + tend_s) + seten
+// (zm_conv_intr.F90:833), every element like the reference (seten is +0 outside the columns momtran wrote)
+__global__ void k_add_seten(size_t nhalf, double2* ps, const double2* seten) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nhalf; e += (size_t)gridDim.x * blockDim.x) {
+    double2 a = ps[e];
+    const double2 b = seten[e];
+    a.x = a.x + b.x; a.y = a.y + b.y;
+    ps[e] = a;
   }
 }
 
@@ -1407,17 +1420,27 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
   // (with the t, q half of the state update) goes to a side stream and overlaps momtran (which only waits for
   // the wind half); kept serial while per-kernel profiling is on
   const bool fork = !g_profile;
+  // With the split winds nothing but zm_conv_evap needs the updated state: the kernel applies physics_update to its
+  // own operands and stores heat + tend_s / qtnd + tend_q straight into ptend_s / ptend_q (k_conv_evap<true>); what is
+  // left for the end of the step is ptend_s += seten.  ZM_TEND_FUSE_EVAP=0: separate state update and final sum.
+  const bool fuse_evap = split && o.mcon_kgm2s && (((uintptr_t)ptend_s) & 15) == 0 &&
+                         !(getenv("ZM_TEND_FUSE_EVAP") && atoi(getenv("ZM_TEND_FUSE_EVAP")) == 0);
+  if (fuse_evap) {
+    ea.t = t; ea.q = q; ea.heat = heat; ea.qtnd = qtnd; ea.ps = ptend_s; ea.pq = ptend_q; ea.tend_s = nullptr;
+  }
   if (fork) {
     if (ws.ensure_side()) return -100;
     CK(cudaEventRecord(ws.ev_fork, s));
     CK(cudaStreamWaitEvent(ws.side, ws.ev_fork, 0));
-    k_state_update<1><<<1184, 256, 0, ws.side>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
+    if (!fuse_evap) {
+      k_state_update<1><<<1184, 256, 0, ws.side>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
+      ++tls_launches;
+    }
     if (do_mom && !split) {     // packed winds feed momtran only
       k_state_update<2><<<1184, 256, 0, s>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
       ++tls_launches;
     }
-    ++tls_launches;
-  } else {
+  } else if (!fuse_evap) {
     k_state_update<0><<<1184, 256, 0, s>>>((int)n2, nper, t, q, heat, qtnd, u, v, ztodt, t1, q1, winds);
     ++tls_launches;
   }
@@ -1473,7 +1496,9 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
   }
   if (tran_stream != s) CK(cudaStreamWaitEvent(s, ws.ev_join2, 0));
   if (fork) CK(cudaStreamWaitEvent(s, ws.ev_join, 0));
-  {
+  if (fuse_evap) {
+    k_add_seten<<<1184, 256, 0, s>>>(n2 / 2, (double2*)ptend_s, (const double2*)seten);
+  } else {
     auto fin = !do_mom ? (o.mcon_kgm2s ? k_tend_finalize<0, false> : k_tend_finalize<0, true>)
                : split ? (o.mcon_kgm2s ? k_tend_finalize<2, false> : k_tend_finalize<2, true>)
                        : (o.mcon_kgm2s ? k_tend_finalize<1, false> : k_tend_finalize<1, true>);

@@ -546,23 +546,26 @@ def test_conv_tend_glue_variants(built, monkeypatch, pcols, pver):
     converted to kg/m2/s in the plume kernel, zm_conv_evap's tend_q written straight into evapcdp (default, needs
     an even pcols*pver for its 16-byte zero-fills) -- and the packed winds(pcols,pver,2) / wind_tends form of
     zm_conv_intr.F90:814-826 with the conversion in the final kernel (ZM_TEND_SPLIT_WINDS=0, and the automatic fallback
-    for odd pcols*pver).  Both bit for bit against the oracle, host-pointer and device-resident calls."""
+    for odd pcols*pver); with the split form zm_conv_evap's kernel also applies physics_update itself and stores the
+    summed tendencies (ZM_TEND_FUSE_EVAP=0: separate kernels).  All bit for bit against the oracle, host-pointer and
+    device-resident calls."""
     Z = init_cuda(pcols, pver)
     o, _, _ = get_oracle("pm", pcols, pver)
     from cam_nor_physics_b200.device import DeviceTend
     ch = S.make_chunks(pcols * 91 - 3, pver, pcols, p_conv=0.6)      # 91 chunks: 13 x 29 x 91 elements are odd
     ref = o.conv_tend_batch(ch)
     assert int(ref["lengath"].sum()) > 100
-    for split in ("1", "0"):
+    for split, fuse in (("1", "1"), ("1", "0"), ("0", "1")):
         monkeypatch.setenv("ZM_TEND_SPLIT_WINDS", split)
+        monkeypatch.setenv("ZM_TEND_FUSE_EVAP", fuse)     # physics_update + the ptend sums inside zm_conv_evap's kernel
         monkeypatch.setenv("ZM_DEV_GRAPH", "0")
         out = Z.zm_conv_tend(ch.ncol, state_of(ch), ch.ztodt)
-        assert_same(out, ref, TEND_KEYS, pcols, exact=True, what=f"host-pointer step, split={split}")
+        assert_same(out, ref, TEND_KEYS, pcols, exact=True, what=f"host-pointer step, split={split} fuse={fuse}")
         dev = DeviceTend(ch)
         dev.step()
         assert dev.check() == 0
         dout = {k: v.cpu().numpy() for k, v in dev.out.items()}
-        assert_same(dout, ref, TEND_KEYS, pcols, exact=True, what=f"device-resident step, split={split}")
+        assert_same(dout, ref, TEND_KEYS, pcols, exact=True, what=f"device-resident step, split={split} fuse={fuse}")
     assert np.count_nonzero(ref["ptend_u"]) > 0 and np.count_nonzero(ref["mcon"]) > 0
 
 
