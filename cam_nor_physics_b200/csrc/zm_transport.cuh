@@ -222,8 +222,11 @@ __global__ void k_momtran_init_split(double2* du, double2* dv, double2* seten, s
 // the same instructions as its neighbours:  val = use ? ((A*prev + B1) + B2) / D : default
 enum MomArr { M_MU = 0, M_MD, M_ED, M_DP, M_C, M_CHAT = M_C + 2, M_PGU = M_CHAT + 2, M_PGD = M_PGU + 2,
               M_CONU = M_PGD + 2, M_COND = M_CONU + 2,      // = "chain value" arrays M_CONU + chain
-              M_MF = M_COND + 2, M_WF = M_MF + 2,
-              M_B1 = M_WF + 2, M_B2 = M_B1 + 4,             // per chain
+              M_B1 = M_COND + 2, M_B2 = M_B1 + 4,           // per chain
+              // momentum flux and end-of-step wind are formed after the recurrences, when their numerator terms B1 are
+              // dead: same storage (level pver+1 of MF is set ahead of the recurrences; B1 ends at level pver).
+              // 32 instead of 36 arrays: six instead of five 4-warp blocks per SM at L32
+              M_MF = M_B1, M_WF = M_B1 + 2,
               M_A = M_B2 + 4, M_D = M_A + 2, M_R = M_D + 2, M_USE = M_R + 2,   // per direction
               M_NARR = M_USE + 2 };
 __host__ __device__ inline size_t momtran_smem_bytes(int pver) {
