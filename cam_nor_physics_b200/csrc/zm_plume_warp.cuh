@@ -17,10 +17,12 @@
 
 enum PlumeArr {
   A_Q, A_T, A_P, A_Z, A_S, A_ZF, A_DZ, A_DP, A_SHAT, A_QHAT,
-  A_MU, A_EU, A_DU, A_MD, A_ED, A_SD, A_QD, A_MC, A_QU, A_SU, A_QST, A_HMN, A_HSAT, A_QL, A_CMEG,
-  A_PFLX, A_EVP, A_CU, A_RPRD,
+  A_MU, A_EU, A_DU, A_QU, A_SU, A_QST, A_HMN, A_HSAT,
   A_GAMMA, A_HU, A_EPS, A_F, A_K1, A_I2, A_I3, A_I4, A_QSTHAT, A_HSTHAT, A_GAMHAT,
   A_W1,
+  A_FRONT_COUNT,   // 30 arrays are all the first cldprp call touches (cldprp_warp<false>, up to the cloud-top reset):
+                   // k_cldprp_pass1_w allocates only these -- 24-26 warps per SM at L32 instead of 20
+  A_MD = A_FRONT_COUNT, A_ED, A_SD, A_QD, A_MC, A_QL, A_CMEG, A_PFLX, A_EVP, A_CU, A_RPRD,
   A_COUNT,     // 41 arrays: 4 warps x 41 x 34 doubles = 44.6 KB per block, FIVE blocks (20 warps) per SM at L32
   // Arrays with disjoint lifetimes share storage (occupancy of these kernels is bounded by shared memory).
   // Host array -> last use; guest -> first use, in the (straight-line) order of cldprp_warp / k_plume_w:
@@ -104,12 +106,17 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
   // ---- level-parallel initialisation (zm_conv.F90:3256-3314) ----
   PAR(k, 1, pver + 1) {
     S(A_K1, k) = 0.0; S(A_I2, k) = 0.0; S(A_I3, k) = 0.0; S(A_I4, k) = 0.0;
-    S(A_MU, k) = 0.0; S(A_F, k) = 0.0; S(A_EPS, k) = 0.0; S(A_QL, k) = 0.0;
+    S(A_MU, k) = 0.0; S(A_F, k) = 0.0; S(A_EPS, k) = 0.0;
+    if (FULL) S(A_QL, k) = 0.0;          // the arrays from A_MD on exist in the full kernel only
     if (k <= pver) {
       const double qk = S(A_Q, k), tk = S(A_T, k), pk = S(A_P, k), zk = S(A_Z, k), sk = S(A_S, k);
-      S(A_EU, k) = 0.0; S(A_DU, k) = 0.0; S(A_CU, k) = 0.0; S(A_EVP, k) = 0.0; S(A_CMEG, k) = 0.0;
-      S(A_MD, k) = 0.0; S(A_ED, k) = 0.0; S(A_SD, k) = sk; S(A_QD, k) = qk;
-      S(A_MC, k) = 0.0; S(A_QU, k) = qk; S(A_SU, k) = sk;
+      S(A_EU, k) = 0.0; S(A_DU, k) = 0.0;
+      if (FULL) {
+        S(A_CU, k) = 0.0; S(A_EVP, k) = 0.0; S(A_CMEG, k) = 0.0;
+        S(A_MD, k) = 0.0; S(A_ED, k) = 0.0; S(A_SD, k) = sk; S(A_QD, k) = qk;
+        S(A_MC, k) = 0.0; S(A_RPRD, k) = 0.0;
+      }
+      S(A_QU, k) = qk; S(A_SU, k) = sk;
       double est, qs;
       qsat_hPa(tk, pk, est, qs);
       if (pk - est <= 0.0) qs = 1.0;
@@ -122,10 +129,9 @@ __device__ __forceinline__ PlumeIdx cldprp_warp(const PlumeSh& S, int jb, int le
       S(A_HMN, k) = hmn;
       S(A_HSAT, k) = mcp * tk + grav * zk + mrl * qs;
       S(A_HU, k) = hmn;
-      S(A_RPRD, k) = 0.0;
     }
   }
-  if (lane == 0) S(A_PFLX, 1) = 0.0;
+  if (FULL && lane == 0) S(A_PFLX, 1) = 0.0;
   WSYNC();
   PAR(k, 1, pver) {
     if (k <= msg + 1) {
@@ -585,8 +591,8 @@ inline int plume_ld(int pver) { return pver <= 32 ? 34 : (pver <= 64 ? 66 : 130)
 // Warps per block: shared memory bounds the residency of these kernels, and what is left over after the last
 // whole block is wasted -- pick the block size that leaves the most warps resident per SM (227 KB, 1 KB reserved
 // per block).  L32: 4 warps x 5 blocks = 20 warps; L58/L64: 1 warp x 10 blocks (4-warp blocks would hold 8).
-inline int plume_warps_per_block(int pver) {
-  const size_t per_warp = (size_t)A_COUNT * plume_ld(pver) * sizeof(double), sm = 227 * 1024;
+inline int plume_warps_per_block(int pver, int narr = A_COUNT) {
+  const size_t per_warp = (size_t)narr * plume_ld(pver) * sizeof(double), sm = 227 * 1024;
   int best = 1; size_t best_res = 0;
   for (int w = PL_WARPS; w >= 1; --w) {
     const size_t blocks = sm / (w * per_warp + 1024);
@@ -595,8 +601,8 @@ inline int plume_warps_per_block(int pver) {
   }
   return best;
 }
-inline size_t plume_smem_bytes(int pver) {
-  return (size_t)plume_warps_per_block(pver) * A_COUNT * plume_ld(pver) * sizeof(double);
+inline size_t plume_smem_bytes(int pver, int narr = A_COUNT) {
+  return (size_t)plume_warps_per_block(pver, narr) * narr * plume_ld(pver) * sizeof(double);
 }
 
 // ---- pass-1 plume: diagnose the pass-2 test-parcel entrainment rate (zm_conv.F90:1047-1078) ---
@@ -610,7 +616,7 @@ k_cldprp_pass1_w(ConvrIn in, ConvrWork w) {
   const int col = w.wl1[gw];
   const int pcols = P.pcols, pver = P.pver, msg = P.msg;
   const int c = col / pcols, i = col - c * pcols;
-  const PlumeShT<LD> S{sm_pl + (size_t)wib * A_COUNT * LD};
+  const PlumeShT<LD> S{sm_pl + (size_t)wib * A_FRONT_COUNT * LD};     // the front arrays only
   const int maxg = w.mx[col];
   gather_column_w(S, in, c, i, maxg, lane);
   cldprp_warp<false>(S, maxg, w.lel[col], in.landfrac[(size_t)c * pcols + i], lane);

@@ -430,7 +430,11 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   const int pl_ld = plume_ld(pver);
   auto k_cld1 = pl_ld == 34 ? k_cldprp_pass1_w<34> : (pl_ld == 66 ? k_cldprp_pass1_w<66> : k_cldprp_pass1_w<130>);
   auto k_plm = pl_ld == 34 ? k_plume_w<34> : (pl_ld == 66 ? k_plume_w<66> : k_plume_w<130>);
-  CK(cudaFuncSetAttribute(k_cld1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
+  // the first cldprp call needs 30 of the 41 work arrays: its own (smaller) blocks, more warps per SM
+  const int pl1_warps = plume_warps_per_block(pver, A_FRONT_COUNT);
+  const int nblk_pl1 = (int)((ncolpad + pl1_warps - 1) / pl1_warps);
+  const size_t smem_pl1 = plume_smem_bytes(pver, A_FRONT_COUNT);
+  CK(cudaFuncSetAttribute(k_cld1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl1));
   CK(cudaFuncSetAttribute(k_plm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pl));
   {   // static tables (ZMM_HOT_SMEM_BYTES, 26 KB) + the buoyancy rows exceed the 48 KB default: opt in (dynamic part)
     CK(cudaFuncSetAttribute(k_buoyan_dilute<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -499,7 +503,7 @@ int convr_launch(Workspace& ws, cudaStream_t s, const ConvrIn& in, const ConvrOu
   k_order_count<2><<<nblk_ord, 256, 0, s>>>(in, w); ++tls_launches;
   k_order_scatter<2><<<nblk_ord, 256, 0, s>>>(in, w); ++tls_launches;
   tick(ws, s, "trigger_pass1");
-  k_cld1<<<nblk_pl, 32 * pl_warps, smem_pl, s>>>(in, w);
+  k_cld1<<<nblk_pl1, 32 * pl1_warps, smem_pl1, s>>>(in, w);
   ++tls_launches;
   tick(ws, s, "cldprp_pass1");
   // The reference's second call covers every column of a chunk that has a convective column after the first gather
