@@ -332,6 +332,11 @@ def test_device_resident_path_and_conservation(built):
     assert np.isclose(c[0], (ch.pdel / g * ref["ptend_q"]).sum(), rtol=1e-12)
     assert np.isclose(c[1], 1000.0 * (ref["prec"] + ref["rliq"]).sum(), rtol=1e-12)
     assert c[4] == ref["lengath"].sum() and c[5] == 4096
+    assert np.isclose(c[2], (ch.pdel / g * ref["ptend_s"]).sum(), rtol=1e-11)
+    assert np.isclose(c[3], 1000.0 * (2.501e6 * (ref["prec"] + ref["rliq"]) + 3.337e5 * ref["snow"]).sum(), rtol=1e-12)
+    # deterministic: a fixed grid and a fixed order of additions -- the same bits every time
+    c2 = dev.conservation().cpu().numpy()
+    assert np.array_equal(c.view(np.int64), c2.view(np.int64))
 
 
 def test_momtran_component_flags_and_reentrancy(built):
