@@ -895,15 +895,15 @@ k_tend_diag(int nchunks, const int* ncol, const double* ps, const double* pmid, 
 
 __global__ void k_dpdry_gather(int nchunks, const int* ideep, const int* lengath, const double* pdeldry,
                                double* dpdry) {
-  const int pcols = P.pcols, pver = P.pver;
-  const size_t n2 = (size_t)nchunks * pcols * pver;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)(e % pcols);
-    const size_t r = e / pcols;
-    const int k = (int)(r % pver), c = (int)(r / pver);
-    double v = 0.0;
-    if (i < lengath[c]) v = pdeldry[cidx(c, k, ideep[(size_t)c * pcols + i] - 1, pver)] / 100.0;
-    dpdry[e] = v;
+  const int pcols = P.pcols, pver = P.pver, nper = pcols * pver;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {        // a block per chunk: 32-bit index arithmetic only
+    const int len = lengath[c];
+    for (int r = threadIdx.x; r < nper; r += blockDim.x) {
+      const int k = r / pcols, i = r - k * pcols;
+      double v = 0.0;
+      if (i < len) v = pdeldry[cidx(c, k, ideep[(size_t)c * pcols + i] - 1, pver)] / 100.0;
+      dpdry[(size_t)c * nper + r] = v;
+    }
   }
 }
 
@@ -2147,7 +2147,7 @@ int zm_conv_tend_2_batch_dev(int nchunks, const int* doconvtran, const double* q
   for (auto e : ws.tev) cudaEventDestroy(e);
   ws.tev.clear(); ws.tnames.clear();
   tick(ws, s, "start");
-  k_dpdry_gather<<<592, 256, 0, s>>>(nchunks, ideep, lengath, pdeldry, dpdry); ++tls_launches;
+  k_dpdry_gather<<<1184, 256, 0, s>>>(nchunks, ideep, lengath, pdeldry, dpdry); ++tls_launches;
   TranArgs a;
   a.nchunks = nchunks; a.ncnst = pcnst; a.nactive = tls_tmeta.nactive; a.jt = jt; a.mx = maxg; a.ideep = ideep;
   a.lengath = lengath; a.active = tls_tmeta.active(); a.is_dry = tls_tmeta.dry();
@@ -2179,7 +2179,7 @@ int zm_conv_tend_2_batch(int nchunks, const int* doconvtran, const double* q, in
   double* d_dpdry = st.take<double>(n2);
   double* d_dqdt = S.inout(ptend_q, n3);
   // dpdry(i,:) = pdeldry(ideep(i),:)/100 for i <= lengath, else 0 (zm_conv_intr.F90:1014-1017)
-  k_dpdry_gather<<<592, 256, 0, st.stream>>>(nchunks, M.ideep, M.lengath, d_pdd, d_dpdry); ++tls_launches;
+  k_dpdry_gather<<<1184, 256, 0, st.stream>>>(nchunks, M.ideep, M.lengath, d_pdd, d_dpdry); ++tls_launches;
   for (auto e : st.tev) cudaEventDestroy(e);
   st.tev.clear(); st.tnames.clear();
   tick(st, st.stream, "start");
