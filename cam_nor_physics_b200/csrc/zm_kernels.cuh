@@ -5,6 +5,8 @@
 //     loops of the reference (zm_conv.F90:4997-5148 and 5175-5273) are fused into ONE
 //     bottom-up sweep with all per-level state carried in registers, the only per-level
 //     storage being one buoyancy value in shared memory ([level][thread], conflict free);
+//     launches that leave the schedulers mostly idle (second passes, small batches) put the two
+//     loops on two warps instead (k_buoyan_dilute_ws);
 //   * trigger/gather (zm_conv.F90:905-917, 1095-1111) is an order-preserving warp-ballot
 //     compaction per chunk, so ideep/lengath are bit-identical to the serial loop, plus a
 //     device-side worklist so that later kernels run only on convective columns and the host
@@ -15,8 +17,8 @@
 //   * both CAPE passes take their columns from a list bucketed by parcel launch level, most levels
 //     first (k_order_*): a warp lasts as long as its longest lane, and the level count decides that;
 //   * cldprp + closure + q1q2_pjr + scatter + precipitation are one fused per-column kernel;
-//   * zm_conv_evap / momtran are thread-per-column level scans; convtran is a 2-D
-//     (gathered column x constituent) grid.
+//   * zm_conv_evap is a thread-per-column level scan, momtran a warp per convective column,
+//     convtran a block per chunk (zm_transport.cuh).
 // All arithmetic is FP64 with -fmad=false and the portable zm_math.h transcendentals, so
 // results are bit-identical to the CPU oracle built with the same math header.
 #pragma once

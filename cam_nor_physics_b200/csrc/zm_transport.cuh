@@ -1,7 +1,11 @@
-// zm_transport.cuh -- zm_conv_evap, momtran, convtran kernels (HBM-bound level scans).
-//   zm_conv_evap  zm_conv.F90:1712-1972   thread per column, top-down scan, no per-level storage
-//   momtran       zm_conv.F90:2315-2715   thread per gathered column, both wind components
-//   convtran      zm_conv.F90:1976-2311   thread per (gathered column, constituent)
+// zm_transport.cuh -- zm_conv_evap, momtran, convtran kernels and the two neighbours of the path (geopotential_t,
+// convect_diagnostics_calc).
+//   zm_conv_evap  zm_conv.F90:1712-1972   thread per column, top-down scan, no per-level storage; inside the fused
+//                                         step it also applies physics_update and stores the summed tendencies
+//   momtran       zm_conv.F90:2315-2715   warp per gathered column, lane = level, the four wind recurrences in one
+//                                         instruction stream
+//   convtran      zm_conv.F90:1976-2311   block per chunk (k_convtran_c); thread per (gathered column, constituent)
+//                                         as the fallback (k_convtran_t)
 // The chunk-wide loop bounds ktm/kbm (zm_conv.F90:2076-2081, 2449-2454) are reproduced exactly
 // by a tiny per-chunk reduction kernel so the level ranges match the reference bit for bit.
 #pragma once
@@ -177,8 +181,7 @@ struct MomArgs {
   // -> ptend%u, ptend%v) instead of the packed winds(pcols,pver,2) / wind_tends(pcols,pver,2) of zm_conv_intr.F90:814-826,
   // so the step neither packs the winds nor unpacks the tendencies.  NULL: the packed q / dqdt above.
   const double *q_u = nullptr, *q_v = nullptr;
-  double *dq_u = nullptr, *dq_v = nullptr;
-  int prefilled = 0;                     // dq_u, dq_v, seten were zero-filled earlier in the step
+  double *dq_u = nullptr, *dq_v = nullptr;   // (zero-filled, like seten, by the caller: momtran writes convective columns only)
 };
 
 // initialisation of the outgoing fields (zm_conv.F90:2429-2443, 2630)
@@ -199,13 +202,6 @@ __global__ void k_momtran_init(MomArgs a) {
     if (m < 2 && a.domom[m]) a.dqdt[e] = 0.0;
   }
   for (size_t e = tid; e < n2; e += nth) a.seten[e] = 0.0;
-}
-// the same for the fused step (split wind arrays, no history diagnostics): three plain zero-fills, 16 bytes per store
-__global__ void k_momtran_init_split(double2* du, double2* dv, double2* seten, size_t nhalf) {
-  const double2 z = make_double2(0.0, 0.0);
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nhalf; e += (size_t)gridDim.x * blockDim.x) {
-    du[e] = z; dv[e] = z; seten[e] = z;
-  }
 }
 
 // Warp per gathered (convective) column, lane = level.  Everything that is independent from level to level

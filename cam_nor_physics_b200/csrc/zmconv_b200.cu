@@ -631,15 +631,9 @@ int momtran_launch(Workspace& ws, cudaStream_t s, MomArgs a, bool own_arena = tr
     cb = &own;
   }
   a.ktm = cb->ktm; a.kbm = cb->kbm; a.slots = cb->slots; a.count = cb->count;
-  if (a.q_u) {     // fused step: split wind arrays (even length and 16-byte alignment checked by the caller)
-    const size_t n2 = (size_t)ncolpad * pver;
-    if (!a.prefilled) {      // else zero-filled with zm_convr's outputs at the start of the step
-      k_momtran_init_split<<<1184, 256, 0, s>>>((double2*)a.dq_u, (double2*)a.dq_v, (double2*)a.seten, n2 / 2);
-      ++tls_launches;
-    }
-  } else {
-    k_momtran_init<<<592, 256, 0, s>>>(a); ++tls_launches;
-  }
+  // fused step with split wind arrays: dq_u, dq_v and seten were zero-filled with zm_convr's outputs at the start of
+  // the step (k_zero_fill); the packed form initialises its outgoing fields here
+  if (!a.q_u) { k_momtran_init<<<592, 256, 0, s>>>(a); ++tls_launches; }
   const size_t smem_mom = momtran_smem_bytes(pver);
   if (smem_mom > 48 * 1024)
     CK(cudaFuncSetAttribute(k_momtran_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mom));
@@ -1481,7 +1475,7 @@ int conv_tend_impl(Workspace& ws, int nchunks, const int* ncol, const double* t,
     ma.q = winds; ma.mu = mu; ma.md = md; ma.du = du; ma.eu = eu; ma.ed = ed; ma.dp = dp;
     ma.dqdt = wtend; ma.pguall = pgu; ma.pgdall = pgd; ma.icwu = icwu; ma.icwd = icwd; ma.seten = seten;
     ma.dt = ztodt;
-    if (split) { ma.q_u = u; ma.q_v = v; ma.dq_u = ptend_u; ma.dq_v = ptend_v; ma.prefilled = 1; }
+    if (split) { ma.q_u = u; ma.q_v = v; ma.dq_u = ptend_u; ma.dq_v = ptend_v; }
     rc = momtran_launch(ws, s, ma, false, &cb);
     if (rc) return rc;
   }
