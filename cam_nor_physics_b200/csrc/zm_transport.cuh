@@ -245,7 +245,7 @@ k_momtran_t(MomArgs a) {
   double* S = sm_mom + (size_t)wib * M_NARR * ld;
 #define SA(arr, k) S[(arr) * ld + (k)]
 #define QI(m, k) ((((size_t)c * 2 + (m)) * pver + (k) - 1) * pcols + ii)
-#define PAR for (int k = lane + 1; k <= pver; k += 32)
+#define PAR _Pragma("unroll 1") for (int k = lane + 1; k <= pver; k += 32)
   // wind component m of level k: packed (pcols,pver,2) arrays or the split ones of the fused step
   const bool split = a.q_u != nullptr;
   const double* qsrc[2] = {split ? a.q_u : a.q, split ? a.q_v : a.q + (size_t)pver * pcols};
