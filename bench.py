@@ -331,21 +331,36 @@ def main():
         dist.all_gather(allsums, mine)
         if rank == 0:
             equal = []
+            cons_parts = []          # per-shard budget terms, each reduced on rank 0's GPU
             for r in range(world):
                 c0r, nr = shard_of(r, world, args.ncols, args.scaling)
                 if r == 0:
                     ref = mine
+                    dr = dev
                 else:
                     dr = DeviceTend(S.make_chunks(nr, L, 16, p_conv=args.pconv, col0=c0r), ncnst=args.convtran)
                     dr.step()
                     if dr.ncnst:
                         dr.step2()
                     ref = dr.checksums()
+                try:
+                    cons_parts.append(dr.conservation().double().cpu().numpy().copy())
+                except Exception as e:           # informational: never fatal for the bench line
+                    cons_parts.append(repr(e))
+                if r != 0:
                     del dr
                 equal.append(bool(torch.equal(ref, allsums[r])))
             parity = {"ranks_checked": world, "fields": int(mine.numel()), "equal": all(equal), "per_rank": equal,
                       "how": "wrap-around 64-bit sums of the bit patterns of every zm_conv_tend output, rank r's shard "
                              "recomputed on rank 0's GPU"}
+            try:
+                import numpy as np
+                tot = np.sum(np.stack(cons_parts), axis=0)
+                rel = float(np.max(np.abs(tot - cons_h) / np.maximum(np.abs(cons_h), 1e-300)))
+                parity["conservation_allreduce_rel_err"] = rel       # NCCL sum of the ranks' six budget terms against
+                parity["conservation_within_1e-13"] = bool(rel <= 1e-13)   # the sum of the same shards reduced on rank 0
+            except Exception as e:
+                parity["conservation_check_error"] = repr(e)
         barrier()
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------------------
